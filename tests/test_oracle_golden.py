@@ -1,0 +1,189 @@
+"""Pins the CPU oracle (oracle/season_oracle.py) against fixtures produced by the
+UNMODIFIED reference (oracle/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch as t
+
+from conftest import load_golden
+from oracle import barron_loss
+from oracle import season_oracle as so
+
+S = 96
+TOL = dict(rtol=2e-5, atol=2e-6)
+
+
+def T(x):
+    return t.tensor(np.asarray(x))
+
+
+def close(a, b, **kw):
+    tol = dict(TOL)
+    tol.update(kw)
+    a = a.detach().numpy() if isinstance(a, t.Tensor) else np.asarray(a)
+    np.testing.assert_allclose(a, b, **tol)
+
+
+def clone(p):
+    return {k: v.clone() for k, v in p.items()}
+
+
+def test_state_dict_keys(params0):
+    assert len(params0) == 94
+    assert sum(v.numel() for k, v in params0.items() if "running" not in k and "tracked" not in k) == 3195820
+
+
+def test_network_entry_points(params0):
+    g = load_golden("net_eval")
+    X, sun, Time = T(g["X"]), T(g["sun"]), T(g["Time"])
+    with t.no_grad():
+        close(so.pe_encode(X, 10), g["pe10"], rtol=0, atol=0)
+        close(so.pe_encode(sun, 4), g["pe4"], rtol=0, atol=0)
+        close(so.pe_encode(Time[:, :2], 2), g["pe2"], rtol=0, atol=0)
+        fw = so.forward(params0, X, sun, Time)
+        for o, k in zip(fw, ["rho", "col", "vis", "sky", "cls", "adj"]):
+            close(o, g["fw_" + k])
+        fs = so.forward_seperate(params0, X, sun, Time)
+        for o, k in zip(fs, ["rho", "col", "vis", "sky", "cls", "adj"]):
+            close(o, g["fs_" + k])
+        sol = so.forward_solar(params0, X, sun)
+        for o, k in zip(sol, ["rho", "vis", "sky"]):
+            close(o, g["sol_" + k])
+        close(so.forward_sigma_only(params0, X), g["sigma_only"])
+        close(so.time_classes(params0, Time), g["class_only"])
+        close(so.forward_color_only(params0, X), g["color_only"])
+
+
+def test_sampling_bit_exact():
+    g = load_golden("sampling")
+    top, bot = T(g["top"]), T(g["bot"])
+    p, d = so.sample_pt_coarse(top, bot, S, True)
+    assert np.array_equal(p.numpy(), g["pts_eval"]) and np.array_equal(d.numpy(), g["del_eval"])
+    p, d = so.sample_pt_coarse(top, bot, S, True, include_end_pt=True)
+    assert np.array_equal(p.numpy(), g["pts_end"]) and np.array_equal(d.numpy(), g["del_end"])
+    assert np.array_equal(so.invalid_pts(p).numpy(), g["bad"])
+    assert g["bad"].any() and not g["bad"].all()
+    close(so.get_PV(T(g["rho"]), d), g["pv"], rtol=0, atol=0)
+    p, d = so.sample_pt_coarse(top, bot, S, False, jitter=T(g["jitter"]))
+    assert np.array_equal(p.numpy(), g["pts_train"]) and np.array_equal(d.numpy(), g["del_train"])
+
+
+KEYS = ["Rendered_Col", "PE", "PV", "PS", "Solar_Vis", "Sky_Col", "Classes", "Adjust", "Rho", "Col", "deltas",
+        "sample_pts", "Albedo_Color"]
+
+
+def _data(g):
+    return {k[3:]: T(v) for k, v in g.items() if k.startswith("in_")}
+
+
+def test_engine_eval(params0):
+    g = load_golden("engine_eval")
+    with t.no_grad():
+        R = so.engine_eval(so.default_args(), _data(g), params0, 0, False)
+    for k in KEYS:
+        close(R[k], g[k])
+
+
+def test_engine_train_forward_batchnorm(params0):
+    g = load_golden("engine_train_fwd")
+    p = clone(params0)
+    with t.no_grad():
+        R = so.engine_eval(so.default_args(), _data(g), p, 0, True, jitter=T(g["jitter"]))
+    assert np.array_equal(R["sample_pts"].numpy(), g["sample_pts"])
+    for k in KEYS:
+        close(R[k], g[k], rtol=2e-4, atol=2e-5)
+    close(p["G_NeRF_net.fc2.norm.running_mean"], g["fc2_rm"], rtol=1e-4, atol=1e-6)
+    close(p["G_NeRF_net.fc2.norm.running_var"], g["fc2_rv"], rtol=1e-4, atol=1e-6)
+    close(p["G_NeRF_net.fc9.norm.running_mean"], g["fc9_rm"], rtol=1e-4, atol=1e-6)
+    close(p["G_NeRF_net.fc9.norm.running_var"], g["fc9_rv"], rtol=1e-4, atol=1e-6)
+
+
+def _ada(use_prior):
+    mk = barron_loss.AdaptiveLossFunction
+    a0 = mk(3, t.float32, "cpu", alpha_hi=2.99, alpha_init=2.0, scale_init=0.03, scale_lo=0.01)
+    if not use_prior:
+        return a0
+    return [a0, mk(1, t.float32, "cpu", alpha_hi=2.99, alpha_init=2.0, scale_init=0.5, scale_lo=0.05)]
+
+
+@pytest.mark.parametrize("name,kw", [("loss_barron", {}), ("loss_mse", {"mse": True}),
+                                     ("loss_prior", {"use_prior": True}), ("loss_type2", {"type2": True})])
+def test_get_loss_and_gradients(params0, name, kw):
+    g = load_golden(name)
+    use_prior, mse, type2 = kw.get("use_prior", False), kw.get("mse", False), kw.get("type2", False)
+    args = so.default_args(Use_MSE_loss=mse, Solar_Type_2=type2)
+    p = clone(params0)
+    leaves = {}
+    for k, v in p.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+            leaves[k] = v
+    ada = None if mse else _ada(use_prior)
+    solar = (T(g["s_top"]), T(g["s_bot"]), T(g["s_sun"]), T(g["s_time"]))
+    L, _ = so.get_loss(args, _data(g), p, 30, True, ada, jitter=T(g["jitter"]), solar=solar,
+                       solar_jitter=T(g["solar_jitter"]), use_prior=use_prior, n_steps=100,
+                       hm=g.get("hm"))
+    for k in L:
+        close(t.as_tensor(L[k][0]), g["loss_" + k], rtol=3e-4, atol=1e-6)
+        assert abs(float(L[k][1]) - float(g["w_" + k])) <= 1e-5 * abs(float(g["w_" + k]))
+    tot = so.total_loss(L)
+    close(tot, g["total"], rtol=3e-4)
+    tot.backward()
+    norms = dict(zip(g["grad_names"].tolist(), g["grad_norms"].tolist()))
+    for k, v in leaves.items():
+        n = 0.0 if v.grad is None else float(v.grad.norm())
+        # biases feeding a BatchNorm have an analytically zero gradient: absolute floor for that noise
+        assert abs(n - norms[k]) <= 2e-3 * norms[k] + 1e-4, (k, n, norms[k])
+    for k in g:
+        if k.startswith("grad_") and k not in ("grad_names", "grad_norms"):
+            ref = g[k]
+            close(leaves[k[5:]].grad, ref, rtol=5e-3, atol=max(2e-3 * float(np.abs(ref).max()), 3e-5))
+    # unused heads get no gradient
+    for k in ["adjust_rho.weight", "adjust_solar_vis.weight", "adjust_sky_col.weight"]:
+        assert norms[k] == 0.0
+    close(p["G_NeRF_net.fc2.norm.running_mean"], g["fc2_rm"], rtol=1e-4, atol=1e-6)
+    close(p["G_NeRF_net.fc2.norm.running_var"], g["fc2_rv"], rtol=1e-4, atol=1e-6)
+    assert int(p["G_NeRF_net.fc2.norm.num_batches_tracked"]) == int(g["fc2_nbt"]) == 2
+
+
+def test_cli_component_render(params0):
+    g = load_golden("cli_render")
+    W2L = so.oma_w2l_h()
+    D = so.component_render_by_dir(params0, [80, 0], [45, 135], 184 / 365, (5, 6, S), so.OMA_W2C, W2L,
+                                   include_exact_solar=False)
+    for k in ["World_Points", "Deltas"]:
+        assert np.array_equal(D[k].astype(np.float32), g["d_" + k]), k
+    for k in ["Rho", "Base_Col", "Est_Solar_Vis", "Sky_Col", "Output_class", "Adjust_col"]:
+        close(D[k], g["d_" + k])
+    assert np.array_equal(D["Image_Points"], g["d_Image_Points"])
+    imgs = so.get_imgs_from_img_dict(D, (5, 6, S))
+    for k in ["Base_Img", "Season_Adj_Img", "Shadow_Adjust", "Shadow_Mask", "Raw_Shadow_Mask", "Sky_Col",
+              "Time_Class"]:
+        close(imgs[k], g[k], rtol=1e-4, atol=1e-5)
+    close(np.array(imgs["Extreme_Imgs"]), g["Extreme_Imgs"], rtol=1e-4, atol=1e-5)
+    sweep = so.get_imgs_from_img_dict_t_step(D, (5, 6, S), g["class_vecs"].astype(np.float64))
+    close(sweep, g["sweep"], rtol=1e-4, atol=1e-5)
+
+
+def test_cli_exact_shadow_march(params0):
+    g = load_golden("cli_render_exact")
+    D = so.component_render_by_dir(params0, [70, 30], [35, 200], 0.25, (2, 3, S), so.OMA_W2C, so.oma_w2l_h(),
+                                   include_exact_solar=True)
+    close(D["Exact_Solar"], g["d_Exact_Solar"], rtol=1e-4, atol=1e-6)
+    imgs = so.get_imgs_from_img_dict(D, (2, 3, S))
+    for k in ["Season_Adj_Img", "Shadow_Adjust_Exact", "Shadow_Mask_Exact", "Raw_Shadow_Mask_Exact"]:
+        close(imgs[k], g[k], rtol=1e-4, atol=1e-5)
+
+
+def test_engine_exact_solar(params0):
+    g = load_golden("quick_run")
+    with t.no_grad():
+        R = so.eval_exact_solar(so.default_args(), _data(g), params0)
+    close(R["Solar_Vis"], g["ex_Solar_Vis"], rtol=1e-4, atol=1e-6)
+    close(R["Est_Solar_Vis"], g["ex_Est_Solar_Vis"])
+    close(R["Rendered_Col"], g["ex_Rendered_Col"], rtol=1e-4, atol=1e-6)
+
+
+def test_geometry():
+    g = load_golden("geometry")
+    for a, v in zip(g["ang"], g["vecs"]):
+        np.testing.assert_allclose(so.world_angle_2_local_vec(a[0], a[1], g["W2C"], g["W2L_H"]), v, rtol=1e-12)
