@@ -1,0 +1,116 @@
+/* season_nerf_b200 -- C ABI of the B200 (sm_100a) Season-NeRF render/train hot path.
+ *
+ * The upstream reference (EnterpriseCV-6/Season-NeRF) is pure Python/PyTorch and has no FFI; the
+ * boundary it exposes for this path is its Python object API.  This header is
+ * the C ABI that the drop-in Python classes in season_nerf_b200/ bind with ctypes: plain device
+ * pointers, sizes and a cudaStream_t passed as void*.  Every entry point cites the reference
+ * code (file:line, relative to the upstream repo root) whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - matrices are row-major with an explicit leading dimension (elements);
+ *   - dtype codes: SNB_F32 = 0, SNB_BF16 = 1;
+ *   - return value 0 = success, >0 = cudaError_t, <0 = SNB_ERR_*; no entry point synchronises;
+ *   - N = rays, S = samples per ray, M = N*S sample points.
+ */
+#ifndef SEASON_NERF_B200_H
+#define SEASON_NERF_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNB_F32 0
+#define SNB_BF16 1
+#define SNB_F64 2
+
+/* library / device info ------------------------------------------------------------------- */
+int snb_version(void);
+/* number of kernels this library has launched since load (bench.py "gpu_launches") */
+long long snb_launch_count(void);
+const char* snb_error_string(int code);
+
+/* ---- ray sampling: misc.py:234-247 sample_pt_coarse + misc.py:249-261 zero_invalid_pts ----
+ * pts[n,s,:] = top[n]*(1-ts[s]) + bot[n]*ts[s]   (two rounded products, one rounded sum: bit-exact)
+ * deltas[n,s] = ||top[n]-bot[n]||_2 / S           (0 where zero_oob and the point leaves [-1,1]^3)
+ * ts is the length-S parameter vector the host builds exactly like the reference
+ * (linspace (+ one shared jitter vector in train mode)). pts may be NULL. */
+int snb_sample_rays(const float* top, const float* bot, const float* ts, int N, int S, int zero_oob,
+                    float* pts, float* deltas, void* stream);
+
+/* ---- shadow-march ray construction: mg_Img_Eval.py:57-64 / Eval_Tools_2.py:255-258 ----------
+ * new_top = float32( double(p) + ((1-p_z)/sun_z) * double(sun) ) (float64 arithmetic as the reference's
+ * numpy promotion does when f64 != 0; float32 arithmetic when f64 == 0, the engine variant). */
+int snb_solar_tops(const float* pts, long long M, const double* sun3_host, int f64, float* tops, void* stream);
+
+/* ---- compositing (engine convention): Eval_Tools_2.py:13-16 get_PV and :187-215 ------------
+ * deltas: [N,S].  col: [N,S,3] activated colour.  vis: [N,S].  sky: [N,3] (sky_per_sample=0) or [N,S,3].
+ * classic = args.Solar_Type_2.  Outputs PV,PE,PS [N,S] (each may be NULL), albedo [N,3], rendered [N,3],
+ * vis_sum [N] = sum_s vis*PS (may be NULL). */
+int snb_composite_fwd(const float* rho, const float* deltas, const float* col, const float* vis, const float* sky,
+                      int sky_per_sample, int N, int S, int classic, float* PV, float* PE, float* PS,
+                      float* albedo, float* rendered, float* vis_sum, void* stream);
+/* backward of the above.  Incoming gradients (any may be NULL): d_rendered[N,3], d_albedo[N,3], dPE,dPV,dPS [N,S].
+ * Outgoing: d_rho[N,S], d_col[N,S,3], d_sky (same layout as sky), d_vis[N,S] (written only when classic;
+ * vis is detached otherwise, Eval_Tools_2.py:214). */
+int snb_composite_bwd(const float* rho, const float* deltas, const float* col, const float* vis, const float* sky,
+                      int sky_per_sample, int N, int S, int classic, const float* d_rendered, const float* d_albedo,
+                      const float* dPE, const float* dPV, const float* dPS, float* d_rho, float* d_col, float* d_sky,
+                      float* d_vis, void* stream);
+
+/* transmittance of the shadow march: out[m] = exp(-sum_{k<S-1} rho[m,k]*deltas[m,k])  (mg_Img_Eval.py:68-70) */
+int snb_march_transmittance(const float* rho, const float* deltas, long long M, int S, float* out, void* stream);
+
+/* ---- CLI compositing: mg_Img_Eval.py:123-190 get_imgs_from_Img_Dict, float64 like the reference ------
+ * rho,deltas,vis [N,S]; base [N,S,3] raw logits; adj [N,S,C,3] (element type in_dtype: SNB_F32 network outputs
+ * promoted exactly, or SNB_F64); cls [C] float64.
+ * base_img, season_img [N,3]; extreme [C,N,3]; raw_shadow [N] (all float64). exact_vis/raw_shadow_exact optional. */
+int snb_cli_composite(const void* rho, const void* deltas, const void* base, const void* vis, const void* adj,
+                      const double* cls, const void* exact_vis, int in_dtype, int N, int S, int C, double* base_img,
+                      double* season_img, double* extreme, double* raw_shadow, double* raw_shadow_exact, void* stream);
+/* year sweep: mg_Img_Eval.py:192-228 get_imgs_from_Img_Dict_t_step, fused over T class vectors.
+ * cls [T,C] -> out [T,N,3] (float64), out = season colour only (host multiplies the shadow mask). */
+int snb_year_sweep(const void* rho, const void* deltas, const void* base, const void* adj, const double* cls,
+                   int in_dtype, int N, int S, int C, int T, double* out, void* stream);
+
+/* ---- positional encoding: misc.py:105-139 PE_Encode (extended) ------------------------------
+ * out[m, col0 + ...] = [x (D), per dim: cos(k_j x) j<n, sin(k_j x) j<n], k_j = 2^j * fl32(pi/2);
+ * width D*(2n+1), zero padded up to pad_to columns.  x: [M,D] float32, ldx elements. out dtype f32/bf16. */
+int snb_pe_encode(const float* x, int ldx, long long M, int D, int n_freq, void* out, int out_dtype, int ldo,
+                  int col0, int pad_to, void* stream);
+/* d_x += d_enc * d enc / d x is never needed: inputs carry no gradient in the reference. */
+
+/* ---- dense layers -----------------------------------------------------------------------------
+ * C[M,N] = alpha * (A[M,K] . B[N,K]^T + bias[N]) (+ C if accumulate).  "TN" GEMM: both operands K-contiguous.
+ * a_t / b_t select the transposed ("MN-major") operand forms used by the weight gradient:
+ *   a_t=1: A is stored [K,M] (lda = row stride of that storage);  b_t=1: B is stored [K,N].
+ * dtype SNB_F32 : CUDA-core fp32 validation path.  SNB_BF16: tcgen05/TMEM tensor-core path, fp32 accumulate.
+ * out_dtype may differ from dtype (bf16 operands -> f32 result for weight gradients).
+ * Replaces nn.Linear inside misc.py:188-189 and its autograd backward. */
+int snb_gemm(const void* A, int lda, int a_t, const void* B, int ldb, int b_t, void* C, int ldc, const float* bias,
+             float alpha, int accumulate, long long M, int N, int K, int dtype, int out_dtype, void* stream);
+
+/* column statistics for train-mode BatchNorm1d (misc.py:169-170): sum[n], sumsq[n] over M rows (float64 out). */
+int snb_col_stats(const void* Z, int dtype, int ldz, long long M, int N, double* sum, double* sumsq, void* stream);
+
+/* Y = sin(a[n]*Z + c[n])  (a,c fold BatchNorm / identity).  Y dtype = dtype.  misc.py:189. */
+int snb_sine_fwd(const void* Z, int ldz, const float* a, const float* c, void* Y, int ldy, long long M, int N,
+                 int dtype, void* stream);
+/* backward of sin(BN(Z)):  g = dY*cos(a Z + c).
+ * pass 1 (reduce): sg[n] = sum_m g, sgx[n] = sum_m g*xhat, xhat = (Z-mean)*invstd   (float64 out)
+ * pass 2 (apply):  dZ = a*(g - k1[n] - xhat*k2[n]); k1,k2 = sg/M, sgx/M in train-mode BN, 0 otherwise. */
+int snb_sine_bwd_reduce(const void* dY, int ldd, const void* Z, int ldz, const float* a, const float* c,
+                        const float* mean, const float* invstd, long long M, int N, int dtype, double* sg,
+                        double* sgx, void* stream);
+int snb_sine_bwd_apply(const void* dY, int ldd, const void* Z, int ldz, const float* a, const float* c,
+                       const float* mean, const float* invstd, const float* k1, const float* k2, void* dZ, int ldo,
+                       long long M, int N, int dtype, void* stream);
+
+/* dtype conversion with leading dimensions (f32 <-> bf16), used to stage operands */
+int snb_convert(const void* src, int src_dtype, int lds, void* dst, int dst_dtype, int ldd, long long M, int N,
+                void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

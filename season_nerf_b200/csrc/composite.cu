@@ -1,0 +1,447 @@
+// Alpha-compositing with a transmittance scan: forward, fused backward, shadow-march transmittance,
+// float64 CLI composite and the fused year sweep.  One warp per ray; lanes stride over the samples
+// so that every load/store of a warp covers one contiguous span of the ray's record; the
+// exclusive transmittance prefix is a warp-shuffle scan carried across 32-sample chunks.
+//   reference: Eval_Tools_2.py:13-16 (get_PV), :187-215 (eval), mg_Img_Eval.py:68-70, :123-228.
+#include "common.cuh"
+#include "api.h"
+
+namespace snb {
+
+constexpr int kMaxChunks = 8;  // S <= 256 for the register-resident backward
+
+struct RayAcc {
+  float a0, a1, a2;  // sum PS*col
+  float r0, r1, r2;  // classic: sum PS*col*(vis+(1-vis)*sky)
+  float vs;          // sum vis*PS
+  float k0, k1, k2;  // sum_s sky (per-sample sky)
+};
+
+template <bool kClassic, bool kSkyPerSample>
+__global__ void __launch_bounds__(256)
+composite_fwd_kernel(const float* __restrict__ rho, const float* __restrict__ deltas, const float* __restrict__ col,
+                     const float* __restrict__ vis, const float* __restrict__ sky, int N, int S,
+                     float* __restrict__ PV, float* __restrict__ PE, float* __restrict__ PS,
+                     float* __restrict__ albedo, float* __restrict__ rendered, float* __restrict__ vis_sum) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int n = blockIdx.x * wpb + (threadIdx.x >> 5); n < N; n += gridDim.x * wpb) {
+    const long long base = (long long)n * S;
+    float carry = 0.f;
+    RayAcc acc = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    float ks0 = 0, ks1 = 0, ks2 = 0;
+    if (!kSkyPerSample) {
+      ks0 = __ldg(sky + 3 * n), ks1 = __ldg(sky + 3 * n + 1), ks2 = __ldg(sky + 3 * n + 2);
+    }
+    for (int s0 = 0; s0 < S; s0 += 32) {
+      const int s = s0 + lane;
+      const bool ok = s < S;
+      const long long o = base + s;
+      const float y = ok ? __ldg(rho + o) * __ldg(deltas + o) : 0.f;
+      const float incl = warp_scan_incl(y, lane);
+      float prev = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (lane == 0) prev = 0.f;
+      const float pv = expf(-(carry + prev));
+      const float pe = 1.f - expf(-y);
+      const float ps = pv * pe;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+      if (ok) {
+        if (PV) PV[o] = pv;
+        if (PE) PE[o] = pe;
+        if (PS) PS[o] = ps;
+        const float c0 = __ldg(col + 3 * o), c1 = __ldg(col + 3 * o + 1), c2 = __ldg(col + 3 * o + 2);
+        const float v = __ldg(vis + o);
+        acc.a0 += ps * c0, acc.a1 += ps * c1, acc.a2 += ps * c2;
+        acc.vs += v * ps;
+        float q0 = ks0, q1 = ks1, q2 = ks2;
+        if (kSkyPerSample) {
+          q0 = __ldg(sky + 3 * o), q1 = __ldg(sky + 3 * o + 1), q2 = __ldg(sky + 3 * o + 2);
+          acc.k0 += q0, acc.k1 += q1, acc.k2 += q2;
+        }
+        if (kClassic) {
+          acc.r0 += ps * c0 * (v + (1.f - v) * q0);
+          acc.r1 += ps * c1 * (v + (1.f - v) * q1);
+          acc.r2 += ps * c2 * (v + (1.f - v) * q2);
+        }
+      }
+    }
+    acc.a0 = warp_sum(acc.a0), acc.a1 = warp_sum(acc.a1), acc.a2 = warp_sum(acc.a2);
+    acc.vs = warp_sum(acc.vs);
+    if (kClassic) acc.r0 = warp_sum(acc.r0), acc.r1 = warp_sum(acc.r1), acc.r2 = warp_sum(acc.r2);
+    if (kSkyPerSample) {
+      ks0 = warp_sum(acc.k0) / (float)S, ks1 = warp_sum(acc.k1) / (float)S, ks2 = warp_sum(acc.k2) / (float)S;
+    }
+    if (lane == 0) {
+      albedo[3 * n] = acc.a0, albedo[3 * n + 1] = acc.a1, albedo[3 * n + 2] = acc.a2;
+      if (vis_sum) vis_sum[n] = acc.vs;
+      if (kClassic) {
+        rendered[3 * n] = acc.r0, rendered[3 * n + 1] = acc.r1, rendered[3 * n + 2] = acc.r2;
+      } else {
+        const float sv3 = sigmoidf_((acc.vs - .2f) * 30.f);  // Eval_Tools_2.py:214
+        rendered[3 * n] = acc.a0 * (sv3 + (1.f - sv3) * ks0);
+        rendered[3 * n + 1] = acc.a1 * (sv3 + (1.f - sv3) * ks1);
+        rendered[3 * n + 2] = acc.a2 * (sv3 + (1.f - sv3) * ks2);
+      }
+    }
+  }
+}
+
+// Fused backward.  Sweep 1 (forward order) rebuilds PV/PE per sample into registers and the per-ray sums;
+// sweep 2 (reverse order) runs the suffix scan  sum_{t>s} dPV_t*PV_t  with shuffles and emits all gradients.
+template <bool kClassic, bool kSkyPerSample, int kChunks>
+__global__ void __launch_bounds__(256)
+composite_bwd_kernel(const float* __restrict__ rho, const float* __restrict__ deltas, const float* __restrict__ col,
+                     const float* __restrict__ vis, const float* __restrict__ sky, int N, int S,
+                     const float* __restrict__ d_rendered, const float* __restrict__ d_albedo,
+                     const float* __restrict__ dPE, const float* __restrict__ dPV, const float* __restrict__ dPS,
+                     float* __restrict__ d_rho, float* __restrict__ d_col, float* __restrict__ d_sky,
+                     float* __restrict__ d_vis) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int n = blockIdx.x * wpb + (threadIdx.x >> 5); n < N; n += gridDim.x * wpb) {
+    const long long base = (long long)n * S;
+    float pv[kChunks], pe[kChunks];
+    float carry = 0.f, a0 = 0, a1 = 0, a2 = 0, vs = 0, k0 = 0, k1 = 0, k2 = 0;
+    if (!kSkyPerSample) k0 = __ldg(sky + 3 * n), k1 = __ldg(sky + 3 * n + 1), k2 = __ldg(sky + 3 * n + 2);
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      const int s = c * 32 + lane;
+      const bool ok = s < S;
+      const long long o = base + s;
+      const float y = ok ? __ldg(rho + o) * __ldg(deltas + o) : 0.f;
+      const float incl = warp_scan_incl(y, lane);
+      float prev = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (lane == 0) prev = 0.f;
+      pv[c] = expf(-(carry + prev));
+      pe[c] = 1.f - expf(-y);
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+      if (ok && !kClassic) {
+        const float ps = pv[c] * pe[c];
+        a0 += ps * __ldg(col + 3 * o), a1 += ps * __ldg(col + 3 * o + 1), a2 += ps * __ldg(col + 3 * o + 2);
+        vs += __ldg(vis + o) * ps;
+        if (kSkyPerSample) k0 += __ldg(sky + 3 * o), k1 += __ldg(sky + 3 * o + 1), k2 += __ldg(sky + 3 * o + 2);
+      }
+    }
+    float g0 = d_rendered ? __ldg(d_rendered + 3 * n) : 0.f, g1 = d_rendered ? __ldg(d_rendered + 3 * n + 1) : 0.f,
+          g2 = d_rendered ? __ldg(d_rendered + 3 * n + 2) : 0.f;
+    const float e0 = d_albedo ? __ldg(d_albedo + 3 * n) : 0.f, e1 = d_albedo ? __ldg(d_albedo + 3 * n + 1) : 0.f,
+                e2 = d_albedo ? __ldg(d_albedo + 3 * n + 2) : 0.f;
+    float dA0 = e0, dA1 = e1, dA2 = e2;  // gradient w.r.t. the albedo sum
+    float dk0 = 0, dk1 = 0, dk2 = 0;     // gradient w.r.t. the mean sky colour (non-classic)
+    if (!kClassic) {
+      a0 = warp_sum(a0), a1 = warp_sum(a1), a2 = warp_sum(a2), vs = warp_sum(vs);
+      if (kSkyPerSample) k0 = warp_sum(k0) / (float)S, k1 = warp_sum(k1) / (float)S, k2 = warp_sum(k2) / (float)S;
+      const float sv3 = sigmoidf_((vs - .2f) * 30.f);
+      dA0 += g0 * (sv3 + (1.f - sv3) * k0), dA1 += g1 * (sv3 + (1.f - sv3) * k1), dA2 += g2 * (sv3 + (1.f - sv3) * k2);
+      dk0 = g0 * a0 * (1.f - sv3), dk1 = g1 * a1 * (1.f - sv3), dk2 = g2 * a2 * (1.f - sv3);
+      if (!kSkyPerSample && lane == 0 && d_sky) d_sky[3 * n] = dk0, d_sky[3 * n + 1] = dk1, d_sky[3 * n + 2] = dk2;
+      if (kSkyPerSample) dk0 /= (float)S, dk1 /= (float)S, dk2 /= (float)S;
+    }
+    float suffix = 0.f;                    // sum over later chunks of dPV_t*PV_t
+    float dsk0 = 0, dsk1 = 0, dsk2 = 0;    // classic + per-ray sky accumulation
+#pragma unroll
+    for (int c = kChunks - 1; c >= 0; --c) {
+      const int s = c * 32 + lane;
+      const bool ok = s < S;
+      const long long o = base + s;
+      float q = 0.f, dpe_tot = 0.f;
+      if (ok) {
+        const float c0 = __ldg(col + 3 * o), c1 = __ldg(col + 3 * o + 1), c2 = __ldg(col + 3 * o + 2);
+        const float ps = pv[c] * pe[c];
+        float dps = dPS ? __ldg(dPS + o) : 0.f;
+        if (kClassic) {
+          const float v = __ldg(vis + o);
+          float q0 = k0, q1 = k1, q2 = k2;
+          if (kSkyPerSample) q0 = __ldg(sky + 3 * o), q1 = __ldg(sky + 3 * o + 1), q2 = __ldg(sky + 3 * o + 2);
+          const float sh0 = v + (1.f - v) * q0, sh1 = v + (1.f - v) * q1, sh2 = v + (1.f - v) * q2;
+          dps += g0 * c0 * sh0 + g1 * c1 * sh1 + g2 * c2 * sh2 + e0 * c0 + e1 * c1 + e2 * c2;
+          d_col[3 * o] = ps * (g0 * sh0 + e0), d_col[3 * o + 1] = ps * (g1 * sh1 + e1), d_col[3 * o + 2] = ps * (g2 * sh2 + e2);
+          if (d_vis) d_vis[o] = ps * (g0 * c0 * (1.f - q0) + g1 * c1 * (1.f - q1) + g2 * c2 * (1.f - q2));
+          const float t0 = g0 * ps * c0 * (1.f - v), t1 = g1 * ps * c1 * (1.f - v), t2 = g2 * ps * c2 * (1.f - v);
+          if (kSkyPerSample) {
+            if (d_sky) d_sky[3 * o] = t0, d_sky[3 * o + 1] = t1, d_sky[3 * o + 2] = t2;
+          } else {
+            dsk0 += t0, dsk1 += t1, dsk2 += t2;
+          }
+        } else {
+          dps += dA0 * c0 + dA1 * c1 + dA2 * c2;
+          d_col[3 * o] = ps * dA0, d_col[3 * o + 1] = ps * dA1, d_col[3 * o + 2] = ps * dA2;
+          if (kSkyPerSample && d_sky) d_sky[3 * o] = dk0, d_sky[3 * o + 1] = dk1, d_sky[3 * o + 2] = dk2;
+        }
+        dpe_tot = dps * pv[c] + (dPE ? __ldg(dPE + o) : 0.f);
+        const float dpv_tot = dps * pe[c] + (dPV ? __ldg(dPV + o) : 0.f);
+        q = dpv_tot * pv[c];
+      }
+      // exclusive suffix sum of q over lanes (reverse scan) + later chunks
+      float incl = q;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const float t = __shfl_down_sync(0xffffffffu, incl, off);
+        if (lane + off < 32) incl += t;
+      }
+      const float excl = incl - q + suffix;
+      suffix += __shfl_sync(0xffffffffu, incl, 0);
+      if (ok) {
+        const float dy = dpe_tot * (1.f - pe[c]) - excl;
+        d_rho[o] = dy * __ldg(deltas + o);
+      }
+    }
+    if (kClassic && !kSkyPerSample && d_sky) {
+      dsk0 = warp_sum(dsk0), dsk1 = warp_sum(dsk1), dsk2 = warp_sum(dsk2);
+      if (lane == 0) d_sky[3 * n] = dsk0, d_sky[3 * n + 1] = dsk1, d_sky[3 * n + 2] = dsk2;
+    }
+  }
+}
+
+// out[m] = exp(-sum_{k<S-1} rho[m,k]*deltas[m,k])   (mg_Img_Eval.py:68-70)
+__global__ void __launch_bounds__(256) march_transmittance_kernel(const float* __restrict__ rho,
+                                                                  const float* __restrict__ deltas, long long M, int S,
+                                                                  float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (long long m = blockIdx.x * (long long)wpb + (threadIdx.x >> 5); m < M; m += (long long)gridDim.x * wpb) {
+    float acc = 0.f;
+    for (int s = lane; s < S - 1; s += 32) acc += __ldg(rho + m * S + s) * __ldg(deltas + m * S + s);
+    acc = warp_sum(acc);
+    if (lane == 0) out[m] = expf(-acc);
+  }
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double sigd(double x) { return 1.0 / (1.0 + exp(-x)); }
+
+// float64 exclusive-prefix transmittance * emission for one chunk of 32 samples
+__device__ __forceinline__ double ps_chunk_d(double y, int lane, double& carry) {
+  double incl = y;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  double prev = __shfl_up_sync(0xffffffffu, incl, 1);
+  if (lane == 0) prev = 0.0;
+  const double ps = exp(-(carry + prev)) * (1.0 - exp(-y));
+  carry += __shfl_sync(0xffffffffu, incl, 31);
+  return ps;
+}
+
+// mg_Img_Eval.py:123-190 in float64: Base_Img, Season_Adj_Img, per-class extreme images, raw shadow sums.
+template <typename T>
+__global__ void __launch_bounds__(128)
+cli_composite_kernel(const T* __restrict__ rho, const T* __restrict__ deltas, const T* __restrict__ base,
+                     const T* __restrict__ vis, const T* __restrict__ adj, const double* __restrict__ cls,
+                     const T* __restrict__ exact_vis, int N, int S, int C, double* __restrict__ base_img,
+                     double* __restrict__ season_img, double* __restrict__ extreme, double* __restrict__ raw_shadow,
+                     double* __restrict__ raw_shadow_exact) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int n = blockIdx.x * wpb + (threadIdx.x >> 5); n < N; n += gridDim.x * wpb) {
+    double carry = 0.0, b[3] = {0, 0, 0}, se[3] = {0, 0, 0}, sh = 0, she = 0;
+    double ex[8][3];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) ex[c][0] = ex[c][1] = ex[c][2] = 0;
+    for (int s0 = 0; s0 < S; s0 += 32) {
+      const int s = s0 + lane;
+      const bool ok = s < S;
+      const long long o = (long long)n * S + s;
+      const double ps = ps_chunk_d(ok ? (double)rho[o] * (double)deltas[o] : 0.0, lane, carry);
+      if (ok) {
+        sh += ps * (double)vis[o];
+        if (exact_vis) she += ps * (double)exact_vis[o];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const double bc = (double)base[3 * o + d];
+          b[d] += ps * sigd(bc);
+          double mix = 0;
+          for (int c = 0; c < C; ++c) {
+            const double a = (double)adj[(o * C + c) * 3 + d];
+            mix += cls[c] * a;
+            if (c < 8) ex[c][d] += ps * sigd(bc + a);
+          }
+          se[d] += ps * sigd(bc + mix);
+        }
+      }
+    }
+    sh = warp_sum_d(sh);
+    if (exact_vis) she = warp_sum_d(she);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) b[d] = warp_sum_d(b[d]), se[d] = warp_sum_d(se[d]);
+    for (int c = 0; c < C && c < 8; ++c)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) ex[c][d] = warp_sum_d(ex[c][d]);
+    if (lane == 0) {
+      raw_shadow[n] = sh;
+      if (exact_vis && raw_shadow_exact) raw_shadow_exact[n] = she;
+      for (int d = 0; d < 3; ++d) base_img[3 * n + d] = b[d], season_img[3 * n + d] = se[d];
+      for (int c = 0; c < C && c < 8; ++c)
+        for (int d = 0; d < 3; ++d) extreme[((long long)c * N + n) * 3 + d] = ex[c][d];
+    }
+  }
+}
+
+// mg_Img_Eval.py:192-228 fused over the T class vectors: PS, base and adjust are read ONCE per ray and kept
+// in registers (3 samples per lane at S=96); the T recombinations run out of registers.
+template <typename TI, int kChunks>
+__global__ void __launch_bounds__(128)
+year_sweep_kernel(const TI* __restrict__ rho, const TI* __restrict__ deltas, const TI* __restrict__ base,
+                  const TI* __restrict__ adj, const double* __restrict__ cls, int N, int S, int C, int T,
+                  double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int n = blockIdx.x * wpb + (threadIdx.x >> 5); n < N; n += gridDim.x * wpb) {
+    double carry = 0.0;
+    double ps[kChunks], bc[kChunks][3], ad[kChunks][4][3];
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      const int s = c * 32 + lane;
+      const bool ok = s < S;
+      const long long o = (long long)n * S + s;
+      ps[c] = ps_chunk_d(ok ? (double)rho[o] * (double)deltas[o] : 0.0, lane, carry);
+      if (!ok) ps[c] = 0.0;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        bc[c][d] = ok ? (double)base[3 * o + d] : 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ad[c][k][d] = (ok && k < C) ? (double)adj[(o * C + k) * 3 + d] : 0.0;
+      }
+    }
+    for (int t = 0; t < T; ++t) {
+      double w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) w[k] = k < C ? cls[t * C + k] : 0.0;
+      double acc[3] = {0, 0, 0};
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const double mix = w[0] * ad[c][0][d] + w[1] * ad[c][1][d] + w[2] * ad[c][2][d] + w[3] * ad[c][3][d];
+          acc[d] += ps[c] * sigd(bc[c][d] + mix);
+        }
+#pragma unroll
+      for (int d = 0; d < 3; ++d) acc[d] = warp_sum_d(acc[d]);
+      if (lane == 0)
+        for (int d = 0; d < 3; ++d) out[((long long)t * N + n) * 3 + d] = acc[d];
+    }
+  }
+}
+
+}  // namespace snb
+
+using namespace snb;
+
+extern "C" int snb_composite_fwd(const float* rho, const float* deltas, const float* col, const float* vis,
+                                 const float* sky, int sky_per_sample, int N, int S, int classic, float* PV, float* PE,
+                                 float* PS, float* albedo, float* rendered, float* vis_sum, void* stream) {
+  SNB_CHECK_ARG(rho && deltas && col && vis && sky && albedo && rendered && N >= 0 && S > 0);
+  if (N == 0) return SNB_OK;
+  const int grid = grid_for(N, 8, 16);
+  cudaStream_t st = (cudaStream_t)stream;
+#define SNB_FWD(C_, K_) \
+  composite_fwd_kernel<C_, K_><<<grid, 256, 0, st>>>(rho, deltas, col, vis, sky, N, S, PV, PE, PS, albedo, rendered, vis_sum)
+  if (classic) { if (sky_per_sample) SNB_FWD(true, true); else SNB_FWD(true, false); }
+  else { if (sky_per_sample) SNB_FWD(false, true); else SNB_FWD(false, false); }
+#undef SNB_FWD
+  count_launch();
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+template <bool C_, bool K_>
+static int launch_bwd(int chunks, int grid, cudaStream_t st, const float* rho, const float* deltas, const float* col,
+                      const float* vis, const float* sky, int N, int S, const float* d_rendered, const float* d_albedo,
+                      const float* dPE, const float* dPV, const float* dPS, float* d_rho, float* d_col, float* d_sky,
+                      float* d_vis) {
+#define SNB_BWD(CH) \
+  composite_bwd_kernel<C_, K_, CH><<<grid, 256, 0, st>>>(rho, deltas, col, vis, sky, N, S, d_rendered, d_albedo, dPE, dPV, dPS, d_rho, d_col, d_sky, d_vis)
+  if (chunks <= 1) SNB_BWD(1);
+  else if (chunks == 2) SNB_BWD(2);
+  else if (chunks == 3) SNB_BWD(3);
+  else if (chunks == 4) SNB_BWD(4);
+  else SNB_BWD(8);
+#undef SNB_BWD
+  return 0;
+}
+
+extern "C" int snb_composite_bwd(const float* rho, const float* deltas, const float* col, const float* vis,
+                                 const float* sky, int sky_per_sample, int N, int S, int classic,
+                                 const float* d_rendered, const float* d_albedo, const float* dPE, const float* dPV,
+                                 const float* dPS, float* d_rho, float* d_col, float* d_sky, float* d_vis,
+                                 void* stream) {
+  SNB_CHECK_ARG(rho && deltas && col && vis && sky && d_rho && d_col && N >= 0 && S > 0);
+  if (S > 32 * kMaxChunks) return SNB_ERR_UNSUPPORTED;
+  if (N == 0) return SNB_OK;
+  const int chunks = (S + 31) / 32;
+  const int grid = grid_for(N, 8, 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (classic) {
+    if (sky_per_sample) launch_bwd<true, true>(chunks, grid, st, rho, deltas, col, vis, sky, N, S, d_rendered, d_albedo, dPE, dPV, dPS, d_rho, d_col, d_sky, d_vis);
+    else launch_bwd<true, false>(chunks, grid, st, rho, deltas, col, vis, sky, N, S, d_rendered, d_albedo, dPE, dPV, dPS, d_rho, d_col, d_sky, d_vis);
+  } else {
+    if (sky_per_sample) launch_bwd<false, true>(chunks, grid, st, rho, deltas, col, vis, sky, N, S, d_rendered, d_albedo, dPE, dPV, dPS, d_rho, d_col, d_sky, d_vis);
+    else launch_bwd<false, false>(chunks, grid, st, rho, deltas, col, vis, sky, N, S, d_rendered, d_albedo, dPE, dPV, dPS, d_rho, d_col, d_sky, d_vis);
+  }
+  count_launch();
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_march_transmittance(const float* rho, const float* deltas, long long M, int S, float* out,
+                                       void* stream) {
+  SNB_CHECK_ARG(rho && deltas && out && M >= 0 && S > 0);
+  if (M == 0) return SNB_OK;
+  march_transmittance_kernel<<<grid_for(M, 8, 16), 256, 0, (cudaStream_t)stream>>>(rho, deltas, M, S, out);
+  count_launch();
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_cli_composite(const void* rho, const void* deltas, const void* base, const void* vis,
+                                 const void* adj, const double* cls, const void* exact_vis, int in_dtype, int N, int S,
+                                 int C, double* base_img, double* season_img, double* extreme, double* raw_shadow,
+                                 double* raw_shadow_exact, void* stream) {
+  SNB_CHECK_ARG(rho && deltas && base && vis && adj && cls && base_img && season_img && extreme && raw_shadow);
+  SNB_CHECK_ARG(N >= 0 && S > 0 && C >= 1 && C <= 8 && (in_dtype == SNB_F32 || in_dtype == SNB_F64));
+  if (N == 0) return SNB_OK;
+  const int grid = grid_for(N, 4, 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (in_dtype == SNB_F64)
+    cli_composite_kernel<double><<<grid, 128, 0, st>>>((const double*)rho, (const double*)deltas, (const double*)base,
+        (const double*)vis, (const double*)adj, cls, (const double*)exact_vis, N, S, C, base_img, season_img, extreme,
+        raw_shadow, raw_shadow_exact);
+  else
+    cli_composite_kernel<float><<<grid, 128, 0, st>>>((const float*)rho, (const float*)deltas, (const float*)base,
+        (const float*)vis, (const float*)adj, cls, (const float*)exact_vis, N, S, C, base_img, season_img, extreme,
+        raw_shadow, raw_shadow_exact);
+  count_launch();
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+template <typename TI>
+static void launch_sweep(int chunks, int grid, cudaStream_t st, const void* rho, const void* deltas, const void* base,
+                         const void* adj, const double* cls, int N, int S, int C, int T, double* out) {
+  const TI *r = (const TI*)rho, *d = (const TI*)deltas, *b = (const TI*)base, *a = (const TI*)adj;
+  if (chunks <= 1) year_sweep_kernel<TI, 1><<<grid, 128, 0, st>>>(r, d, b, a, cls, N, S, C, T, out);
+  else if (chunks == 2) year_sweep_kernel<TI, 2><<<grid, 128, 0, st>>>(r, d, b, a, cls, N, S, C, T, out);
+  else if (chunks == 3) year_sweep_kernel<TI, 3><<<grid, 128, 0, st>>>(r, d, b, a, cls, N, S, C, T, out);
+  else year_sweep_kernel<TI, 4><<<grid, 128, 0, st>>>(r, d, b, a, cls, N, S, C, T, out);
+}
+
+extern "C" int snb_year_sweep(const void* rho, const void* deltas, const void* base, const void* adj,
+                              const double* cls, int in_dtype, int N, int S, int C, int T, double* out, void* stream) {
+  SNB_CHECK_ARG(rho && deltas && base && adj && cls && out && N >= 0 && S > 0 && T >= 0);
+  SNB_CHECK_ARG(in_dtype == SNB_F32 || in_dtype == SNB_F64);
+  if (C < 1 || C > 4 || S > 128) return SNB_ERR_UNSUPPORTED;
+  if (N == 0 || T == 0) return SNB_OK;
+  const int grid = grid_for(N, 4, 16);
+  const int chunks = (S + 31) / 32;
+  if (in_dtype == SNB_F64) launch_sweep<double>(chunks, grid, (cudaStream_t)stream, rho, deltas, base, adj, cls, N, S, C, T, out);
+  else launch_sweep<float>(chunks, grid, (cudaStream_t)stream, rho, deltas, base, adj, cls, N, S, C, T, out);
+  count_launch();
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}

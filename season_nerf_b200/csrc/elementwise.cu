@@ -1,0 +1,282 @@
+// Bandwidth-bound per-element kernels around the dense layers: positional encoding, SIREN activation with a
+// folded BatchNorm affine (forward / two-pass backward), column statistics, dtype staging.
+//   reference: misc.py:105-139 (PE_Encode), misc.py:169-170,188-189 (SineLayer + BatchNorm1d).
+#include "common.cuh"
+#include "api.h"
+
+namespace snb {
+
+// ---------------------------------------------------------------------------------------------------
+// PE_Encode, extended: out = [x | per dim: cos(k_j x) j<n , sin(k_j x) j<n], k_j = 2^j * fl32(pi/2).
+// The argument is rounded to float32 exactly like the reference's tensor product (misc.py:127) and the
+// accurate sinf/cosf are used: arguments reach ~800 rad, so no fast-math.
+// One thread per (row, dim); a warp covers consecutive rows so stores of one column group are strided
+// by the row pitch only (L2 write-combined).
+template <typename TO>
+__global__ void __launch_bounds__(256) pe_encode_kernel(const float* __restrict__ x, int ldx, long long M, int D, int n,
+                                                        TO* __restrict__ out, int ldo, int col0, int pad_to) {
+  const float kPiHalf = 1.57079637050628662109375f;  // float32(pi/2)
+  const long long total = M * D;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / D;
+    const int d = (int)(i - m * D);
+    const float v = __ldg(x + m * ldx + d);
+    TO* row = out + m * ldo + col0;
+    row[d] = from_f32<TO>(v);
+    TO* blk = row + D + d * 2 * n;
+    float k = kPiHalf;
+    for (int j = 0; j < n; ++j) {
+      const float arg = __fmul_rn(k, v);
+      float sv, cv;
+      sincosf(arg, &sv, &cv);
+      blk[j] = from_f32<TO>(cv);
+      blk[n + j] = from_f32<TO>(sv);
+      k = __fmul_rn(k, 2.0f);
+    }
+    if (d == 0)
+      for (int c = D * (2 * n + 1); c < pad_to; ++c) row[c] = from_f32<TO>(0.f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Column sums over M rows (float64 results through double atomics; inner accumulation in float32 over
+// at most 128 rows per flush).  Threads own column pairs -> 4/8-byte loads, fully coalesced per row.
+template <typename T, typename F>
+__device__ __forceinline__ void column_reduce(const T* __restrict__ base0, int ld0, const T* __restrict__ base1, int ld1,
+                                              long long M, int N, double* __restrict__ o0, double* __restrict__ o1, F f) {
+  const long long rows_per_block = (M + gridDim.x - 1) / gridDim.x;
+  const long long r0 = blockIdx.x * rows_per_block;
+  const long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+  const int ty = threadIdx.y, ny = blockDim.y;
+  for (int c = threadIdx.x * 2; c < N; c += blockDim.x * 2) {
+    const bool two = c + 1 < N;
+    double s0a = 0, s1a = 0, s0b = 0, s1b = 0;
+    for (long long rb = r0 + ty; rb < r1; rb += (long long)ny * 128) {
+      float f0a = 0, f1a = 0, f0b = 0, f1b = 0;
+      long long rend = rb + (long long)ny * 128;
+      if (rend > r1) rend = r1;
+      for (long long r = rb; r < rend; r += ny) {
+        float p0, p1, q0, q1;
+        f(base0, ld0, base1, ld1, r, c, two, p0, p1, q0, q1);
+        f0a += p0, f1a += p1, f0b += q0, f1b += q1;
+      }
+      s0a += f0a, s1a += f1a, s0b += f0b, s1b += f1b;
+    }
+    atomicAdd(o0 + c, s0a);
+    atomicAdd(o1 + c, s1a);
+    if (two) {
+      atomicAdd(o0 + c + 1, s0b);
+      atomicAdd(o1 + c + 1, s1b);
+    }
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void load2(const T* p, bool two, float& a, float& b);
+template <>
+__device__ __forceinline__ void load2<float>(const float* p, bool two, float& a, float& b) {
+  a = p[0];
+  b = two ? p[1] : 0.f;
+}
+template <>
+__device__ __forceinline__ void load2<__nv_bfloat16>(const __nv_bfloat16* p, bool two, float& a, float& b) {
+  a = __bfloat162float(p[0]);
+  b = two ? __bfloat162float(p[1]) : 0.f;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) col_stats_kernel(const T* __restrict__ Z, int ldz, long long M, int N,
+                                                        double* __restrict__ sum, double* __restrict__ sumsq) {
+  column_reduce<T>(Z, ldz, Z, ldz, M, N, sum, sumsq,
+                   [] __device__(const T* z, int ld, const T*, int, long long r, int c, bool two, float& p0, float& p1,
+                                 float& q0, float& q1) {
+                     float a, b;
+                     load2<T>(z + r * ld + c, two, a, b);
+                     p0 = a, p1 = a * a, q0 = b, q1 = b * b;
+                   });
+}
+
+struct AffineCols {
+  const float* a;
+  const float* c;
+  const float* mean;
+  const float* invstd;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) sine_bwd_reduce_kernel(const T* __restrict__ dY, int ldd, const T* __restrict__ Z,
+                                                              int ldz, AffineCols p, long long M, int N,
+                                                              double* __restrict__ sg, double* __restrict__ sgx) {
+  column_reduce<T>(dY, ldd, Z, ldz, M, N, sg, sgx,
+                   [p] __device__(const T* dy, int ld0, const T* z, int ld1, long long r, int c, bool two, float& p0,
+                                  float& p1, float& q0, float& q1) {
+                     float d0, d1, z0, z1;
+                     load2<T>(dy + r * ld0 + c, two, d0, d1);
+                     load2<T>(z + r * ld1 + c, two, z0, z1);
+                     const float g0 = d0 * cosf(p.a[c] * z0 + p.c[c]);
+                     p0 = g0, p1 = g0 * (z0 - p.mean[c]) * p.invstd[c];
+                     q0 = q1 = 0.f;
+                     if (two) {
+                       const float g1 = d1 * cosf(p.a[c + 1] * z1 + p.c[c + 1]);
+                       q0 = g1, q1 = g1 * (z1 - p.mean[c + 1]) * p.invstd[c + 1];
+                     }
+                   });
+}
+
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) sine_fwd_kernel(const T* __restrict__ Z, int ldz, const float* __restrict__ a,
+                                                       const float* __restrict__ c, T* __restrict__ Y, int ldy,
+                                                       long long M, int N) {
+  const int n2 = (N + 1) / 2;
+  const long long total = M * n2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / n2;
+    const int col = (int)(i - m * n2) * 2;
+    const bool two = col + 1 < N;
+    float z0, z1;
+    load2<T>(Z + m * ldz + col, two, z0, z1);
+    Y[m * ldy + col] = from_f32<T>(sinf(__ldg(a + col) * z0 + __ldg(c + col)));
+    if (two) Y[m * ldy + col + 1] = from_f32<T>(sinf(__ldg(a + col + 1) * z1 + __ldg(c + col + 1)));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+sine_bwd_apply_kernel(const T* __restrict__ dY, int ldd, const T* __restrict__ Z, int ldz, AffineCols p,
+                      const float* __restrict__ k1, const float* __restrict__ k2, T* __restrict__ dZ, int ldo,
+                      long long M, int N) {
+  const long long total = M * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / N;
+    const int col = (int)(i - m * N);
+    const float z = to_f32<T>(Z[m * ldz + col]);
+    const float a = __ldg(p.a + col);
+    float g = to_f32<T>(dY[m * ldd + col]) * cosf(a * z + __ldg(p.c + col));
+    if (k1) g -= __ldg(k1 + col) + (z - __ldg(p.mean + col)) * __ldg(p.invstd + col) * __ldg(k2 + col);
+    dZ[m * ldo + col] = from_f32<T>(a * g);
+  }
+}
+
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) convert_kernel(const TS* __restrict__ src, int lds, TD* __restrict__ dst, int ldd,
+                                                      long long M, int N) {
+  const long long total = M * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / N;
+    const int col = (int)(i - m * N);
+    dst[m * ldd + col] = from_f32<TD>(to_f32<TS>(src[m * lds + col]));
+  }
+}
+
+}  // namespace snb
+
+using namespace snb;
+typedef __nv_bfloat16 bf16;
+
+extern "C" int snb_pe_encode(const float* x, int ldx, long long M, int D, int n_freq, void* out, int out_dtype, int ldo,
+                             int col0, int pad_to, void* stream) {
+  SNB_CHECK_ARG(x && out && M >= 0 && D > 0 && n_freq >= 0 && ldx >= D && ldo >= col0 + D * (2 * n_freq + 1));
+  SNB_CHECK_ARG(pad_to <= ldo - col0);
+  if (M == 0) return SNB_OK;
+  const int grid = grid_for(M * D, 256, 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_dtype == SNB_F32) pe_encode_kernel<float><<<grid, 256, 0, st>>>(x, ldx, M, D, n_freq, (float*)out, ldo, col0, pad_to);
+  else if (out_dtype == SNB_BF16) pe_encode_kernel<bf16><<<grid, 256, 0, st>>>(x, ldx, M, D, n_freq, (bf16*)out, ldo, col0, pad_to);
+  else return SNB_ERR_ARG;
+  count_launch();
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+static dim3 reduce_block(int N) {
+  int tx = 32;
+  while (tx * 2 < N && tx < 256) tx *= 2;
+  return dim3(tx, 256 / tx);
+}
+
+extern "C" int snb_col_stats(const void* Z, int dtype, int ldz, long long M, int N, double* sum, double* sumsq,
+                             void* stream) {
+  SNB_CHECK_ARG(Z && sum && sumsq && M >= 0 && N > 0 && ldz >= N);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(sum, 0, sizeof(double) * N, st);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemsetAsync(sumsq, 0, sizeof(double) * N, st);
+  if (e != cudaSuccess) return (int)e;
+  if (M == 0) return SNB_OK;
+  const int grid = grid_for(M, 512, 4);
+  if (dtype == SNB_F32) col_stats_kernel<float><<<grid, reduce_block(N), 0, st>>>((const float*)Z, ldz, M, N, sum, sumsq);
+  else if (dtype == SNB_BF16) col_stats_kernel<bf16><<<grid, reduce_block(N), 0, st>>>((const bf16*)Z, ldz, M, N, sum, sumsq);
+  else return SNB_ERR_ARG;
+  count_launch();
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_sine_fwd(const void* Z, int ldz, const float* a, const float* c, void* Y, int ldy, long long M, int N,
+                            int dtype, void* stream) {
+  SNB_CHECK_ARG(Z && a && c && Y && M >= 0 && N > 0 && ldz >= N && ldy >= N);
+  if (M == 0) return SNB_OK;
+  const int grid = grid_for(M * ((N + 1) / 2), 256, 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SNB_F32) sine_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)Z, ldz, a, c, (float*)Y, ldy, M, N);
+  else if (dtype == SNB_BF16) sine_fwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)Z, ldz, a, c, (bf16*)Y, ldy, M, N);
+  else return SNB_ERR_ARG;
+  count_launch();
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_sine_bwd_reduce(const void* dY, int ldd, const void* Z, int ldz, const float* a, const float* c,
+                                   const float* mean, const float* invstd, long long M, int N, int dtype, double* sg,
+                                   double* sgx, void* stream) {
+  SNB_CHECK_ARG(dY && Z && a && c && mean && invstd && sg && sgx && M >= 0 && N > 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(sg, 0, sizeof(double) * N, st);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemsetAsync(sgx, 0, sizeof(double) * N, st);
+  if (e != cudaSuccess) return (int)e;
+  if (M == 0) return SNB_OK;
+  const int grid = grid_for(M, 512, 4);
+  AffineCols p = {a, c, mean, invstd};
+  if (dtype == SNB_F32) sine_bwd_reduce_kernel<float><<<grid, reduce_block(N), 0, st>>>((const float*)dY, ldd, (const float*)Z, ldz, p, M, N, sg, sgx);
+  else if (dtype == SNB_BF16) sine_bwd_reduce_kernel<bf16><<<grid, reduce_block(N), 0, st>>>((const bf16*)dY, ldd, (const bf16*)Z, ldz, p, M, N, sg, sgx);
+  else return SNB_ERR_ARG;
+  count_launch();
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_sine_bwd_apply(const void* dY, int ldd, const void* Z, int ldz, const float* a, const float* c,
+                                  const float* mean, const float* invstd, const float* k1, const float* k2, void* dZ,
+                                  int ldo, long long M, int N, int dtype, void* stream) {
+  SNB_CHECK_ARG(dY && Z && a && c && dZ && M >= 0 && N > 0);
+  SNB_CHECK_ARG((k1 == nullptr) == (k2 == nullptr));
+  SNB_CHECK_ARG(!k1 || (mean && invstd));
+  if (M == 0) return SNB_OK;
+  const int grid = grid_for(M * N, 256, 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  AffineCols p = {a, c, mean, invstd};
+  if (dtype == SNB_F32) sine_bwd_apply_kernel<float><<<grid, 256, 0, st>>>((const float*)dY, ldd, (const float*)Z, ldz, p, k1, k2, (float*)dZ, ldo, M, N);
+  else if (dtype == SNB_BF16) sine_bwd_apply_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dY, ldd, (const bf16*)Z, ldz, p, k1, k2, (bf16*)dZ, ldo, M, N);
+  else return SNB_ERR_ARG;
+  count_launch();
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_convert(const void* src, int src_dtype, int lds, void* dst, int dst_dtype, int ldd, long long M, int N,
+                           void* stream) {
+  SNB_CHECK_ARG(src && dst && M >= 0 && N > 0 && lds >= N && ldd >= N);
+  if (M == 0) return SNB_OK;
+  const int grid = grid_for(M * N, 256, 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (src_dtype == SNB_F32 && dst_dtype == SNB_BF16) convert_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)src, lds, (bf16*)dst, ldd, M, N);
+  else if (src_dtype == SNB_BF16 && dst_dtype == SNB_F32) convert_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)src, lds, (float*)dst, ldd, M, N);
+  else if (src_dtype == SNB_F32 && dst_dtype == SNB_F32) convert_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, lds, (float*)dst, ldd, M, N);
+  else if (src_dtype == SNB_BF16 && dst_dtype == SNB_BF16) convert_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)src, lds, (bf16*)dst, ldd, M, N);
+  else return SNB_ERR_ARG;
+  count_launch();
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}

@@ -1,0 +1,301 @@
+"""Render / loss engine: drop-in for T_NeRF_Full_2/Eval_Tools_2.py (get_PV :13-16, create_solor_rays_uniform :42-108,
+All_in_One_Eval :111-459) and misc.py:234-261 (sample_pt_coarse, zero_invalid_pts).
+
+Same constructor, methods, result-dict keys and `{name: [value, weight]}` loss dict as the reference.  Inputs may
+arrive as CPU float32 tensors exactly like the reference's DataLoader rows: this shim owns the H2D copy.  Sampling,
+the network and compositing run in the sm_100a library; only the O(N) loss arithmetic stays in torch.
+Extra keyword arguments (`jitter=`, `solar=`, `solar_jitter=`) inject the random draws of the reference for parity
+tests; when omitted the same draws are made from the same global RNGs in the same order as the reference.
+"""
+import numpy as np
+import torch as t
+
+from . import ops
+from .geometry import world_angle_2_local_vec
+
+
+def _dev(x, device):
+    return x.to(device=device, dtype=t.float32, non_blocking=True)
+
+
+def sample_ts(n_course, eval_mode, include_end_pt=False, jitter=None):
+    """misc.py:236-241, on the host exactly like the reference (torch CPU linspace / rand) -> float32 [n]."""
+    if include_end_pt is False or eval_mode is False:
+        ts = t.linspace(0, 1, n_course + 1)[0:-1].clone()
+    else:
+        ts = t.linspace(0, 1, n_course)
+    if eval_mode is False:
+        r = t.rand(n_course) if jitter is None else t.as_tensor(jitter, dtype=t.float32).cpu()
+        ts += 1 / n_course * r
+    return ts
+
+
+def sample_pt_coarse(pt_tops, pt_bots, n_course, eval_mode, include_end_pt=False, jitter=None, device=None):
+    """misc.py:234-247 -> pts [N,S,3], deltas [N,S,1] (on the device)."""
+    device = device or (pt_tops.device if pt_tops.is_cuda else t.device("cuda"))
+    ts = sample_ts(n_course, eval_mode, include_end_pt, jitter).to(device)
+    pts, deltas = ops.sample_rays(_dev(pt_tops, device), _dev(pt_bots, device), ts)
+    return pts, deltas.unsqueeze(-1)
+
+
+class zero_invalid_pts():
+    """misc.py:249-261."""
+
+    def __init__(self, X=(-1, 1), Y=(-1, 1), Z=(-1, 1)):
+        self.X, self.Y, self.Z = X, Y, Z
+
+    def __call__(self, Xs):
+        return ~((Xs <= 1).all(-1) & (Xs >= -1).all(-1))
+
+
+def get_PV(Rhos, Deltas):
+    """Eval_Tools_2.py:13-16 on [N,S,1] tensors (exclusive-prefix transmittance)."""
+    if not Rhos.is_cuda:
+        raise ops._lib.SeasonNerfCudaError("season_nerf_b200.get_PV needs CUDA tensors (no CPU fallback)")
+    N, S = Rhos.shape[0], Rhos.shape[1]
+    rho = Rhos.reshape(N, S).float().contiguous()
+    dl = Deltas.reshape(N, S).float().contiguous()
+    z3 = t.zeros(N, S, 3, device=rho.device)
+    PV = ops.composite_fwd(rho, dl, z3, t.zeros_like(rho), t.zeros(N, 3, device=rho.device))[0]
+    return PV.reshape(N, S, 1).to(Rhos.dtype)
+
+
+class create_solor_rays_uniform():
+    """Eval_Tools_2.py:42-108 with the per-ray Python loop vectorised (same RNG draws in the same order)."""
+
+    def __init__(self, W2L_H, WCW, base_vecs=None):
+        self.W2L = W2L_H
+        self.WC = WCW
+        self._base_vecs = base_vecs
+        self._use_base_vecs = False      # the reference overrides this to False (:48)
+
+    def __call__(self, n, include_times=False):
+        az_el = np.random.random(n * 2).reshape([n, 2]) * np.array([[360, 89]]) + np.array([[-180, 1]])
+        vec = world_angle_2_local_vec(az_el[:, 1], az_el[:, 0], self.WC, self.W2L)
+        delta = 2 * (vec / vec[:, 2::])
+        starts = t.ones([n, 3])
+        starts[:, 0] = t.tensor(2.0) * t.rand(n) + t.tensor(-1.0)
+        starts[:, 1] = t.tensor(2.0) * t.rand(n) + t.tensor(-1.0)
+        ends = (starts - t.tensor(delta)).float()
+        vec = t.tensor(vec).float()
+        if include_times is False:
+            return starts, ends, vec
+        f = t.rand([n, 2]) * 2 * np.pi
+        times = t.stack([t.cos(f[:, 0]), t.sin(f[:, 0]), t.cos(f[:, 1]), t.sin(f[:, 1])], 1)
+        return starts, ends, vec, times, az_el
+
+    def create_given_vec(self, n, solar_angle_vec, include_times=False):
+        delta = 2 * (solar_angle_vec / solar_angle_vec[2::])
+        starts = t.ones([n, 3])
+        starts[:, 0] = t.tensor(2.0) * t.rand(n) + t.tensor(-1.0)
+        starts[:, 1] = t.tensor(2.0) * t.rand(n) + t.tensor(-1.0)
+        ends = (starts - t.tensor(np.expand_dims(delta, 0))).float()
+        vec = t.stack([t.tensor(solar_angle_vec).float()] * n, 0)
+        if include_times is False:
+            return starts, ends, vec
+        f = t.rand([n, 2]) * 2 * np.pi
+        times = t.stack([t.cos(f[:, 0]), t.sin(f[:, 0]), t.cos(f[:, 1]), t.sin(f[:, 1])], 1)
+        return starts, ends, vec, times
+
+
+class All_in_One_Eval():
+    def __init__(self, args, device, n_steps, use_prior, ada_loss, H, WC, base_solar_vecs=None):
+        self.device = t.device(device)
+        if self.device.type != "cuda":
+            raise ops._lib.SeasonNerfCudaError("season_nerf_b200.All_in_One_Eval needs a CUDA device (no CPU fallback)")
+        self.args = args
+        self.n_steps = n_steps
+        self.MSE_loss = t.nn.MSELoss()
+        self.smooth_L1 = t.nn.SmoothL1Loss()
+        self.use_prior = use_prior
+        self.use_reg = args.Use_Reg
+        self.use_classic_solar = args.Solar_Type_2
+        self.use_MSE_loss = args.Use_MSE_loss
+        self.ada_loss = ada_loss
+        self.solar_creation_tool = create_solor_rays_uniform(H, WC, base_solar_vecs)
+        self.Sigmoid = t.nn.Sigmoid()
+        self.BCE_loss = t.nn.BCELoss()
+
+    # ---------------------------------------------------------------------------------------------------
+    def _shade(self, Rho, deltas, Col, Vis, Sky_ray):
+        """PV/PE/PS + colour for one density field (Eval_Tools_2.py:187-215)."""
+        N, S = Rho.shape[0], Rho.shape[1]
+        PV, PE, PS, albedo, rendered, _ = ops.composite(Rho.reshape(N, S), deltas.reshape(N, S), Col,
+                                                        Vis.reshape(N, S), Sky_ray, self.use_classic_solar)
+        return PV.unsqueeze(-1), PE.unsqueeze(-1), PS.unsqueeze(-1), albedo, rendered
+
+    def eval(self, data_dict, Network, current_step, train_mode, jitter=None):
+        """Eval_Tools_2.py:165-252."""
+        S = self.args.n_samples
+        dev = self.device
+        Xs, deltas = sample_pt_coarse(data_dict["Top"], data_dict["Bot"], S, not train_mode, jitter=jitter, device=dev)
+        N = Xs.shape[0]
+        sun, tim = _dev(data_dict["Sun_Angle"], dev), _dev(data_dict["Time_Encoded"], dev)
+        pos, vis, adj, sky, cl = Network.forward_rays(Xs.reshape(-1, 3), sun, tim, S)
+        Rho, Col, Vis, Sky, Cls, Adj = Network._mix(pos, vis, adj, sky, cl, S, True, True)
+        Sky_ray = Network.Sigmoid(sky)
+        Col, Rho, Vis = Col.reshape(N, S, -1), Rho.reshape(N, S, 1), Vis.reshape(N, S, 1)
+        Sky, Cls, Adj = Sky.reshape(N, S, -1), Cls.reshape(N, S, -1), Adj.reshape(N, S, -1)
+        PV, PE, PS, Albedo, Rendered = self._shade(Rho, deltas, Col, Vis, Sky_ray)
+        R = {"Rendered_Col": Rendered, "PE": PE, "PV": PV, "PS": PS, "Solar_Vis": Vis, "Sky_Col": Sky, "Classes": Cls,
+             "Adjust": Adj, "Rho": Rho, "Col": Col, "Col_Adj": -1, "deltas": deltas, "sample_pts": Xs,
+             "Albedo_Color": Albedo}
+        if self.use_prior:
+            trust = current_step / self.n_steps
+            with t.no_grad():
+                Rho_S = Network.Supervised_Sample(Xs.reshape(-1, 3), deltas.reshape(-1, 1)).reshape(N, S, 1)
+            PV_S, PE_S, PS_S, _, Rend_S = self._shade(Rho_S, deltas, Col, Vis, Sky_ray)
+            Rho_M = Rho * trust + Rho_S * (1 - trust)
+            PV_M, PE_M, PS_M, Albedo_M, Rend_M = self._shade(Rho_M, deltas, Col, Vis, Sky_ray)
+            R.update({"PV_Supervised": PV_S, "PE_Supervised": PE_S, "PS_Supervised": PS_S,
+                      "Rendered_Col_Supervised": Rend_S, "PV_Merged": PV_M, "PE_Merged": PE_M, "PS_Merged": PS_M,
+                      "Rendered_Col_Merged": Rend_M, "Rho_Merged": Rho_M, "Albedo_Color": Albedo_M})
+        return R
+
+    def full_eval(self, data_dict, Network, current_step):
+        """Eval_Tools_2.py:127-163 (eval-mode sampling, raw colour activated here)."""
+        S = self.args.n_samples
+        dev = self.device
+        Xs, deltas = sample_pt_coarse(data_dict["Top"], data_dict["Bot"], S, True, device=dev)
+        N = Xs.shape[0]
+        sun, tim = _dev(data_dict["Sun_Angle"], dev), _dev(data_dict["Time_Encoded"], dev)
+        pos, vis, adj, sky, cl = Network.forward_rays(Xs.reshape(-1, 3), sun, tim, S)
+        Rho, Base, Vis, Sky, Cls, Adj = Network._mix(pos, vis, adj, sky, cl, S, True, True)
+        Sky_ray = Network.Sigmoid(sky)
+        Base, Rho, Vis = Base.reshape(N, S, -1), Rho.reshape(N, S, 1), Vis.reshape(N, S, 1)
+        # the reference applies Sigmoid to the already-activated colour here (:155,158)
+        PV, PE, PS, _, Rendered = self._shade(Rho, deltas, self.Sigmoid(Base), Vis, Sky_ray)
+        return {"Rendered_Col": Rendered, "PE": PE, "PV": PV, "PS": PS, "Solar_Vis": Vis,
+                "Sky_Col": Sky.reshape(N, S, -1), "Classes": Cls.reshape(N, S, -1), "Adjust": Adj.reshape(N, S, -1),
+                "Rho": Rho, "Col": Base, "deltas": deltas, "sample_pts": Xs}
+
+    def eval_Rho_Only(self, data_dict, Network, train_mode, current_step=0, jitter=None):
+        """Eval_Tools_2.py:297-337."""
+        S = self.args.n_samples
+        dev = self.device
+        Xs, deltas = sample_pt_coarse(data_dict["Top"], data_dict["Bot"], S, not train_mode, include_end_pt=True,
+                                      jitter=jitter, device=dev)
+        N = Xs.shape[0]
+        sun = _dev(data_dict["Sun_Angle"], dev)
+        rho_raw, vis_raw, sky_raw = Network.forward_rays(Xs.reshape(-1, 3), sun, None, S, mode="solar")
+        Rho = Network.Softplus(rho_raw).reshape(N, S, 1)
+        Vis = Network.Sigmoid(vis_raw).reshape(N, S, 1)
+        Sky = sky_raw.repeat_interleave(S, 0).reshape(N, S, -1)     # RAW sky (T_NeRF_net_v2.py:157)
+        if self.use_prior:
+            trust = current_step / self.n_steps
+            with t.no_grad():
+                Xs2, d2 = Xs.reshape(-1, 3), deltas.reshape(-1, 1)
+                good = t.all((Xs2 <= 1.) * (Xs2 >= -1.), 1)
+                Rho_S = Rho.reshape(-1, 1).detach().clone()
+                Rho_S[good] = Network.Supervised_Sample(Xs2[good], d2[good])
+                Rho_S = Rho_S.reshape(N, S, 1)
+            Rho = Rho * trust + Rho_S * (1 - trust)
+        PE = 1 - t.exp(-Rho * deltas)
+        PV = get_PV(Rho.detach(), deltas) if not Rho.requires_grad else self._pv_autograd(Rho, deltas)
+        return {"PE": PE, "PV_Exact": PV, "Solar_Vis": Vis, "Sky_Col": Sky}
+
+    def _pv_autograd(self, Rho, deltas):
+        N, S = Rho.shape[0], Rho.shape[1]
+        z = t.zeros(N, S, device=Rho.device)
+        PV = ops.composite(Rho.reshape(N, S), deltas.reshape(N, S), t.zeros(N, S, 3, device=Rho.device), z,
+                           t.zeros(N, 3, device=Rho.device), False)[0]
+        return PV.unsqueeze(-1)
+
+    def _get_exact_solar(self, world_pts, sun_angle, Network):
+        """Eval_Tools_2.py:255-269 for all sample points of ONE ray."""
+        dev = self.device
+        world_pts = _dev(world_pts, dev)
+        sun_angle = _dev(sun_angle, dev)
+        n = world_pts.shape[0]
+        tops = ops.solar_tops(world_pts, sun_angle.tolist(), f64=False)
+        sub = {"Top": tops, "Bot": world_pts, "Sun_Angle": sun_angle.reshape(1, 3).expand(n, 3),
+               "Time_Encoded": t.ones(n, 4)}
+        r = self.eval_Rho_Only(sub, Network, False)
+        return r["PV_Exact"][:, -1], r["Solar_Vis"][:, -1]
+
+    def eval_exact_solar(self, data_dict, Network, current_step, train_mode):
+        """Eval_Tools_2.py:273-295; the reference's per-ray Python loop is batched over all rays of the call."""
+        R = self.eval(data_dict, Network, current_step, train_mode)
+        R["Est_Solar_Vis"] = R["Solar_Vis"].clone()
+        dev = self.device
+        pts = R["sample_pts"]
+        N, S = pts.shape[0], pts.shape[1]
+        sun = _dev(data_dict["Sun_Angle"], dev)
+        with t.no_grad():
+            sun_pts = sun.repeat_interleave(S, 0)
+            p = pts.reshape(-1, 3)
+            K = (1 - p[:, 2]) / sun_pts[:, 2]                                   # :257 (float32)
+            tops = p + K.unsqueeze(1) * sun_pts                                 # :258
+            sub = {"Top": tops, "Bot": p, "Sun_Angle": sun_pts, "Time_Encoded": t.ones(p.shape[0], 4)}
+            r = self.eval_Rho_Only(sub, Network, False)
+            R["Solar_Vis"] = r["PV_Exact"][:, -1].reshape(N, S, 1)
+        R["Col_Adj"] = (R["Solar_Vis"] + (1 - R["Solar_Vis"]) * R["Sky_Col"]) * R["Col"]
+        if self.use_classic_solar:
+            R["Rendered_Col"] = t.sum(R["PS"] * R["Col"] * (R["Solar_Vis"] + (1 - R["Solar_Vis"]) * R["Sky_Col"]), 1)
+        else:
+            sv3 = self.Sigmoid((t.sum(R["Solar_Vis"] * R["PS"], 1) - .2) * 30)
+            R["Rendered_Col"] = t.sum(R["PS"] * R["Col"], 1) * (sv3 + (1 - sv3) * t.mean(R["Sky_Col"], 1))
+        return R
+
+    # ---------------------------------------------------------------------------------------------------
+    def get_loss(self, data_dict, Network, current_step, train_mode, jitter=None, solar=None, solar_jitter=None):
+        """Eval_Tools_2.py:340-459."""
+        n_rays = data_dict["Top"].shape[0]
+        device = self.device
+        args = self.args
+        Loss = {}
+        weight = {"Color": 1.0, "Solar_Correction": args.sc_lambda, "Alpha_Adjust": 1.}
+        out = self.eval(data_dict, Network, current_step, train_mode, jitter=jitter)
+        if args.Use_Solar:
+            if solar is None:
+                starts, ends, svec, stime, _ = self.solar_creation_tool(n_rays, include_times=True)
+            else:
+                starts, ends, svec, stime = solar
+            sol = self.eval_Rho_Only({"Top": starts, "Bot": ends, "Sun_Angle": svec, "Time_Encoded": stime}, Network,
+                                     train_mode, current_step, jitter=solar_jitter)
+            err = t.mean(t.sum((sol["Solar_Vis"] - sol["PV_Exact"].detach()) ** 2, 1))
+            Loss["Solar_Correction"] = [err, weight["Solar_Correction"]]
+            absorb = t.mean(1 - t.sum(sol["PE"].detach() * sol["PV_Exact"].detach() * sol["Solar_Vis"], 1))
+            Loss["Solar_Correction_2"] = [absorb if args.Solar_Type_2 else absorb.detach(), weight["Solar_Correction"]]
+            if args.Solar_Type_2 is False:
+                alb = out["Albedo_Color"]
+                sk_alb, _ = t.min(alb, 0)
+                m = (sk_alb < .2).float()           # branch-free: no host sync (.item() stalls)
+                alb_loss = t.sum(m * (1. - sk_alb / .2) ** 2) / alb.shape[0]
+                sk = (out["Sky_Col"] - .5) / .5
+                sk_loss = t.sum(t.relu(sk) ** 2) / float(np.prod(sk.shape))
+                if self.use_prior:
+                    sk_loss = sk_loss.detach()
+                Loss["Sky_Color_Var"] = [sk_loss, weight["Solar_Correction"]]
+                Loss["Albedo_Color"] = [alb_loss, weight["Solar_Correction"]]
+        gt = _dev(data_dict["GT_Color"], device)
+        merged = "Rendered_Col_Merged" if (self.use_prior and train_mode) else "Rendered_Col"
+        if self.use_MSE_loss is True:
+            Loss["Color"] = [self.MSE_loss(out[merged], gt), weight["Color"]]
+            if self.use_prior:
+                Loss["Alpha_Adjust"] = [self.MSE_loss(out["PE"], out["PE_Supervised"].detach()), weight["Alpha_Adjust"]]
+        else:
+            diff = out["Rendered_Col"] - gt
+            if self.use_prior:
+                a0, a1 = self.ada_loss[0], self.ada_loss[1]
+                adiff = (out["PE"] - out["PE_Supervised"].detach()).reshape([-1, 1])
+                Loss["Alpha_Adjust_ada"] = [t.mean(a1.lossfun(adiff)), weight["Alpha_Adjust"]]
+                Loss["Color_ada"] = [t.mean(a0.lossfun(diff)), weight["Color"]]
+                Loss["Color_alpha"] = [t.mean(a0.alpha().detach()), 1.]
+                Loss["Color_width"] = [t.mean(a0.scale().detach()), 1.]
+                Loss["Alpha_Adjust"] = [self.MSE_loss(out["PE"], out["PE_Supervised"].detach()), weight["Alpha_Adjust"]]
+                scale = t.mean(a0.scale().detach()) ** 2
+                Loss["Alpha_alpha"] = [t.mean(a1.alpha().detach()), 1.]
+                Loss["Alpha_width"] = [t.mean(a1.scale().detach()), 1.]
+            else:
+                a0 = self.ada_loss
+                Loss["Color_ada"] = [t.mean(a0.lossfun(diff)), weight["Color"]]
+                Loss["Color_alpha"] = [t.mean(a0.alpha().detach()), 1.]
+                Loss["Color_width"] = [t.mean(a0.scale().detach()), 1.]
+                scale = t.mean(a0.scale().detach()) ** 2
+            if args.Use_Solar:
+                Loss["Solar_Correction"][1] = Loss["Solar_Correction"][1] / scale
+                Loss["Solar_Correction_2"][1] = Loss["Solar_Correction_2"][1] / scale
+            with t.no_grad():
+                Loss["Color"] = [self.MSE_loss(out[merged], gt).detach(), weight["Color"]]
+        return Loss

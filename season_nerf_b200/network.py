@@ -1,0 +1,607 @@
+"""Drop-in `T_NeRF` network (reference: T_NeRF_Full_2/T_NeRF_net_v2.py:20-204, T_NeRF_Full_2/G_NeRF.py:6-157,
+misc.py:105-194) whose dense work runs in the sm_100a library.
+
+Same constructor, same module tree and therefore the same 94 state_dict keys / shapes, same public methods and
+return tuples as the reference, `.train()/.eval()` switch BatchNorm semantics, parameters are ordinary
+`nn.Parameter`s usable by `torch.optim`, and every differentiable output supports autograd.  The modules are
+parameter containers: the arithmetic is scheduled by `_Pass` below as hand-written CUDA kernels
+(GEMM -> column statistics -> sin(BN(.)) per layer, with a hand-scheduled backward) or, in eval mode on whole
+rays, by the fused tcgen05 kernel (season_nerf_b200/fused.py).
+
+precision: "bf16" (production: bf16 operands, fp32 accumulate on tcgen05) or "fp32" (validation build).
+"""
+from math import sqrt
+
+import numpy as np
+import torch as t
+from torch import nn
+
+from . import ops
+
+OMEGA_0 = 30.0
+
+
+def _r8(x):
+    return (x + 7) // 8 * 8
+
+
+class PE_Encode(nn.Module):
+    """misc.py:105-139 (parameter-free).  Kept as a module so `net.G_NeRF_net.PE_encoder(X)` keeps working."""
+
+    def __init__(self, n, use_Extend_encoding, scale=np.pi / 2):
+        super().__init__()
+        self.n = n
+        self.use_Extended = use_Extend_encoding
+
+    def forward(self, X):
+        if not self.use_Extended:
+            raise NotImplementedError("season_nerf_b200 implements the extended encoding the reference network uses")
+        X = X.float().contiguous()
+        out = t.empty(X.shape[0], X.shape[1] * (2 * self.n + 1), device=X.device, dtype=t.float32)
+        return ops.pe_encode(X, self.n, out)
+
+
+class SineLayer(nn.Module):
+    """misc.py:148-194: sin(norm(omega_0 * linear(x))); BatchNorm1d(momentum=0.01) iff use_norm and not is_first."""
+
+    def __init__(self, in_features, out_features, bias=True, is_first=False, omega_0=30, use_norm=False):
+        super().__init__()
+        self.omega_0 = omega_0
+        self.is_first = is_first
+        self.in_features = in_features
+        self.linear = nn.Linear(in_features, out_features, bias=bias)
+        self.init_weights()
+        if is_first is False and use_norm:
+            self.norm = nn.BatchNorm1d(out_features, momentum=0.01)
+        else:
+            self.norm = nn.Identity()
+
+    def init_weights(self):
+        with t.no_grad():
+            if self.is_first:
+                self.linear.weight.uniform_(-1 / self.in_features, 1 / self.in_features)
+            else:
+                b = sqrt(6 / self.in_features) / self.omega_0
+                self.linear.weight.uniform_(-b, b)
+
+    @property
+    def has_bn(self):
+        return isinstance(self.norm, nn.BatchNorm1d)
+
+    def forward(self, input):
+        net = _SingleLayerNet(self)
+        return _run(net, "single", input, None, None, 1, getattr(self, "precision", "fp32"))[0]
+
+
+class _SingleLayerNet:
+    """adapter so that a lone SineLayer can run through the executor"""
+
+    def __init__(self, layer):
+        self.layer = layer
+        self.training = layer.training
+
+    def parameters(self):
+        return self.layer.parameters()
+
+
+class G_NeRF_Net_Classic(nn.Module):
+    """G_NeRF.py:6-71 module tree (non-SIREN2 branch)."""
+
+    def __init__(self, layer_width=512, expand_size_pose=10, expand_size_solar_angle=4, num_out_channels=3,
+                 extended_encoding=False):
+        super().__init__()
+        if not extended_encoding or expand_size_pose == 0 or expand_size_solar_angle == 0:
+            raise NotImplementedError("only the extended positional encoding used by T_NeRF is implemented")
+        self.ignore_hue = False
+        self.use_norm = True
+        self.use_SIREN2 = False
+        self._expand_size_pose = expand_size_pose
+        self._expand_size_solar_angle = expand_size_solar_angle
+        lw, lw2, lw4 = layer_width, max(layer_width // 2, 1), max(layer_width // 4, 1)
+        input_size = 3 * (expand_size_pose * 2 + 1)
+        input_size_solar = 3 * (expand_size_solar_angle * 2 + 1)
+        self.PE_encoder = PE_Encode(expand_size_pose, True)
+        self.PE_encoder_solar = PE_Encode(expand_size_solar_angle, True)
+        self.fc1 = SineLayer(input_size, lw, is_first=True)
+        self.fc2 = SineLayer(lw, lw, use_norm=True)
+        self.fc3 = SineLayer(lw, lw, use_norm=True)
+        self.fc4 = SineLayer(lw, lw, use_norm=True)
+        self.fc5 = SineLayer(lw + input_size, lw, is_first=False, use_norm=True)
+        self.fc6 = SineLayer(lw, lw, use_norm=True)
+        self.fc7 = SineLayer(lw, lw, use_norm=True)
+        self.fc8 = SineLayer(lw, lw, use_norm=True)
+        self.fc9 = SineLayer(lw, lw2, use_norm=True)
+        self.fc10Col = nn.Linear(lw2, num_out_channels)
+        self.fc10Sigma = nn.Linear(lw2, 1)
+        self._inv_delta = 1
+        self.fc_solar_1 = SineLayer(input_size_solar + lw2, lw2, is_first=True)
+        self.fc_solar_2 = SineLayer(lw2, lw2)
+        self.fc_solar_3 = SineLayer(lw2, lw2)
+        self.fc_solar_4 = nn.Linear(lw2, 1)
+        self.fc_sky_color_1 = SineLayer(input_size_solar, lw4, is_first=True)
+        self.fc_sky_color_2 = nn.Linear(lw4, 3)
+        self.num_out_channels = num_out_channels
+        self.sig = nn.Sigmoid()
+        self.SoftPlus = nn.Softplus()
+        self.precision = "bf16"
+
+    # -- public methods of the reference that callers use directly (Eval_funcs.py:286-287,314) ---------------
+    def forward_Sigma_Only(self, X):
+        """G_NeRF.py:74-77."""
+        return self.SoftPlus(_run(self._net(), "sigma", X, None, None, 1)[0]) * self._inv_delta
+
+    def forward_color_only(self, X):
+        """G_NeRF.py:154-157."""
+        return self.sig(_run(self._net(), "color", X, None, None, 1)[0])
+
+    def forward_Position(self, X):
+        """G_NeRF.py:93-98 -> X_Encode, rho_raw, col_raw."""
+        pos, xenc = _run(self._net(), "position", X, None, None, 1)
+        return xenc, pos[:, 0:1], pos[:, 1:]
+
+    def _net(self):
+        return _GOnly(self)
+
+
+class _GOnly:
+    """adapter: the position-only schedules (sigma / color / position) need nothing outside the G-net"""
+
+    def __init__(self, g):
+        self.G_NeRF_net = g
+        self.layer_width = g.fc1.linear.out_features
+        self.training = g.training
+        self.precision = g.precision
+
+    def parameters(self):
+        return self.G_NeRF_net.parameters()
+
+
+class T_NeRF(nn.Module):
+    """T_NeRF_net_v2.py:20-204."""
+
+    def __init__(self, layer_width, n_classes=4, HM=np.array([[0], [0]]), precision="bf16"):
+        super().__init__()
+        self.allow_other_temporal_adjust = False
+        self.hm = t.tensor(HM, requires_grad=False)
+        self._hm_const = t.tensor(self.hm.shape).reshape([1, 2]) - 1
+        self.G_NeRF_net = G_NeRF_Net_Classic(layer_width=layer_width, extended_encoding=True)
+        self.Time_Enocder = PE_Encode(2, use_Extend_encoding=True)
+        self.time_layer_1 = SineLayer(4 * 2 + 2, layer_width, is_first=True)
+        self.time_layer_2 = SineLayer(layer_width, layer_width)
+        self.get_class_layer = nn.Linear(layer_width, n_classes)
+        self.adjust_layer_1 = SineLayer(layer_width // 2, layer_width)
+        self.adjust_layer_2 = SineLayer(layer_width, layer_width)
+        self.adjust_layer_3 = SineLayer(layer_width, layer_width)
+        self.adjust_col = nn.Linear(layer_width, n_classes * 3)
+        self.adjust_rho = nn.Linear(layer_width, n_classes)              # unused heads: present for load_state_dict
+        self.adjust_solar_vis = nn.Linear(layer_width, n_classes)
+        self.adjust_sky_col = nn.Linear(layer_width, n_classes * 3)
+        self.n_classes = n_classes
+        self.layer_width = layer_width
+        self.SoftMax = nn.Softmax(1)
+        self.Softplus = nn.Softplus()
+        self.Sigmoid = nn.Sigmoid()
+        self.batch_params_freeze = False
+        self._ignore_solar = False
+        self.precision = precision
+        self._fused_cache = None
+
+    @property
+    def precision(self):
+        return self.G_NeRF_net.precision
+
+    @precision.setter
+    def precision(self, p):
+        if p not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        self.G_NeRF_net.precision = p
+
+    def ignore_solar(self):
+        self._ignore_solar = True
+
+    def _process_time(self, Time):
+        return Time[:, 0:2]
+
+    # ---- per-ray interface used by the render / loss engine (time, sky and class branches once per ray) ----
+    def forward_rays(self, pts, sun, time, S, mode="full"):
+        """pts [N*S,3]; sun [N,3]; time [N,>=2].  Returns the RAW heads (see _Pass) with autograd."""
+        return _run(self, mode, pts, sun, time, S)
+
+    def _mix(self, pos, vis, adj, sky, cls_logits, S, mix, act_col):
+        M = pos.shape[0]
+        cls = self.SoftMax(cls_logits)
+        clsp = cls if S == 1 else cls.repeat_interleave(S, 0)
+        skyp = sky if S == 1 else sky.repeat_interleave(S, 0)
+        Adj = adj.reshape(M, self.n_classes, -1)
+        Rho = self.Softplus(pos[:, 0:1])
+        Col = pos[:, 1:]
+        if mix:
+            Adjust_col = t.sum(Adj * clsp.unsqueeze(2), 1)
+            Col = self.Sigmoid(Col + Adjust_col) if act_col else Col
+        else:
+            Adjust_col = Adj
+        return Rho, Col, self.Sigmoid(vis), self.Sigmoid(skyp), clsp, Adjust_col
+
+    # ---- per-point public API (reference signatures) -------------------------------------------------------
+    def forward(self, X, Solar_Angle, Time):
+        """T_NeRF_net_v2.py:75-105."""
+        pos, vis, adj, sky, cl = _run(self, "full", X, Solar_Angle, Time, 1)
+        return self._mix(pos, vis, adj, sky, cl, 1, True, True)
+
+    def forward_seperate(self, X, Solar_Angle, Time):
+        """T_NeRF_net_v2.py:131-151: raw col, unmixed Adj [M,C,3]."""
+        pos, vis, adj, sky, cl = _run(self, "full", X, Solar_Angle, Time, 1)
+        return self._mix(pos, vis, adj, sky, cl, 1, False, False)
+
+    def forward_full_eval(self, X, Solar_Angle, Time):
+        """T_NeRF_net_v2.py:184-204 (same tuple as forward_seperate)."""
+        return self.forward_seperate(X, Solar_Angle, Time)
+
+    def forward_Solar(self, X, Solar_Angle, Time):
+        """T_NeRF_net_v2.py:154-157: trunk under no_grad, solar + sky heads with grad, RAW sky."""
+        rho, vis, sky = _run(self, "solar", X, Solar_Angle, None, 1)
+        return self.Softplus(rho), self.Sigmoid(vis), sky
+
+    def get_class_only(self, Time):
+        """T_NeRF_net_v2.py:160-163."""
+        return self.SoftMax(_run(self, "class", None, None, Time, 1)[0])
+
+    def forward_Classic_Sigma_Only(self, X):
+        """T_NeRF_net_v2.py:169-170."""
+        return self.G_NeRF_net.forward_Sigma_Only(X)
+
+    def approx_Solar(self, X, X_solar, Time):
+        """T_NeRF_net_v2.py:107-128."""
+        n = X.shape[0]
+        pos, xenc = _run(self, "position", t.cat([X, X_solar], 0), None, None, 1)
+        cl = _run(self, "class", None, None, Time, 1)[0]
+        adj = _run(self, "adjust", xenc[0:n], None, None, 1)[0]
+        cls = self.SoftMax(cl)
+        Adjust_col = t.sum(adj.reshape(n, self.n_classes, -1) * cls.unsqueeze(2), 1)
+        Rho = self.Softplus(pos[:, 0:1])
+        Col = self.Sigmoid(pos[0:n, 1:] + Adjust_col)
+        return Rho[0:n], Rho[n::], Col, cls, Adjust_col
+
+    def Supervised_Sample(self, world_pts, delta):
+        """T_NeRF_net_v2.py:175-181 (the reference runs this on the CPU; any device works here)."""
+        hm = self.hm.to(world_pts.device)
+        xy = ((world_pts[:, 0:2] + 1) / 2 * self._hm_const.to(world_pts.device)).long()
+        P = (hm[xy[:, 0], xy[:, 1]] >= world_pts[:, 2]).float()
+        P[P > .99] = 0.99
+        return -t.log(1 - P.unsqueeze(1)) / delta
+
+
+# =========================================================================================================
+# executor
+# =========================================================================================================
+class _Spec:
+    __slots__ = ("name", "kind", "inp", "in_col0", "kp", "out", "out_col0", "lin", "layer", "need_dx", "grad")
+
+    def __init__(self, name, kind, inp, in_col0, kp, out, out_col0, lin, layer=None, need_dx=True, grad=True):
+        self.name, self.kind, self.inp, self.in_col0, self.kp = name, kind, inp, in_col0, kp
+        self.out, self.out_col0, self.lin, self.layer, self.need_dx, self.grad = out, out_col0, lin, layer, need_dx, grad
+
+    @property
+    def n_out(self):
+        return sum(l.out_features for l in self.lin)
+
+
+def _plan(net, mode):
+    """Layer schedule.  Buffers (row-major activation matrices):
+       cat5  [M, lw+64]  = [h4 | enc(63) | 0]   (fc1 reads the enc slice, fc5 the whole row)      G_NeRF.py:81-86
+       cats1 [M, lw2+32] = [X_Encode | enc_sun(27) | 0]                                           G_NeRF.py:101-102
+    """
+    if mode == "single":
+        L = net.layer
+        return [_Spec("layer", "sine", "x", 0, _r8(L.in_features), "y", 0, [L.linear], L, need_dx=True)], None
+    g = net.G_NeRF_net
+    lw = net.layer_width
+    S = lambda *a, **k: _Spec(*a, **k)
+    trunk_grad = mode not in ("solar",)
+    tg = dict(grad=trunk_grad)
+    trunk = [
+        S("fc1", "sine", "cat5", lw, 64, "h1", 0, [g.fc1.linear], g.fc1, need_dx=False, **tg),
+        S("fc2", "sine", "h1", 0, lw, "h2", 0, [g.fc2.linear], g.fc2, **tg),
+        S("fc3", "sine", "h2", 0, lw, "h3", 0, [g.fc3.linear], g.fc3, **tg),
+        S("fc4", "sine", "h3", 0, lw, "cat5", 0, [g.fc4.linear], g.fc4, **tg),
+        S("fc5", "sine", "cat5", 0, lw + 64, "h5", 0, [g.fc5.linear], g.fc5, **tg),
+        S("fc6", "sine", "h5", 0, lw, "h6", 0, [g.fc6.linear], g.fc6, **tg),
+        S("fc7", "sine", "h6", 0, lw, "h7", 0, [g.fc7.linear], g.fc7, **tg),
+        S("fc8", "sine", "h7", 0, lw, "h8", 0, [g.fc8.linear], g.fc8, **tg),
+        S("fc9", "sine", "h8", 0, lw, "cats1", 0, [g.fc9.linear], g.fc9, **tg),
+    ]
+    lw2 = g.fc9.linear.out_features
+    pos = S("pos", "linear", "cats1", 0, lw2, "pos", 0, [g.fc10Sigma, g.fc10Col], **tg)
+    sigma = S("sigma", "linear", "cats1", 0, lw2, "pos", 0, [g.fc10Sigma], **tg)
+    color = S("color", "linear", "cats1", 0, lw2, "pos", 0, [g.fc10Col], **tg)
+    solar = [
+        S("fc_solar_1", "sine", "cats1", 0, lw2 + 32, "s1", 0, [g.fc_solar_1.linear], g.fc_solar_1, need_dx=(mode == "full")),
+        S("fc_solar_2", "sine", "s1", 0, lw2, "s2", 0, [g.fc_solar_2.linear], g.fc_solar_2),
+        S("fc_solar_3", "sine", "s2", 0, lw2, "s3", 0, [g.fc_solar_3.linear], g.fc_solar_3),
+        S("fc_solar_4", "linear", "s3", 0, lw2, "vis", 0, [g.fc_solar_4]),
+    ]
+    sky = [
+        S("fc_sky_color_1", "sine", "senc", 0, 32, "k1", 0, [g.fc_sky_color_1.linear], g.fc_sky_color_1, need_dx=False),
+        S("fc_sky_color_2", "linear", "k1", 0, g.fc_sky_color_1.linear.out_features, "sky", 0, [g.fc_sky_color_2]),
+    ]
+    time = [
+        S("time_layer_1", "sine", "tenc", 0, 16, "t1", 0, [net.time_layer_1.linear], net.time_layer_1, need_dx=False),
+        S("time_layer_2", "sine", "t1", 0, lw, "t2", 0, [net.time_layer_2.linear], net.time_layer_2),
+        S("get_class_layer", "linear", "t2", 0, lw, "cls", 0, [net.get_class_layer]),
+    ]
+    adjust = [
+        S("adjust_layer_1", "sine", "cats1", 0, lw2, "a1", 0, [net.adjust_layer_1.linear], net.adjust_layer_1),
+        S("adjust_layer_2", "sine", "a1", 0, lw, "a2", 0, [net.adjust_layer_2.linear], net.adjust_layer_2),
+        S("adjust_layer_3", "sine", "a2", 0, lw, "a3", 0, [net.adjust_layer_3.linear], net.adjust_layer_3),
+        S("adjust_col", "linear", "a3", 0, lw, "adj", 0, [net.adjust_col]),
+    ]
+    if mode == "full":
+        # solar branch of the image pass is forward-only in effect (vis is detached by the caller's colour
+        # formula when not classic) but autograd decides: gradients flow if vis_raw receives one.
+        return trunk + [pos] + solar + sky + time + adjust, ("pos", "vis", "adj", "sky", "cls")
+    if mode == "solar":
+        return trunk + [sigma] + solar + sky, ("pos", "vis", "sky")
+    if mode == "sigma":
+        return trunk + [sigma], ("pos",)
+    if mode == "color":
+        return trunk + [color], ("pos",)
+    if mode == "position":
+        return trunk + [pos], ("pos", "cats1")
+    if mode == "class":
+        return time, ("cls",)
+    if mode == "adjust":
+        adjust[0] = S("adjust_layer_1", "sine", "x", 0, lw2, "a1", 0, [net.adjust_layer_1.linear], net.adjust_layer_1)
+        return adjust, ("adj",)
+    raise ValueError(mode)
+
+
+_RAY_BUFS = ("senc", "k1", "sky", "tenc", "t1", "t2", "cls")
+
+
+class _Pass:
+    """One forward (and optionally backward) sweep over a layer schedule with explicit buffers."""
+
+    def __init__(self, net, mode, precision):
+        self.net, self.mode = net, mode
+        self.dt = t.bfloat16 if precision == "bf16" else t.float32
+        self.specs, self.outs = _plan(net, mode)
+        self.saved = {}
+        self.bufs = {}
+
+    # -- weights in compute dtype, K padded to the buffer width (zero columns) --
+    def _wc(self, spec):
+        W = t.cat([l.weight for l in spec.lin], 0) if len(spec.lin) > 1 else spec.lin[0].weight
+        Wc = t.zeros(W.shape[0], spec.kp, device=W.device, dtype=self.dt)
+        ops.convert(W.detach(), Wc[:, :W.shape[1]])
+        b = t.cat([l.bias for l in spec.lin], 0) if len(spec.lin) > 1 else spec.lin[0].bias
+        return Wc, b.detach().float().contiguous()
+
+    def _buf(self, name, rows, width, dtype=None, zero=False):
+        if name not in self.bufs:
+            mk = t.zeros if zero else t.empty
+            self.bufs[name] = mk(rows, width, device=self.dev, dtype=dtype or self.dt)
+        return self.bufs[name]
+
+    def _width(self, name):
+        lw = getattr(self.net, "layer_width", None)
+        if name == "cat5":
+            return lw + 64
+        if name == "cats1":
+            return lw // 2 + 32
+        raise KeyError(name)
+
+    def forward(self, X, sun, time, S, keep):
+        net = self.net
+        self.keep = keep
+        self.x_requires_grad = bool(X is not None and X.requires_grad and self.mode in ("single", "adjust"))
+        dev = self.dev = (X if X is not None else time).device
+        self.S = S
+        M = X.shape[0] if X is not None else 0
+        N = (M // S) if X is not None else time.shape[0]
+        self.M, self.N = M, N
+        training = net.training
+        names = {s.name for s in self.specs}
+        if self.mode == "single":
+            L = net.layer
+            xin = self._buf("x", M, _r8(L.in_features), zero=True)
+            ops.convert(X.float(), xin[:, :L.in_features])
+        elif self.mode == "adjust":
+            xin = self._buf("x", M, X.shape[1])
+            ops.convert(X.float().contiguous(), xin)
+        elif "fc1" in names:
+            g = net.G_NeRF_net
+            cat5 = self._buf("cat5", M, self._width("cat5"))
+            ops.pe_encode(X.float().contiguous(), g._expand_size_pose, cat5, col0=net.layer_width, pad_to=64)
+            self._buf("cats1", M, self._width("cats1"))
+        if "fc_solar_1" in names:
+            sun = sun.float().contiguous()
+            sun_pts = sun if S == 1 else sun.repeat_interleave(S, 0)
+            ops.pe_encode(sun_pts, net.G_NeRF_net._expand_size_solar_angle, self.bufs["cats1"], col0=net.layer_width // 2, pad_to=32)
+            senc = self._buf("senc", N, 32)
+            ops.pe_encode(sun, net.G_NeRF_net._expand_size_solar_angle, senc, pad_to=32)
+        if "time_layer_1" in names:
+            tenc = self._buf("tenc", N, 16)
+            ops.pe_encode(time[:, 0:2].float().contiguous(), 2, tenc, pad_to=16)
+        for sp in self.specs:
+            rows = N if sp.out in _RAY_BUFS else M
+            Xv = self.bufs[sp.inp][:, sp.in_col0:sp.in_col0 + sp.kp]
+            Wc, b = self._wc(sp)
+            n_out = sp.n_out
+            if sp.kind == "linear":
+                out = self._buf(sp.out, rows, 16 if n_out <= 16 else _r8(n_out), dtype=t.float32)
+                ops.gemm(Xv, Wc, out[:, :n_out], bias=b, alpha=1.0)
+                if keep and sp.grad:
+                    self.saved[sp.name] = (Wc,)
+                continue
+            Z = t.empty(rows, n_out, device=dev, dtype=self.dt)
+            ops.gemm(Xv, Wc, Z, bias=b, alpha=OMEGA_0)
+            a, c, mean, invstd = self._affine(sp.layer, Z, rows, training)
+            if sp.out in ("cat5", "cats1"):
+                Y = self.bufs[sp.out][:, sp.out_col0:sp.out_col0 + n_out]
+            else:
+                Y = self._buf(sp.out, rows, n_out)
+            ops.sine_fwd(Z, a, c, Y)
+            if keep and sp.grad:
+                self.saved[sp.name] = (Wc, Z, a, c, mean, invstd)
+        res = []
+        for o in self.outs:
+            if o == "cats1":
+                res.append(self.bufs["cats1"][:, :net.layer_width // 2].float())
+            elif o in ("pos", "vis", "adj", "sky", "cls"):
+                sp = [s for s in self.specs if s.out == o][0]
+                res.append(self.bufs[o][:, :sp.n_out])
+            else:
+                res.append(self.bufs[o].float())
+        if self.mode == "single":
+            res = [self.bufs["y"].float()]
+        if not keep:
+            self.bufs = {k: v for k, v in self.bufs.items() if k in ("pos", "vis", "adj", "sky", "cls", "y")}
+        return res
+
+    def _affine(self, layer, Z, rows, training):
+        """fold BatchNorm1d(momentum=.01, eps=1e-5) into y = a*z + c  (misc.py:169-170)."""
+        dev = Z.device
+        n = Z.shape[1]
+        if not layer.has_bn:
+            return t.ones(n, device=dev), t.zeros(n, device=dev), None, None
+        bn = layer.norm
+        if training:
+            s, ss = ops.col_stats(Z)
+            mean = s / rows
+            var = t.clamp(ss / rows - mean * mean, min=0.0)
+            with t.no_grad():
+                m = bn.momentum
+                bn.running_mean.mul_(1 - m).add_(mean.float() * m)
+                bn.running_var.mul_(1 - m).add_((var * (rows / max(rows - 1, 1))).float() * m)
+                bn.num_batches_tracked += 1
+            invstd = (1.0 / t.sqrt(var + bn.eps)).float()
+            mean = mean.float()
+        else:
+            mean = bn.running_mean.detach().float()
+            invstd = 1.0 / t.sqrt(bn.running_var.detach().float() + bn.eps)
+        a = bn.weight.detach().float() * invstd
+        c = bn.bias.detach().float() - mean * a
+        return a.contiguous(), c.contiguous(), mean.contiguous(), invstd.contiguous()
+
+    # ------------------------------------------------------------------------------------------------------
+    def backward(self, gouts):
+        """gouts: gradients of self.outs (None allowed).  Returns {parameter: grad}."""
+        net, dt, dev = self.net, self.dt, self.dev
+        training = net.training
+        grads = {}
+        gbuf = {}   # activation-gradient buffers keyed by buffer name
+
+        def gb(name, rows, width):
+            if name not in gbuf:
+                gbuf[name] = t.zeros(rows, width, device=dev, dtype=dt)
+            return gbuf[name]
+
+        gout = dict(zip(self.outs, gouts))
+        if self.mode == "single" and gouts[0] is not None:
+            ops.convert(gouts[0].float().contiguous(), gb("y", self.M, gouts[0].shape[1]))
+        if gout.get("cats1") is not None:   # forward_Position's X_Encode output carries a gradient
+            G = gb("cats1", self.M, self.bufs["cats1"].shape[1])
+            ops.convert(gout["cats1"].float().contiguous(), G[:, :net.layer_width // 2])
+        for sp in reversed(self.specs):
+            if not sp.grad or sp.name not in self.saved:
+                continue
+            rows = self.N if sp.out in _RAY_BUFS else self.M
+            n_out = sp.n_out
+            Xv = self.bufs[sp.inp][:, sp.in_col0:sp.in_col0 + sp.kp]
+            if sp.kind == "linear":
+                g = gout.get(sp.out)
+                if g is None:
+                    continue
+                (Wc,) = self.saved[sp.name]
+                dZ = t.zeros(rows, 16 if n_out <= 16 else _r8(n_out), device=dev, dtype=dt)
+                ops.convert(g.float().contiguous(), dZ[:, :n_out])
+                dZv = dZ[:, :n_out]
+                alpha = 1.0
+                bn_train = False
+            else:
+                if sp.out not in gbuf:
+                    continue
+                Wc, Z, a, c, mean, invstd = self.saved[sp.name]
+                dY = gbuf[sp.out][:, sp.out_col0:sp.out_col0 + n_out]
+                dZ = t.empty(rows, n_out, device=dev, dtype=dt)
+                bn_train = sp.layer.has_bn and training
+                if bn_train:
+                    sg, sgx = ops.sine_bwd_reduce(dY, Z, a, c, mean, invstd)
+                    bn = sp.layer.norm
+                    self._acc(grads, bn.weight, sgx.float())
+                    self._acc(grads, bn.bias, sg.float())
+                    ops.sine_bwd_apply(dY, Z, a, c, dZ, mean, invstd, (sg / rows).float().contiguous(),
+                                       (sgx / rows).float().contiguous())
+                else:
+                    if sp.layer.has_bn:  # eval-mode BN: plain affine, parameters still get gradients
+                        sg, sgx = ops.sine_bwd_reduce(dY, Z, a, c, mean, invstd)
+                        self._acc(grads, sp.layer.norm.weight, sgx.float())
+                        self._acc(grads, sp.layer.norm.bias, sg.float())
+                    ops.sine_bwd_apply(dY, Z, a, c, dZ)
+                dZv = dZ
+                alpha = OMEGA_0
+            # bias gradient: alpha * column sums of dZ (analytically zero in front of a train-mode BatchNorm)
+            if bn_train:
+                db = t.zeros(n_out, device=dev)
+            else:
+                db = alpha * ops.col_stats(dZv)[0].float()
+            # weight gradient dW[n_out, kp] = alpha * dZ^T . X   (split-K, fp32 atomics into zeros)
+            dW = t.zeros(n_out, sp.kp, device=dev, dtype=t.float32)
+            ops.gemm(dZv, Xv, dW, alpha=alpha, accumulate=2, a_t=True, b_t=True)
+            r0 = 0
+            for lin in sp.lin:
+                r1 = r0 + lin.out_features
+                self._acc(grads, lin.weight, dW[r0:r1, :lin.in_features])
+                self._acc(grads, lin.bias, db[r0:r1])
+                r0 = r1
+            # input gradient dX[rows, kin] (+)= alpha * dZ . W
+            if (sp.need_dx and sp.inp != "x") or (sp.inp == "x" and self.x_requires_grad):
+                kin = sp.kp if sp.inp not in ("cat5", "cats1") else (net.layer_width if sp.inp == "cat5" else net.layer_width // 2)
+                first = sp.inp not in gbuf
+                width = self.bufs[sp.inp].shape[1]
+                G = gb(sp.inp, rows, width)
+                ops.gemm(dZv, Wc[:, :kin], G[:, sp.in_col0:sp.in_col0 + kin], alpha=alpha, accumulate=0 if first else 1, b_t=True)
+        self.gbuf = gbuf
+        return grads
+
+    @staticmethod
+    def _acc(grads, p, g):
+        if not p.requires_grad:
+            return
+        g = g.reshape(p.shape).to(p.dtype)
+        grads[p] = g if p not in grads else grads[p] + g
+
+
+class _NetFn(t.autograd.Function):
+    @staticmethod
+    def forward(ctx, run, X, sun, time, S, n_params, *params):
+        outs = run.forward(X, sun, time, S, keep=True)
+        ctx.run = run
+        ctx.params = params
+        ctx.x_cols = X.shape[1] if run.x_requires_grad else 0
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        run = ctx.run
+        grads = run.backward(gouts)
+        gx = run.gbuf["x"][:, :ctx.x_cols].float() if (ctx.x_cols and "x" in run.gbuf) else None
+        run.saved.clear()
+        run.bufs.clear()
+        return (None, gx, None, None, None, None) + tuple(grads.get(p) for p in ctx.params)
+
+
+def _run(net, mode, X, sun, time, S, precision=None):
+    """Dispatch one network pass.  Fails loudly for non-CUDA tensors: there is no CPU path."""
+    probe = X if X is not None else time
+    if not probe.is_cuda:
+        raise ops._lib.SeasonNerfCudaError("season_nerf_b200.T_NeRF runs on CUDA only (got a %s tensor); "
+                                           "move the module and its inputs to the GPU" % probe.device)
+    precision = precision or getattr(net, "precision", "bf16")
+    run = _Pass(net, mode, precision)
+    params = [p for p in net.parameters()]
+    need_grad = t.is_grad_enabled() and (any(p.requires_grad for p in params) or (X is not None and X.requires_grad))
+    if not need_grad:
+        with t.no_grad():
+            return run.forward(X, sun, time, S, keep=False)
+    return _NetFn.apply(run, X, sun, time, S, len(params), *params)

@@ -1,0 +1,218 @@
+"""Tensor-level wrappers over the C ABI (include/season_nerf_b200.h).  torch is used only for device memory,
+streams and autograd bookkeeping; every arithmetic op on the hot path is a kernel of the sm_100a library.
+All wrappers require CUDA tensors: there is no CPU fallback."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, F64, check
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16, torch.float64: F64}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _cuda(t, dtype=None, name="tensor"):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.SeasonNerfCudaError("season_nerf_b200: %s must be a CUDA tensor (no CPU fallback)" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    return t
+
+
+def _mat(t, name="matrix"):
+    """2-D, unit inner stride, arbitrary row pitch -> (tensor, ld)."""
+    _cuda(t, name=name)
+    if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise ValueError("%s must be 2-D with contiguous rows" % name)
+    ld = t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+    return t, int(ld)
+
+
+# ---- sampling ------------------------------------------------------------------------------------------
+def sample_rays(top, bot, ts, zero_oob=False, want_pts=True):
+    """misc.py:234-261.  top, bot [N,3] f32; ts [S] f32 (host-built like the reference) -> pts [N,S,3], deltas [N,S]."""
+    top = _cuda(top, torch.float32, "top").contiguous()
+    bot = _cuda(bot, torch.float32, "bot").contiguous()
+    ts = _cuda(ts, torch.float32, "ts").contiguous()
+    N, S = top.shape[0], ts.shape[0]
+    pts = torch.empty(N, S, 3, device=top.device, dtype=torch.float32) if want_pts else None
+    deltas = torch.empty(N, S, device=top.device, dtype=torch.float32)
+    check(_lib.load().snb_sample_rays(_ptr(top), _ptr(bot), _ptr(ts), N, S, int(zero_oob), _ptr(pts), _ptr(deltas), _stream()))
+    return pts, deltas
+
+
+def solar_tops(pts, sun_vec, f64=True):
+    """mg_Img_Eval.py:57-60 (f64) / Eval_Tools_2.py:255-258 (f32).  pts [M,3] -> tops [M,3]."""
+    pts = _cuda(pts, torch.float32, "pts").contiguous().reshape(-1, 3)
+    sun = (C.c_double * 3)(*[float(v) for v in sun_vec])
+    tops = torch.empty_like(pts)
+    check(_lib.load().snb_solar_tops(_ptr(pts), pts.shape[0], sun, int(f64), _ptr(tops), _stream()))
+    return tops
+
+
+def march_transmittance(rho, deltas):
+    rho = _cuda(rho, torch.float32).contiguous()
+    deltas = _cuda(deltas, torch.float32).contiguous()
+    S = rho.shape[-1]
+    Mrows = rho.numel() // S
+    out = torch.empty(Mrows, device=rho.device, dtype=torch.float32)
+    check(_lib.load().snb_march_transmittance(_ptr(rho), _ptr(deltas), Mrows, S, _ptr(out), _stream()))
+    return out
+
+
+# ---- compositing ---------------------------------------------------------------------------------------
+def composite_fwd(rho, deltas, col, vis, sky, classic=False, want_pv=True):
+    """rho, deltas, vis [N,S]; col [N,S,3]; sky [N,3] or [N,S,3] -> dict (Eval_Tools_2.py:187-215)."""
+    N, S = rho.shape
+    per_sample = sky.dim() == 3
+    dev = rho.device
+    mk = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+    PV, PE, PS = (mk(N, S), mk(N, S), mk(N, S)) if want_pv else (None, None, None)
+    albedo, rendered, vsum = mk(N, 3), mk(N, 3), mk(N)
+    check(_lib.load().snb_composite_fwd(_ptr(rho), _ptr(deltas), _ptr(col), _ptr(vis), _ptr(sky), int(per_sample), N, S,
+                                        int(classic), _ptr(PV), _ptr(PE), _ptr(PS), _ptr(albedo), _ptr(rendered),
+                                        _ptr(vsum), _stream()))
+    return PV, PE, PS, albedo, rendered, vsum
+
+
+class _Composite(torch.autograd.Function):
+    """Alpha compositing with the transmittance scan; vis is detached unless classic (Eval_Tools_2.py:214)."""
+
+    @staticmethod
+    def forward(ctx, rho, deltas, col, vis, sky, classic):
+        rho, deltas, col, vis, sky = [_cuda(x, torch.float32).contiguous() for x in (rho, deltas, col, vis, sky)]
+        PV, PE, PS, albedo, rendered, vsum = composite_fwd(rho, deltas, col, vis, sky, classic)
+        ctx.save_for_backward(rho, deltas, col, vis, sky)
+        ctx.classic = classic
+        ctx.mark_non_differentiable(vsum)
+        return PV, PE, PS, albedo, rendered, vsum
+
+    @staticmethod
+    def backward(ctx, dPV, dPE, dPS, d_albedo, d_rendered, _dvs):
+        rho, deltas, col, vis, sky = ctx.saved_tensors
+        N, S = rho.shape
+        per_sample = sky.dim() == 3
+        c = lambda g: None if g is None else g.contiguous()
+        dPV, dPE, dPS, d_albedo, d_rendered = c(dPV), c(dPE), c(dPS), c(d_albedo), c(d_rendered)
+        d_rho, d_col = torch.empty_like(rho), torch.empty_like(col)
+        d_sky = torch.zeros_like(sky)
+        d_vis = torch.zeros_like(vis) if ctx.classic else None
+        check(_lib.load().snb_composite_bwd(_ptr(rho), _ptr(deltas), _ptr(col), _ptr(vis), _ptr(sky), int(per_sample), N, S,
+                                            int(ctx.classic), _ptr(d_rendered), _ptr(d_albedo), _ptr(dPE), _ptr(dPV),
+                                            _ptr(dPS), _ptr(d_rho), _ptr(d_col), _ptr(d_sky), _ptr(d_vis), _stream()))
+        return d_rho, None, d_col, d_vis, d_sky, None
+
+
+def composite(rho, deltas, col, vis, sky, classic=False):
+    """-> PV, PE, PS [N,S], albedo [N,3], rendered [N,3], vis_sum [N]; differentiable in rho, col, sky (and vis if classic)."""
+    return _Composite.apply(rho, deltas, col, vis, sky, bool(classic))
+
+
+def cli_composite(rho, deltas, base, vis, adj, cls, exact_vis=None):
+    """mg_Img_Eval.py:123-190 sums in float64.  Inputs f32 or f64 device tensors; cls [C] f64."""
+    N, S = rho.shape[0], rho.shape[1]
+    Cn = adj.shape[2]
+    dt = _DT[rho.dtype]
+    dev = rho.device
+    mk = lambda *s: torch.empty(*s, device=dev, dtype=torch.float64)
+    base_img, season, extreme, raw = mk(N, 3), mk(N, 3), mk(Cn, N, 3), mk(N)
+    raw_e = mk(N) if exact_vis is not None else None
+    ins = [x.contiguous() for x in (rho, deltas, base, vis, adj)]
+    ev = None if exact_vis is None else exact_vis.contiguous()
+    cls = _cuda(cls, torch.float64).contiguous()
+    check(_lib.load().snb_cli_composite(*[_ptr(x) for x in ins], _ptr(cls), _ptr(ev), dt, N, S, Cn, _ptr(base_img),
+                                        _ptr(season), _ptr(extreme), _ptr(raw), _ptr(raw_e), _stream()))
+    return base_img, season, extreme, raw, raw_e
+
+
+def year_sweep(rho, deltas, base, adj, cls):
+    """mg_Img_Eval.py:192-228 recombination for T class vectors at once -> [T,N,3] f64."""
+    N, S = rho.shape[0], rho.shape[1]
+    Cn, T = adj.shape[2], cls.shape[0]
+    out = torch.empty(T, N, 3, device=rho.device, dtype=torch.float64)
+    ins = [x.contiguous() for x in (rho, deltas, base, adj)]
+    cls = _cuda(cls, torch.float64).contiguous()
+    check(_lib.load().snb_year_sweep(*[_ptr(x) for x in ins], _ptr(cls), _DT[rho.dtype], N, S, Cn, T, _ptr(out), _stream()))
+    return out
+
+
+# ---- dense-layer building blocks -------------------------------------------------------------------------
+def pe_encode(x, n_freq, out, col0=0, pad_to=None):
+    """misc.py:105-139 into columns [col0, col0+D*(2n+1)) of `out` (zero padded to pad_to columns)."""
+    x, ldx = _mat(_cuda(x, torch.float32, "x"))
+    out, ldo = _mat(out, "out")
+    D = x.shape[1]
+    width = D * (2 * n_freq + 1)
+    pad_to = width if pad_to is None else pad_to
+    check(_lib.load().snb_pe_encode(_ptr(x), ldx, x.shape[0], D, n_freq, _ptr(out), _DT[out.dtype], ldo, col0, pad_to, _stream()))
+    return out
+
+
+def gemm(A, B, out, bias=None, alpha=1.0, accumulate=0, a_t=False, b_t=False):
+    """out[M,N] = alpha*(A.B^T + bias) (+out).  a_t: A stored [K,M]; b_t: B stored [K,N].
+    accumulate: 0 store, 1 add, 2 split-K atomic add into a pre-zeroed f32 `out`."""
+    A, lda = _mat(A, "A")
+    B, ldb = _mat(B, "B")
+    out, ldc = _mat(out, "out")
+    if A.dtype != B.dtype:
+        raise TypeError("gemm operands must share a dtype")
+    M, N = out.shape
+    K = A.shape[0] if a_t else A.shape[1]
+    Kb = B.shape[0] if b_t else B.shape[1]
+    if K != Kb or (A.shape[1] if a_t else A.shape[0]) != M or (B.shape[1] if b_t else B.shape[0]) != N:
+        raise ValueError("gemm shape mismatch: A%s B%s out%s a_t=%s b_t=%s" % (tuple(A.shape), tuple(B.shape), tuple(out.shape), a_t, b_t))
+    if bias is not None:
+        _cuda(bias, torch.float32, "bias")
+    check(_lib.load().snb_gemm(_ptr(A), lda, int(a_t), _ptr(B), ldb, int(b_t), _ptr(out), ldc, _ptr(bias), float(alpha),
+                               int(accumulate), M, N, K, _DT[A.dtype], _DT[out.dtype], _stream()))
+    return out
+
+
+def col_stats(Z):
+    """-> (sum[N], sumsq[N]) float64 over the rows of Z."""
+    Z, ldz = _mat(Z, "Z")
+    N = Z.shape[1]
+    s = torch.empty(2, N, device=Z.device, dtype=torch.float64)
+    check(_lib.load().snb_col_stats(_ptr(Z), _DT[Z.dtype], ldz, Z.shape[0], N, _ptr(s[0]), _ptr(s[1]), _stream()))
+    return s[0], s[1]
+
+
+def sine_fwd(Z, a, c, Y):
+    Z, ldz = _mat(Z, "Z")
+    Y, ldy = _mat(Y, "Y")
+    check(_lib.load().snb_sine_fwd(_ptr(Z), ldz, _ptr(a), _ptr(c), _ptr(Y), ldy, Z.shape[0], Z.shape[1], _DT[Z.dtype], _stream()))
+    return Y
+
+
+def sine_bwd_reduce(dY, Z, a, c, mean, invstd):
+    dY, ldd = _mat(dY, "dY")
+    Z, ldz = _mat(Z, "Z")
+    N = Z.shape[1]
+    s = torch.empty(2, N, device=Z.device, dtype=torch.float64)
+    check(_lib.load().snb_sine_bwd_reduce(_ptr(dY), ldd, _ptr(Z), ldz, _ptr(a), _ptr(c), _ptr(mean), _ptr(invstd), Z.shape[0],
+                                          N, _DT[Z.dtype], _ptr(s[0]), _ptr(s[1]), _stream()))
+    return s[0], s[1]
+
+
+def sine_bwd_apply(dY, Z, a, c, dZ, mean=None, invstd=None, k1=None, k2=None):
+    dY, ldd = _mat(dY, "dY")
+    Z, ldz = _mat(Z, "Z")
+    dZ, ldo = _mat(dZ, "dZ")
+    check(_lib.load().snb_sine_bwd_apply(_ptr(dY), ldd, _ptr(Z), ldz, _ptr(a), _ptr(c), _ptr(mean), _ptr(invstd), _ptr(k1),
+                                         _ptr(k2), _ptr(dZ), ldo, Z.shape[0], Z.shape[1], _DT[Z.dtype], _stream()))
+    return dZ
+
+
+def convert(src, dst):
+    src, lds = _mat(src, "src")
+    dst, ldd = _mat(dst, "dst")
+    check(_lib.load().snb_convert(_ptr(src), _DT[src.dtype], lds, _ptr(dst), _DT[dst.dtype], ldd, src.shape[0], src.shape[1], _stream()))
+    return dst

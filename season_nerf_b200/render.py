@@ -1,0 +1,219 @@
+"""CLI render engine: drop-in for T_NeRF_Eval_Utils/mg_Img_Eval.py:17-228 (_internal_render,
+component_render_by_P, component_render_by_dir, get_imgs_from_Img_Dict, get_imgs_from_Img_Dict_t_step).
+
+Same arguments and the same dict of per-sample component arrays (float64 numpy on access, as downstream numpy code
+expects).  The components stay resident in HBM as float32 (`DeviceImgDict`), so compositing and the year sweep run
+on the device without the six D2H copies per chunk of the reference; float64 host arrays are materialised lazily,
+only for the keys a caller actually touches.
+"""
+import numpy as np
+import torch as t
+
+from . import ops
+from .engine import sample_ts
+from .geometry import encode_time, world_angle_2_local_vec
+
+_KEYS = ["World_Points", "Deltas", "Rho", "Base_Col", "Est_Solar_Vis", "Sky_Col", "Output_class", "Adjust_col"]
+
+
+class DeviceImgDict(dict):
+    """dict of float64 numpy arrays backed by float32 device tensors (converted on first access)."""
+
+    def __init__(self, dev_tensors, host_items=None):
+        super().__init__()
+        self.dev = dict(dev_tensors)
+        for k in self.dev:
+            dict.__setitem__(self, k, None)
+        for k, v in (host_items or {}).items():
+            dict.__setitem__(self, k, v)
+
+    def __getitem__(self, k):
+        v = dict.__getitem__(self, k)
+        if v is None and k in self.dev:
+            v = self.dev[k].detach().cpu().numpy().astype(np.float64)
+            dict.__setitem__(self, k, v)
+        return v
+
+    def get(self, k, default=None):
+        return self[k] if k in self else default
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
+
+    def values(self):
+        return [self[k] for k in self.keys()]
+
+    def __setitem__(self, k, v):
+        self.dev.pop(k, None)      # a caller-modified array is the truth from now on
+        dict.__setitem__(self, k, v)
+
+
+def _points_per_call(the_network):
+    return 1 << 22 if getattr(the_network, "_fused_ready", lambda: False)() else 1 << 19
+
+
+def _internal_render(the_network, tops, bots, a_sun_el_az_vec, a_year_frac, out_img_size, max_batch_size,
+                     include_exact_solar, device):
+    """mg_Img_Eval.py:17-72.  `max_batch_size` is accepted for compatibility; chunking is by device memory."""
+    device = t.device(device)
+    if device.type != "cuda":
+        raise ops._lib.SeasonNerfCudaError("season_nerf_b200 renders on CUDA only (no CPU fallback)")
+    S = out_img_size[2]
+    C = the_network.n_classes
+    N = tops.shape[0]
+    tops = tops.to(device=device, dtype=t.float32)
+    bots = bots.to(device=device, dtype=t.float32)
+    sun_np = np.asarray(a_sun_el_az_vec, dtype=np.float64)
+    sun = t.tensor(sun_np, dtype=t.float32, device=device).reshape(1, 3)           # .float() of the f64 vector (:43)
+    tim = t.tensor(encode_time(a_year_frac), dtype=t.float32, device=device).reshape(1, 4)
+    ts = sample_ts(S, eval_mode=True, include_end_pt=True).to(device)
+    mk = lambda *s: t.empty(*s, device=device, dtype=t.float32)
+    out = {"World_Points": mk(N, S, 3), "Deltas": mk(N, S, 1), "Rho": mk(N, S, 1), "Base_Col": mk(N, S, 3),
+           "Est_Solar_Vis": mk(N, S, 1), "Sky_Col": mk(N, S, 3), "Output_class": mk(N, S, C), "Adjust_col": mk(N, S, C, 3)}
+    if include_exact_solar:
+        out["Exact_Solar"] = mk(N, S, 1)
+    step = max(1, _points_per_call(the_network) // S)
+    step_exact = max(1, _points_per_call(the_network) // (S * S))
+    with t.no_grad():
+        for i in range(0, N, step):
+            e = min(i + step, N)
+            n = e - i
+            pts, deltas = ops.sample_rays(tops[i:e], bots[i:e], ts, zero_oob=True)           # :40-42
+            pos, vis, adj, sky, cl = the_network.forward_rays(pts.reshape(-1, 3), sun.expand(n, 3), tim.expand(n, 4), S)
+            out["World_Points"][i:e] = pts
+            out["Deltas"][i:e] = deltas.unsqueeze(-1)
+            out["Rho"][i:e] = the_network.Softplus(pos[:, 0:1]).reshape(n, S, 1)
+            out["Base_Col"][i:e] = pos[:, 1:4].reshape(n, S, 3)
+            out["Est_Solar_Vis"][i:e] = the_network.Sigmoid(vis).reshape(n, S, 1)
+            out["Sky_Col"][i:e] = the_network.Sigmoid(sky).reshape(n, 1, 3)
+            out["Output_class"][i:e] = the_network.SoftMax(cl).reshape(n, 1, C)
+            out["Adjust_col"][i:e] = adj.reshape(n, S, C, 3)
+        if include_exact_solar:                                                               # :57-70
+            for i in range(0, N, step_exact):
+                e = min(i + step_exact, N)
+                nb = out["World_Points"][i:e].reshape(-1, 3)
+                nt = ops.solar_tops(nb, sun_np, f64=True)
+                _, nd = ops.sample_rays(nt, nb, ts, zero_oob=True, want_pts=False)
+                rho = _sigma_on_rays(the_network, nt, nb, ts, S)
+                out["Exact_Solar"][i:e] = ops.march_transmittance(rho, nd).reshape(e - i, S, 1)
+    return DeviceImgDict(out)
+
+
+def _sigma_on_rays(the_network, tops, bots, ts, S):
+    """softplus(sigma) at the S samples of each (top, bot) ray -> [n, S] (T_NeRF_net_v2.py:169-170)."""
+    pts, _ = ops.sample_rays(tops, bots, ts)
+    rho_raw = the_network.forward_rays(pts.reshape(-1, 3), None, None, S, mode="sigma")[0]
+    return the_network.Softplus(rho_raw).reshape(-1, S).contiguous()
+
+
+def component_render_by_dir(the_network, view_el_az, sun_el_az, time_frac, out_img_size: tuple, W2C, W2L_H, device,
+                            max_batch_size=150000, include_exact_solar=True):
+    """mg_Img_Eval.py:96-115."""
+    H, W = out_img_size[0], out_img_size[1]
+    with t.no_grad():
+        XYZ = np.stack(np.meshgrid(np.linspace(1, -1, H), np.linspace(-1, 1, W), indexing="ij"), -1).reshape([-1, 2])
+        XYZ = np.concatenate([XYZ, np.zeros([XYZ.shape[0], 1])], 1)
+        view_vec = world_angle_2_local_vec(view_el_az[0], view_el_az[1], W2C, W2L_H)
+        sun_vec = world_angle_2_local_vec(sun_el_az[0], sun_el_az[1], W2C, W2L_H)
+        tops = t.tensor(XYZ + np.expand_dims(view_vec / view_vec[2], 0)).float()
+        bots = t.tensor(XYZ - np.expand_dims(view_vec / view_vec[2], 0)).float()
+        R = _internal_render(the_network, tops, bots, sun_vec, time_frac, out_img_size, max_batch_size,
+                             include_exact_solar, device)
+        R["Image_Points"] = np.stack(np.meshgrid(np.arange(H), np.arange(W), indexing="ij"), -1).reshape([-1, 2])
+    return R
+
+
+def component_render_by_P(the_network, a_P_img, out_img_size: tuple, device, max_batch_size=150000,
+                          include_exact_solar=True):
+    """mg_Img_Eval.py:74-94 (a_P_img: the reference's P_img object: .img, .invert_P, .sun_el_and_az_vec, .get_year_frac)."""
+    with t.no_grad():
+        XY = np.stack(np.meshgrid(np.linspace(0, a_P_img.img.shape[0] - 1, out_img_size[0]),
+                                  np.linspace(0, a_P_img.img.shape[1] - 1, out_img_size[1]), indexing="ij"), -1)
+        XY = np.round(XY).astype(int).reshape([-1, 2])
+        x, y, z = a_P_img.invert_P(XY[:, 0], XY[:, 1], 1.)
+        tops = np.stack([x, y, np.ones_like(x)], -1)
+        x, y, z = a_P_img.invert_P(XY[:, 0], XY[:, 1], -1.)
+        bots = np.stack([x, y, -np.ones_like(x)], -1)
+        good = (tops[:, 0] >= -1) * (tops[:, 1] <= 1) * (bots[:, 0] >= -1) * (bots[:, 1] <= 1) * \
+               (tops[:, 1] >= -1) * (tops[:, 0] <= 1) * (bots[:, 1] >= -1) * (bots[:, 0] <= 1)
+        R = _internal_render(the_network, t.tensor(tops[good]).float(), t.tensor(bots[good]).float(),
+                             a_P_img.sun_el_and_az_vec, a_P_img.get_year_frac(), out_img_size, max_batch_size,
+                             include_exact_solar, device)
+        R["Image_Points_in_GT_Img"] = XY[good]
+        R["Image_Points"] = np.stack(np.meshgrid(np.arange(out_img_size[0]), np.arange(out_img_size[1]),
+                                                 indexing="ij"), -1).reshape([-1, 2])[good]
+    return R
+
+
+def sig(X):
+    return 1 / (1 + np.exp(-X))
+
+
+def inv_sig(X):
+    return -np.log(1 / X - 1)
+
+
+def _device_components(D, keys):
+    """float32 device tensors if the dict is ours and untouched, else float64 uploads of the caller's arrays."""
+    if isinstance(D, DeviceImgDict) and all(k in D.dev for k in keys):
+        return [D.dev[k] for k in keys]
+    if not t.cuda.is_available():
+        raise ops._lib.SeasonNerfCudaError("season_nerf_b200 composites on CUDA only (no CPU fallback)")
+    return [t.as_tensor(np.ascontiguousarray(D[k]), dtype=t.float64).cuda() for k in keys]
+
+
+def _scatter(D, size, vals):
+    vals = vals.detach().cpu().numpy()
+    img = np.zeros([size[0], size[1]] + list(vals.shape[1:])) * np.nan
+    img[D["Image_Points"][:, 0], D["Image_Points"][:, 1]] = vals
+    return img
+
+
+def get_imgs_from_Img_Dict(Img_Dict, out_img_size: tuple, use_classic_shadows: bool):
+    """mg_Img_Eval.py:123-190: float64 compositing of the cached components into images."""
+    if use_classic_shadows:
+        raise NotImplementedError("use_classic_shadows=True (mg_Img_Eval.py:166-181) is not on the render CLI path")
+    has_exact = "Exact_Solar" in Img_Dict.keys()
+    keys = ["Rho", "Deltas", "Base_Col", "Est_Solar_Vis", "Adjust_col", "Output_class", "Sky_Col"]
+    rho, dl, base, vis, adj, ocl, skyc = _device_components(Img_Dict, keys)
+    ev = _device_components(Img_Dict, ["Exact_Solar"])[0] if has_exact else None
+    N, S = rho.shape[0], rho.shape[1]
+    Sky_Col = skyc[0, 0].double().cpu().numpy()                                   # ray 0 / sample 0 (:125-126)
+    cls = ocl[0, 0].double()
+    base_img, season, extreme, raw, raw_e = ops.cli_composite(
+        rho.reshape(N, S), dl.reshape(N, S), base, vis.reshape(N, S), adj, cls.contiguous(),
+        None if ev is None else ev.reshape(N, S))
+    size = out_img_size
+    Raw = _scatter(Img_Dict, size, raw)
+    Shadow_Mask = sig((Raw - .2) * 30)
+    Shadow_Adjust = np.expand_dims(Shadow_Mask, -1) + np.expand_dims(1 - Shadow_Mask, -1) * Sky_Col.reshape([1, 1, 3])
+    R = {"Base_Img": _scatter(Img_Dict, size, base_img), "Season_Adj_Img": _scatter(Img_Dict, size, season),
+         "Extreme_Imgs": [_scatter(Img_Dict, size, extreme[i]) for i in range(extreme.shape[0])],
+         "Shadow_Adjust": Shadow_Adjust, "Shadow_Mask": Shadow_Mask, "Raw_Shadow_Mask": Raw, "Sky_Col": Sky_Col,
+         "Time_Class": cls.cpu().numpy()}
+    if has_exact:
+        Raw_e = _scatter(Img_Dict, size, raw_e)
+        Mask_e = sig((Raw_e - .2) * 30)
+        R["Shadow_Adjust_Exact"] = np.expand_dims(Mask_e, -1) + np.expand_dims(1 - Mask_e, -1) * Sky_Col.reshape([1, 1, 3])
+        R["Shadow_Mask_Exact"] = Mask_e
+        R["Raw_Shadow_Mask_Exact"] = Raw_e
+    return R
+
+
+def get_imgs_from_Img_Dict_t_step(Img_Dict, out_img_size: tuple, class_vecs_array):
+    """mg_Img_Eval.py:192-228: T seasonal recombinations in one fused pass (components read once)."""
+    has_exact = "Exact_Solar" in Img_Dict.keys()
+    vkey = "Exact_Solar" if has_exact else "Est_Solar_Vis"
+    rho, dl, base, vis, adj, skyc = _device_components(Img_Dict, ["Rho", "Deltas", "Base_Col", vkey, "Adjust_col", "Sky_Col"])
+    N, S = rho.shape[0], rho.shape[1]
+    Sky_Col = skyc[0, 0].double().cpu().numpy()
+    cls = t.as_tensor(np.asarray(class_vecs_array), dtype=t.float64).to(rho.device).contiguous()
+    _, _, _, raw, _ = ops.cli_composite(rho.reshape(N, S), dl.reshape(N, S), base, vis.reshape(N, S), adj, cls[0].contiguous())
+    Raw = _scatter(Img_Dict, out_img_size, raw)
+    Mask = sig((Raw - .2) * 30)
+    Shadow_Adjust = np.expand_dims(Mask, -1) + np.expand_dims(1 - Mask, -1) * Sky_Col.reshape([1, 1, 3])
+    cols = ops.year_sweep(rho.reshape(N, S), dl.reshape(N, S), base, adj, cls).cpu().numpy()       # [T,N,3]
+    ip = Img_Dict["Image_Points"]
+    imgs = np.zeros([cols.shape[0], out_img_size[0], out_img_size[1], 3]) * np.nan
+    imgs[:, ip[:, 0], ip[:, 1]] = cols
+    return imgs * Shadow_Adjust[None]

@@ -1,0 +1,84 @@
+"""Training step: drop-in for mg_run_NeRF.py:288-326 (Net_tool.train_step) and the optimiser / scheduler set-up of
+T_NeRF_Full_2/Net_Tool_2.py:63-129 (T_NeRF_Net_Tool.reset_eval), plus the ONLY parallelism of the build: ray-sharded
+data parallel over the GPUs of one box with one flat NCCL all-reduce of the gradients per step.
+The reference's DataLoader / TensorBoard / checkpoint glue stays out of scope; `step()` takes the batch dict."""
+import torch as t
+import torch.distributed as dist
+
+from .adaptive_loss import AdaptiveLossFunction
+from .engine import All_in_One_Eval
+from .network import T_NeRF
+
+
+class TrainStep:
+    """One learning-mode section of T_NeRF_Net_Tool (learning_mode 2..4: free training, use_prior False) or the
+    DSM-guided section (use_prior True, learning_mode 1 with jump_start)."""
+
+    def __init__(self, args, device, H, WC, network=None, training_DSM=None, use_prior=False, total_steps=None,
+                 world_size=1, precision="bf16"):
+        self.args, self.device = args, t.device(device)
+        self.world_size = world_size
+        self.network = network if network is not None else T_NeRF(
+            args.fc_units, n_classes=args.number_low_frequency_cases,
+            **({} if training_DSM is None else {"HM": training_DSM}), precision=precision).to(self.device)
+        self.network.train()
+        total_steps = total_steps or args.max_train_steps
+        mk = lambda d, si, sl: AdaptiveLossFunction(d, t.float32, self.device, alpha_hi=2.99, alpha_init=2.0,
+                                                    scale_init=si, scale_lo=sl)
+        if args.Use_MSE_loss:
+            ada, ada_params = None, []
+        elif use_prior:                                                            # Net_Tool_2.py:69,82
+            ada = [mk(3, .03, 0.01), mk(1, 0.5, 0.05)]
+            ada_params = list(ada[0].parameters()) + list(ada[1].parameters())
+        else:                                                                      # Net_Tool_2.py:78
+            ada = mk(3, .03, 0.01)
+            ada_params = list(ada.parameters())
+        self.eval_tool = All_in_One_Eval(args, self.device, total_steps, use_prior, ada, H, WC)
+        self.params = [p for p in self.network.parameters()]
+        self.ada_params = ada_params
+        self.optim = t.optim.Adam(self.params, lr=args.lr)                         # Net_Tool_2.py:110-119
+        self.optim2 = t.optim.Adam(ada_params, lr=args.lr * args.lr_alpha_scale) if ada_params else None
+        oc = dict(total_steps=total_steps, base_momentum=0.85, max_momentum=0.95, cycle_momentum=False)
+        self.sched = t.optim.lr_scheduler.OneCycleLR(self.optim, max_lr=args.lr, **oc)
+        self.sched2 = t.optim.lr_scheduler.OneCycleLR(self.optim2, max_lr=args.lr * args.lr_alpha_scale, **oc) \
+            if self.optim2 is not None else None
+        self._flat = None
+        self.last_loss = None
+
+    def _allreduce_grads(self):
+        """one flat fp32 bucket (3.19 M network gradients + the adaptive-loss scalars), NCCL sum -> mean"""
+        ps = [p for p in self.params + self.ada_params if p.grad is not None]
+        n = sum(p.numel() for p in ps)
+        if self._flat is None or self._flat.numel() != n:
+            self._flat = t.empty(n, device=self.device, dtype=t.float32)
+        o = 0
+        for p in ps:
+            self._flat[o:o + p.numel()].copy_(p.grad.reshape(-1))
+            o += p.numel()
+        dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
+        self._flat.div_(self.world_size)
+        o = 0
+        for p in ps:
+            p.grad.copy_(self._flat[o:o + p.numel()].reshape(p.shape))
+            o += p.numel()
+
+    def step(self, data_dict, current_step, **inject):
+        """mg_run_NeRF.py:288-326 without the per-term TensorBoard .item() syncs; returns the loss dict."""
+        self.optim.zero_grad(set_to_none=True)
+        if self.optim2 is not None:
+            self.optim2.zero_grad(set_to_none=True)
+        loss = self.eval_tool.get_loss(data_dict, self.network, current_step, train_mode=True, **inject)
+        total = 0
+        for k in loss.keys():
+            total = total + loss[k][0] * loss[k][1]
+        total.backward()
+        if self.world_size > 1:
+            self._allreduce_grads()
+        self.optim.step()
+        if self.optim2 is not None:
+            self.optim2.step()
+        self.sched.step()
+        if self.sched2 is not None:
+            self.sched2.step()
+        self.last_loss = total.detach()
+        return loss

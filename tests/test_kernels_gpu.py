@@ -1,0 +1,189 @@
+"""GPU parity of the bandwidth-bound kernels and the GEMMs against the CPU oracle / golden fixtures."""
+import numpy as np
+import pytest
+import torch as t
+
+from conftest import load_golden
+from gpu_util import T, maxabs, relerr
+
+pytestmark = pytest.mark.gpu
+S = 96
+
+
+def test_sampling_bit_exact_vs_reference_golden():
+    from season_nerf_b200 import ops, sample_ts
+    g = load_golden("sampling")
+    top, bot = T(g["top"]), T(g["bot"])
+    for eval_mode, end, kp, kd, jit in [(True, False, "pts_eval", "del_eval", None), (True, True, "pts_end", "del_end", None),
+                                        (False, False, "pts_train", "del_train", g["jitter"])]:
+        ts = sample_ts(S, eval_mode, end, jitter=jit).cuda()
+        pts, d = ops.sample_rays(top, bot, ts)
+        assert np.array_equal(pts.cpu().numpy(), g[kp]), kp                      # bit-exact positions
+        assert np.array_equal(d.cpu().numpy()[..., None], g[kd]), kd              # bit-exact deltas
+    ts = sample_ts(S, True, True).cuda()
+    pts, d = ops.sample_rays(top, bot, ts, zero_oob=True)
+    bad = g["bad"]
+    assert np.array_equal(d.cpu().numpy() == 0, bad | (g["del_end"][..., 0] == 0))
+    assert bad.any()
+
+
+def test_sampling_bit_exact_vs_oracle_large_and_ragged():
+    from oracle import season_oracle as so
+    from season_nerf_b200 import ops, sample_ts
+    for n, s in [(1, 96), (4097, 96), (33, 7), (5, 200), (0, 96)]:
+        d = so.synthetic_batch(max(n, 1), seed=n + 3)
+        top, bot = d["Top"][:n], d["Bot"][:n]
+        p_ref, d_ref = so.sample_pt_coarse(top, bot, s, True, include_end_pt=True)
+        pts, dl = ops.sample_rays(top.cuda(), bot.cuda(), sample_ts(s, True, True).cuda())
+        assert np.array_equal(pts.cpu().numpy(), p_ref.numpy())
+        assert np.array_equal(dl.cpu().numpy(), d_ref.numpy()[..., 0])
+
+
+def test_solar_tops_match_reference_float64_promotion():
+    from season_nerf_b200 import ops
+    g = t.Generator().manual_seed(3)
+    pts = t.rand(1000, 3, generator=g) * 2 - 1
+    sun = np.array([0.31, -0.42, 0.85])
+    ref = (pts + ((1. - pts[:, 2]) / sun[2]).reshape(-1, 1) * t.tensor(sun).reshape(1, -1)).float()   # mg_Img_Eval.py:58-60
+    out = ops.solar_tops(pts.cuda(), sun, f64=True)
+    assert np.array_equal(out.cpu().numpy(), ref.numpy())
+    sun32 = t.tensor(sun).float()
+    ref32 = pts + ((1 - pts[:, 2]) / sun32[2]).unsqueeze(1) * sun32.reshape(1, 3)                     # Eval_Tools_2.py:257-258
+    out32 = ops.solar_tops(pts.cuda(), sun32.tolist(), f64=False)
+    assert np.array_equal(out32.cpu().numpy(), ref32.numpy())
+
+
+def _comp_inputs(N, Sx, seed, per_sample_sky):
+    g = t.Generator().manual_seed(seed)
+    rho = t.rand(N, Sx, generator=g) * 4
+    dl = t.rand(N, 1, generator=g).expand(N, Sx).contiguous() * 0.05
+    col = t.rand(N, Sx, 3, generator=g)
+    vis = t.rand(N, Sx, generator=g)
+    sky = t.rand(N, Sx, 3, generator=g) if per_sample_sky else t.rand(N, 3, generator=g)
+    return rho, dl, col, vis, sky
+
+
+def _comp_ref(rho, dl, col, vis, sky, classic):
+    from oracle import season_oracle as so
+    N, Sx = rho.shape
+    R, D, V = rho.reshape(N, Sx, 1), dl.reshape(N, Sx, 1), vis.reshape(N, Sx, 1)
+    K = sky if sky.dim() == 3 else sky.reshape(N, 1, 3).expand(N, Sx, 3)
+    PV = so.get_PV(R, D)
+    PE = 1 - t.exp(-R * D)
+    PS = PV * PE
+    alb = t.sum(PS * col, 1)
+    if classic:
+        ren = t.sum(PS * col * (V + (1 - V) * K), 1)
+    else:
+        sv3 = t.sigmoid((t.sum(V.detach() * PS, 1) - .2) * 30)
+        ren = alb * (sv3 + (1 - sv3) * t.mean(K, 1))
+    return PV, PE, PS, alb, ren
+
+
+@pytest.mark.parametrize("classic", [False, True])
+@pytest.mark.parametrize("per_sample", [False, True])
+@pytest.mark.parametrize("N,Sx", [(37, 96), (3, 40), (129, 160)])
+def test_composite_forward_backward(classic, per_sample, N, Sx):
+    from season_nerf_b200 import ops
+    rho, dl, col, vis, sky = _comp_inputs(N, Sx, 5 + N, per_sample)
+    leaves = [x.clone().requires_grad_(True) for x in (rho, col, vis, sky)]
+    PV, PE, PS, alb, ren = _comp_ref(leaves[0], dl, leaves[1], leaves[2], leaves[3], classic)
+    g = t.Generator().manual_seed(9)
+    w = [t.rand(x.shape, generator=g) for x in (PV, PE, PS, alb, ren)]
+    (sum((o * wi).sum() for o, wi in zip((PV, PE, PS, alb, ren), w))).backward()
+    dleaves = [x.clone().cuda().requires_grad_(True) for x in (rho, col, vis, sky)]
+    oPV, oPE, oPS, oalb, oren, _ = ops.composite(dleaves[0], dl.cuda(), dleaves[1], dleaves[2], dleaves[3], classic)
+    for o, r in zip((oPV, oPE, oPS, oalb, oren), (PV[..., 0], PE[..., 0], PS[..., 0], alb, ren)):
+        assert maxabs(o, r) < 2e-5
+    (sum((o * wi.cuda().reshape(o.shape)).sum() for o, wi in zip((oPV, oPE, oPS, oalb, oren), w))).backward()
+    for i, (a, b) in enumerate(zip(dleaves, leaves)):
+        if i == 2 and not classic:
+            assert a.grad is None or float(a.grad.abs().max()) == 0.0          # vis is detached (Eval_Tools_2.py:214)
+            continue
+        assert relerr(a.grad, b.grad) < 2e-4, (i, relerr(a.grad, b.grad))
+
+
+def test_get_PV_golden():
+    import season_nerf_b200 as snb
+    g = load_golden("sampling")
+    pv = snb.get_PV(T(g["rho"]), T(g["del_end"]))
+    assert maxabs(pv, g["pv"]) < 2e-6
+
+
+def test_pe_encode_vs_reference_golden():
+    from season_nerf_b200 import ops
+    g = load_golden("net_eval")
+    for x, n, key in [(g["X"], 10, "pe10"), (g["sun"], 4, "pe4"), (g["Time"][:, :2], 2, "pe2")]:
+        x = T(x).contiguous()
+        out = t.empty(x.shape[0], x.shape[1] * (2 * n + 1), device="cuda")
+        ops.pe_encode(x, n, out)
+        assert maxabs(out, g[key]) < 5e-7, key        # accurate sincosf on the same float32 arguments (<= 2 ulp)
+
+
+@pytest.mark.parametrize("a_t,b_t", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (1000, 512, 576), (4096, 16, 256), (333, 72, 136), (512, 576, 9216),
+                                   (129, 256, 320), (64, 512, 512)])
+def test_gemm_bf16_tcgen05(a_t, b_t, M, N, K):
+    from season_nerf_b200 import ops
+    g = t.Generator().manual_seed(M + N + K)
+    A = (t.rand(M, K, generator=g) - .5).bfloat16().cuda()
+    B = (t.rand(N, K, generator=g) - .5).bfloat16().cuda()
+    bias = (t.rand(N, generator=g) - .5).cuda()
+    ref = 1.5 * (A.float() @ B.float().T + bias)
+    As = A.T.contiguous() if a_t else A
+    Bs = B.T.contiguous() if b_t else B
+    if (a_t and M % 8) or (b_t and N % 8):
+        pytest.skip("transposed storage needs a 16-byte row pitch")
+    out = t.empty(M, N, device="cuda")
+    ops.gemm(As, Bs, out, bias=bias, alpha=1.5, a_t=a_t, b_t=b_t)
+    t.cuda.synchronize()
+    assert relerr(out, ref) < 1e-5, relerr(out, ref)
+    outb = t.empty(M, N, device="cuda", dtype=t.bfloat16)
+    ops.gemm(As, Bs, outb, bias=bias, alpha=1.5, a_t=a_t, b_t=b_t)
+    assert relerr(outb, ref) < 6e-3
+    acc = ref.clone()
+    ops.gemm(As, Bs, acc, bias=bias, alpha=1.5, accumulate=1, a_t=a_t, b_t=b_t)
+    assert relerr(acc, 2 * ref) < 1e-5
+    z = t.zeros(M, N, device="cuda")
+    ops.gemm(As, Bs, z, alpha=2.0, accumulate=2, a_t=a_t, b_t=b_t)      # split-K atomics
+    assert relerr(z, 2.0 * (A.float() @ B.float().T)) < 1e-5
+
+
+@pytest.mark.parametrize("a_t,b_t", [(False, False), (True, True), (False, True)])
+def test_gemm_fp32_simt(a_t, b_t):
+    from season_nerf_b200 import ops
+    g = t.Generator().manual_seed(1)
+    M, N, K = 257, 70, 131
+    A, B = (t.rand(M, K, generator=g) - .5).cuda(), (t.rand(N, K, generator=g) - .5).cuda()
+    bias = t.rand(N, generator=g).cuda()
+    out = t.empty(M, N, device="cuda")
+    ops.gemm(A.T.contiguous() if a_t else A, B.T.contiguous() if b_t else B, out, bias=bias, alpha=30.0, a_t=a_t, b_t=b_t)
+    assert relerr(out, 30 * (A @ B.T + bias)) < 2e-6
+
+
+@pytest.mark.parametrize("dt", [t.float32, t.bfloat16])
+def test_sine_and_stats_kernels(dt):
+    from season_nerf_b200 import ops
+    g = t.Generator().manual_seed(2)
+    M, N = 1537, 256
+    Z = (t.randn(M, N, generator=g) * 3).to(dt).cuda()
+    a, c = (t.rand(N, generator=g) + .5).cuda(), (t.rand(N, generator=g) - .5).cuda()
+    s, ss = ops.col_stats(Z)
+    assert relerr(s, Z.double().sum(0)) < 1e-6 and relerr(ss, (Z.double() ** 2).sum(0)) < 1e-6
+    Y = t.empty_like(Z)
+    ops.sine_fwd(Z, a, c, Y)
+    ref = t.sin(a * Z.float() + c)
+    assert maxabs(Y, ref) < (1e-6 if dt == t.float32 else 4e-3)
+    # backward of sin(BN(z)) against autograd
+    Zf = Z.float().clone().requires_grad_(True)
+    gam, bet = (t.rand(N, generator=g) + .5).cuda(), (t.rand(N, generator=g) - .5).cuda()
+    mean, var = Zf.mean(0), Zf.var(0, unbiased=False)
+    out = t.sin((Zf - mean) / t.sqrt(var + 1e-5) * gam + bet)
+    dY = t.randn(M, N, generator=g).to(dt).cuda()
+    out.backward(dY.float())
+    invstd = (1 / t.sqrt(var + 1e-5)).detach()
+    aa, cc = (gam * invstd).contiguous(), (bet - mean.detach() * gam * invstd).contiguous()
+    sg, sgx = ops.sine_bwd_reduce(dY, Z, aa, cc, mean.detach().contiguous(), invstd.contiguous())
+    dZ = t.empty_like(Z)
+    ops.sine_bwd_apply(dY, Z, aa, cc, dZ, mean.detach().contiguous(), invstd.contiguous(), (sg / M).float(), (sgx / M).float())
+    assert relerr(dZ, Zf.grad) < (1e-4 if dt == t.float32 else 1e-2)

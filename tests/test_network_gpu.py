@@ -1,0 +1,209 @@
+"""GPU parity of the drop-in network / engine / CLI render against fixtures produced by the unmodified reference
+(tests/golden, oracle/make_golden.py) and against the CPU oracle on the same seeded inputs.
+Tolerances (north star): fp32 validation build 1e-4 max-abs on rendered outputs; bf16 production build 1e-2."""
+import numpy as np
+import pytest
+import torch as t
+
+from conftest import load_golden
+from gpu_util import T, make_net, maxabs, relerr
+
+pytestmark = pytest.mark.gpu
+S = 96
+TOL = {"fp32": dict(out=1e-4, rho=2e-3, grad=2e-3), "bf16": dict(out=1e-2, rho=6e-2, grad=8e-2)}
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_network_entry_points_eval(params0, precision):
+    g = load_golden("net_eval")
+    net = make_net(params0, precision)
+    X, sun, Time = T(g["X"]), T(g["sun"]), T(g["Time"])
+    tol = TOL[precision]
+    with t.no_grad():
+        fw = net.forward(X, sun, Time)
+        fs = net.forward_seperate(X, sun, Time)
+        sol = net.forward_Solar(X, sun, Time)
+        sig = net.forward_Classic_Sigma_Only(X)
+        cls = net.get_class_only(Time)
+        colo = net.G_NeRF_net.forward_color_only(X)
+    names = ["rho", "col", "vis", "sky", "cls", "adj"]
+    for o, k in zip(fw, names):
+        assert maxabs(o, g["fw_" + k]) < (tol["rho"] if k in ("rho", "adj") else tol["out"]), ("fw", k, maxabs(o, g["fw_" + k]))
+    for o, k in zip(fs, names):
+        assert tuple(o.shape) == g["fs_" + k].shape
+        assert maxabs(o, g["fs_" + k]) < (tol["out"] if k in ("vis", "sky", "cls") else tol["rho"]), ("fs", k)
+    for o, k in zip(sol, ["rho", "vis", "sky"]):
+        assert maxabs(o, g["sol_" + k]) < tol["rho"], ("sol", k)
+    assert maxabs(sig, g["sigma_only"]) < tol["rho"]
+    assert maxabs(cls, g["class_only"]) < tol["out"]
+    assert maxabs(colo, g["color_only"]) < tol["out"]
+
+
+KEYS = ["Rendered_Col", "PE", "PV", "PS", "Solar_Vis", "Sky_Col", "Classes", "Adjust", "Rho", "Col", "deltas",
+        "Albedo_Color"]
+
+
+def _data(g):
+    return {k[3:]: t.tensor(v) for k, v in g.items() if k.startswith("in_")}     # CPU tensors, like the DataLoader rows
+
+
+def _tool(args=None, use_prior=False, ada=None, n_steps=100):
+    import season_nerf_b200 as snb
+    from oracle import season_oracle as so
+    return snb.All_in_One_Eval(args or so.default_args(), t.device("cuda"), n_steps, use_prior, ada, so.oma_w2l_h(), so.OMA_W2C)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_engine_eval_golden(params0, precision):
+    g = load_golden("engine_eval")
+    net = make_net(params0, precision)
+    with t.no_grad():
+        R = _tool().eval(_data(g), net, 0, False)
+    assert np.array_equal(R["sample_pts"].cpu().numpy(), g["sample_pts"])
+    tol = TOL[precision]
+    for k in KEYS:
+        assert tuple(R[k].shape) == g[k].shape, k
+        lim = tol["rho"] if k in ("Rho", "Adjust") else tol["out"]
+        assert maxabs(R[k], g[k]) < lim, (k, maxabs(R[k], g[k]))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_engine_train_forward_batchnorm_golden(params0, precision):
+    g = load_golden("engine_train_fwd")
+    net = make_net(params0, precision, train=True)
+    with t.no_grad():
+        R = _tool().eval(_data(g), net, 0, True, jitter=g["jitter"])
+    assert np.array_equal(R["sample_pts"].cpu().numpy(), g["sample_pts"])
+    tol = TOL[precision]
+    for k in KEYS:
+        lim = tol["rho"] if k in ("Rho", "Adjust") else tol["out"]
+        assert maxabs(R[k], g[k]) < lim, (k, maxabs(R[k], g[k]))
+    sd = net.state_dict()
+    rt = 1e-4 if precision == "fp32" else 2e-2
+    assert relerr(sd["G_NeRF_net.fc2.norm.running_mean"], g["fc2_rm"]) < rt
+    assert relerr(sd["G_NeRF_net.fc2.norm.running_var"], g["fc2_rv"]) < rt
+    assert relerr(sd["G_NeRF_net.fc9.norm.running_var"], g["fc9_rv"]) < rt
+    assert int(sd["G_NeRF_net.fc2.norm.num_batches_tracked"]) == 1
+
+
+def _ada(use_prior):
+    from season_nerf_b200 import AdaptiveLossFunction as mk
+    a0 = mk(3, t.float32, "cuda", alpha_hi=2.99, alpha_init=2.0, scale_init=0.03, scale_lo=0.01)
+    if not use_prior:
+        return a0
+    return [a0, mk(1, t.float32, "cuda", alpha_hi=2.99, alpha_init=2.0, scale_init=0.5, scale_lo=0.05)]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name,kw", [("loss_barron", {}), ("loss_mse", {"mse": True}), ("loss_prior", {"use_prior": True}),
+                                     ("loss_type2", {"type2": True})])
+def test_get_loss_and_gradients_golden(params0, precision, name, kw):
+    from oracle import season_oracle as so
+    import season_nerf_b200 as snb
+    g = load_golden(name)
+    use_prior, mse, type2 = kw.get("use_prior", False), kw.get("mse", False), kw.get("type2", False)
+    args = so.default_args(Use_MSE_loss=mse, Solar_Type_2=type2)
+    net = snb.T_NeRF(512, 4, **({"HM": g["hm"]} if use_prior else {}), precision=precision)
+    net.load_state_dict({k: v.clone() for k, v in params0.items()})
+    net = net.cuda().train()
+    ada = None if mse else _ada(use_prior)
+    tool = _tool(args, use_prior, ada)
+    solar = tuple(t.tensor(g[k]) for k in ("s_top", "s_bot", "s_sun", "s_time"))
+    L = tool.get_loss(_data(g), net, 30, True, jitter=g["jitter"], solar=solar, solar_jitter=g["solar_jitter"])
+    tol = TOL[precision]
+    assert set(L.keys()) == {k[5:] for k in g if k.startswith("loss_")}
+    for k in L:
+        ref = float(g["loss_" + k])
+        assert abs(float(L[k][0]) - ref) < (3e-3 if precision == "fp32" else 8e-2) * max(abs(ref), 1e-2), (k, float(L[k][0]), ref)
+        assert abs(float(L[k][1]) - float(g["w_" + k])) <= 1e-4 * abs(float(g["w_" + k]))
+    tot = sum(L[k][0] * L[k][1] for k in L)
+    tot.backward()
+    norms = dict(zip(g["grad_names"].tolist(), g["grad_norms"].tolist()))
+    scale = max(norms.values())
+    bad = []
+    for k, p in net.named_parameters():
+        n = 0.0 if p.grad is None else float(p.grad.norm())
+        if abs(n - norms[k]) > tol["grad"] * norms[k] + 1e-4 * scale:
+            bad.append((k, n, norms[k]))
+    assert not bad, bad
+    for k in g:
+        if k.startswith("grad_") and k not in ("grad_names", "grad_norms"):
+            p = dict(net.named_parameters())[k[5:]]
+            if float(np.abs(g[k]).max()) < 1e-4 * scale:
+                continue
+            assert relerr(p.grad, g[k]) < (5e-3 if precision == "fp32" else 0.15), (k, relerr(p.grad, g[k]))
+    for k in ["adjust_rho.weight", "adjust_solar_vis.weight", "adjust_sky_col.weight"]:
+        p = dict(net.named_parameters())[k]
+        assert p.grad is None or float(p.grad.abs().max()) == 0.0
+    sd = net.state_dict()
+    assert int(sd["G_NeRF_net.fc2.norm.num_batches_tracked"]) == 2           # image pass + no_grad solar pass
+    assert relerr(sd["G_NeRF_net.fc2.norm.running_var"], g["fc2_rv"]) < (1e-4 if precision == "fp32" else 2e-2)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_cli_component_render_and_composite_golden(params0, precision):
+    import season_nerf_b200 as snb
+    from oracle import season_oracle as so
+    g = load_golden("cli_render")
+    net = make_net(params0, precision)
+    D = snb.component_render_by_dir(net, [80, 0], [45, 135], 184 / 365, (5, 6, S), so.OMA_W2C, so.oma_w2l_h(),
+                                    t.device("cuda"), include_exact_solar=False)
+    assert D["World_Points"].dtype == np.float64
+    assert np.array_equal(D["World_Points"].astype(np.float32), g["d_World_Points"])
+    assert np.array_equal(D["Deltas"].astype(np.float32), g["d_Deltas"])
+    assert np.array_equal(D["Image_Points"], g["d_Image_Points"])
+    tol = TOL[precision]
+    for k in ["Rho", "Base_Col", "Est_Solar_Vis", "Sky_Col", "Output_class", "Adjust_col"]:
+        assert D[k].shape == g["d_" + k].shape, k
+        lim = tol["out"] if k in ("Est_Solar_Vis", "Sky_Col", "Output_class") else tol["rho"]
+        assert maxabs(D[k], g["d_" + k]) < lim, (k, maxabs(D[k], g["d_" + k]))
+    imgs = snb.get_imgs_from_Img_Dict(D, (5, 6, S), False)
+    for k in ["Base_Img", "Season_Adj_Img", "Shadow_Adjust", "Shadow_Mask", "Sky_Col", "Time_Class"]:
+        assert maxabs(imgs[k], g[k]) < tol["out"], (k, maxabs(imgs[k], g[k]))
+    assert maxabs(np.array(imgs["Extreme_Imgs"]), g["Extreme_Imgs"]) < tol["out"]
+    sweep = snb.get_imgs_from_Img_Dict_t_step(D, (5, 6, S), g["class_vecs"].astype(np.float64))
+    assert maxabs(sweep, g["sweep"]) < tol["out"]
+    # float64 compositing kernels on the REFERENCE's own component arrays: pure arithmetic parity
+    Dref = {k[2:]: g[k].astype(np.float64) for k in g if k.startswith("d_") and k != "d_Image_Points"}
+    Dref["Image_Points"] = g["d_Image_Points"]
+    imgs = snb.get_imgs_from_Img_Dict(Dref, (5, 6, S), False)
+    for k in ["Base_Img", "Season_Adj_Img", "Shadow_Adjust", "Shadow_Mask", "Raw_Shadow_Mask"]:
+        assert maxabs(imgs[k], g[k]) < 2e-6, (k, maxabs(imgs[k], g[k]))
+    sweep = snb.get_imgs_from_Img_Dict_t_step(Dref, (5, 6, S), g["class_vecs"].astype(np.float64))
+    assert maxabs(sweep, g["sweep"]) < 2e-6
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_cli_exact_shadow_march_golden(params0, precision):
+    import season_nerf_b200 as snb
+    from oracle import season_oracle as so
+    g = load_golden("cli_render_exact")
+    net = make_net(params0, precision)
+    D = snb.component_render_by_dir(net, [70, 30], [35, 200], 0.25, (2, 3, S), so.OMA_W2C, so.oma_w2l_h(),
+                                    t.device("cuda"), include_exact_solar=True)
+    tol = TOL[precision]
+    assert maxabs(D["Exact_Solar"], g["d_Exact_Solar"]) < tol["out"]
+    imgs = snb.get_imgs_from_Img_Dict(D, (2, 3, S), False)
+    for k in ["Season_Adj_Img", "Shadow_Adjust_Exact", "Shadow_Mask_Exact"]:
+        assert maxabs(imgs[k], g[k]) < tol["out"], (k, maxabs(imgs[k], g[k]))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_quick_run_and_engine_exact_solar_golden(params0, precision):
+    import season_nerf_b200 as snb
+    from oracle import season_oracle as so
+    g = load_golden("quick_run")
+    net = make_net(params0, precision)
+    args = so.default_args()
+    q = snb.Quick_Run_Net(net, args, so.OMA_W2C, so.oma_w2l_h(), t.device("cuda"), use_full_solar=False)
+    img, mask = q.render_img([75, 20], [50, 120], 0.4, 6)
+    tol = TOL[precision]
+    assert np.array_equal(mask, g["mask"])
+    assert maxabs(img["Col_Img"], g["Col_Img"]) < tol["out"]
+    assert maxabs(img["Shadow_Mask"], g["Shadow_Mask"]) < tol["out"]
+    dsm = q.get_DSM((4, 4))
+    assert maxabs(np.nan_to_num(dsm), np.nan_to_num(g["dsm"])) < tol["out"] * 2
+    with t.no_grad():
+        R = _tool().eval_exact_solar(_data(g), net, -1, False)
+    assert maxabs(R["Solar_Vis"], g["ex_Solar_Vis"]) < tol["out"]
+    assert maxabs(R["Rendered_Col"], g["ex_Rendered_Col"]) < tol["out"]
