@@ -110,6 +110,19 @@ int snb_sine_bwd_apply(const void* dY, int ldd, const void* Z, int ldz, const fl
 int snb_convert(const void* src, int src_dtype, int lds, void* dst, int dst_dtype, int ldd, long long M, int N,
                 void* stream);
 
+/* ---- fused eval-mode network (render): T_NeRF_net_v2.py:75-105,131-151,169-170 + G_NeRF.py:74-133 --------------
+ * One persistent tcgen05 kernel runs encoding -> trunk -> sigma/colour heads -> solar branch -> adjust branch for
+ * tiles of 128 sample points with activations kept in shared memory / TMEM.  `program` is the device image built by
+ * season_nerf_b200/packing.py (schedule tables + biases + BatchNorm-folded bf16 weights pre-swizzled into the
+ * shared-memory tile layout); the *_off arguments are byte offsets of its sections, n_mma / n_epi the table lengths.
+ *   pts [M,3] f32; sun [ceil(M/S),3] f32 (one solar direction per S consecutive points; S=1: per point; may be
+ *   NULL for a sigma-only program).
+ * outputs (float32, any may be NULL): rho_raw [M], pos4 [M,4] = (sigma, colour[3]), vis_raw [M], adj [M,12]
+ * (class-major [C,3]), all BEFORE softplus / sigmoid. */
+int snb_fused_eval(const void* program, unsigned n_mma, unsigned n_epi, unsigned mma_off, unsigned epi_off,
+                   unsigned bias_off, unsigned w_off, const float* pts, long long M, int S, const float* sun,
+                   float* rho_raw, float* pos4, float* vis_raw, float* adj, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,7 @@ SIGNATURES = {
     "snb_sine_bwd_reduce": [_p, _i, _p, _i, _p, _p, _p, _p, _ll, _i, _i, _p, _p, _p],
     "snb_sine_bwd_apply": [_p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _ll, _i, _i, _p],
     "snb_convert": [_p, _i, _i, _p, _i, _i, _ll, _i, _p],
+    "snb_fused_eval": [_p, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, _p, _ll, _i, _p, _p, _p, _p, _p, _p],
 }
 _RESTYPES = {"snb_launch_count": _ll, "snb_error_string": C.c_char_p}
 

@@ -128,12 +128,14 @@ composite_bwd_kernel(const float* __restrict__ rho, const float* __restrict__ de
                 e2 = d_albedo ? __ldg(d_albedo + 3 * n + 2) : 0.f;
     float dA0 = e0, dA1 = e1, dA2 = e2;  // gradient w.r.t. the albedo sum
     float dk0 = 0, dk1 = 0, dk2 = 0;     // gradient w.r.t. the mean sky colour (non-classic)
+    float dvs = 0.f;                     // gradient w.r.t. sum_s vis*PS: vis is detached but PS is not (Eval_Tools_2.py:214)
     if (!kClassic) {
       a0 = warp_sum(a0), a1 = warp_sum(a1), a2 = warp_sum(a2), vs = warp_sum(vs);
       if (kSkyPerSample) k0 = warp_sum(k0) / (float)S, k1 = warp_sum(k1) / (float)S, k2 = warp_sum(k2) / (float)S;
       const float sv3 = sigmoidf_((vs - .2f) * 30.f);
       dA0 += g0 * (sv3 + (1.f - sv3) * k0), dA1 += g1 * (sv3 + (1.f - sv3) * k1), dA2 += g2 * (sv3 + (1.f - sv3) * k2);
       dk0 = g0 * a0 * (1.f - sv3), dk1 = g1 * a1 * (1.f - sv3), dk2 = g2 * a2 * (1.f - sv3);
+      dvs = (g0 * a0 * (1.f - k0) + g1 * a1 * (1.f - k1) + g2 * a2 * (1.f - k2)) * sv3 * (1.f - sv3) * 30.f;
       if (!kSkyPerSample && lane == 0 && d_sky) d_sky[3 * n] = dk0, d_sky[3 * n + 1] = dk1, d_sky[3 * n + 2] = dk2;
       if (kSkyPerSample) dk0 /= (float)S, dk1 /= (float)S, dk2 /= (float)S;
     }
@@ -164,7 +166,7 @@ composite_bwd_kernel(const float* __restrict__ rho, const float* __restrict__ de
             dsk0 += t0, dsk1 += t1, dsk2 += t2;
           }
         } else {
-          dps += dA0 * c0 + dA1 * c1 + dA2 * c2;
+          dps += dA0 * c0 + dA1 * c1 + dA2 * c2 + dvs * __ldg(vis + o);
           d_col[3 * o] = ps * dA0, d_col[3 * o + 1] = ps * dA1, d_col[3 * o + 2] = ps * dA2;
           if (kSkyPerSample && d_sky) d_sky[3 * o] = dk0, d_sky[3 * o + 1] = dk1, d_sky[3 * o + 2] = dk2;
         }

