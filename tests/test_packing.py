@@ -47,7 +47,7 @@ def test_schedule_checker_catches_hazards(params0):
     assert packing.check_schedule(mma, epi)
     bad = mma.copy()
     i = int(np.nonzero(bad["flags"] & packing.F_WAIT_CHUNK)[0][5])
-    bad["flags"][i] &= ~packing.F_WAIT_CHUNK                      # drop a chunk-ready wait
+    bad["flags"][i] &= np.uint8(0xFF ^ packing.F_WAIT_CHUNK)                      # drop a chunk-ready wait
     try:
         packing.check_schedule(bad, epi)
         raise SystemExit("hazard not detected")
@@ -55,7 +55,7 @@ def test_schedule_checker_catches_hazards(params0):
         pass
     bad = mma.copy()
     i = int(np.nonzero((bad["flags"] & packing.F_ACC) == 0)[0][7])
-    bad["flags"][i] &= ~packing.F_WAIT_EMPTY                      # restart a TMEM region without waiting for its drain
+    bad["flags"][i] &= np.uint8(0xFF ^ packing.F_WAIT_EMPTY)                      # restart a TMEM region without waiting for its drain
     try:
         packing.check_schedule(bad, epi)
         raise SystemExit("hazard not detected")
