@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""Benchmark of the Season-NeRF hot path on B200 (contract: see the task statement / DESIGN.md section "Measurement").
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one JSON line on rank 0)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU cores (oracle port)
+  torchrun --nproc-per-node N bench.py --gpus N ...        # ray-sharded data parallel, NCCL gradient all-reduce
+
+Headline workload (BASELINE.json configs[1]): one training step on 4096 synthetic OMA_281-shaped rays per GPU
+(+4096 solar rays), Barron adaptive loss + solar losses, forward + backward + Adam/OneCycle step.
+metric = training rays/s (image rays; every image ray is paired with one solar ray).
+  value : inputs (rays, solar rays, jitter) resident in HBM before the timed region.
+  e2e   : the public API call `TrainStep.step(batch)` with HOST tensors like the reference's DataLoader rows: H2D of the
+          batch, host-side solar-ray generation + H2D, and a D2H read of the loss every step.
+A secondary `render` object reports the fused render kernel on a 512x512x96 view (BASELINE.json configs[2] without
+the exact shadow march) with its own tensor roofline.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+S = 96
+TRAIN_FLOP_PER_RAY = 2.086e9          # 1 image ray fwd+bwd + 1 solar ray, algorithmic
+RENDER_FLOP_PER_RAY = 556_750_336     # 96*5,793,792 + 546,304
+RENDER_FLOP_PER_POINT = 5_793_792
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index, self.lines, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def bench_args():
+    import types
+    return types.SimpleNamespace(n_samples=S, Use_Reg=True, Solar_Type_2=False, Use_MSE_loss=False, sc_lambda=0.03,
+                                 Use_Solar=True, number_low_frequency_cases=4, fc_units=512, lr=10 ** -4.86,
+                                 lr_alpha_scale=1000.0, max_train_steps=50000)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_reference(a):
+    """The reference algorithm on the host CPU (oracle port, all host threads): bounded sample per step."""
+    import torch as t
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import barron_loss
+    from oracle import season_oracle as so
+    cores = os.cpu_count() or 1
+    t.set_num_threads(cores)
+    n = a.ref_rays
+    args = so.default_args()
+    P = so.init_params(seed=0)
+    leaves = [v.requires_grad_(True) for k, v in P.items() if v.is_floating_point() and "running" not in k]
+    ada = barron_loss.AdaptiveLossFunction(3, t.float32, "cpu", alpha_hi=2.99, alpha_init=2.0, scale_init=0.03, scale_lo=0.01)
+    batch = so.synthetic_batch(n, seed=1)
+    import numpy as np
+    H, WC = so.oma_w2l_h(), so.OMA_W2C
+
+    def step():
+        st, en, vec, tm, _ = so.create_solar_rays_uniform(n, WC, H, np.random.RandomState(3), t.Generator().manual_seed(3))
+        L, _ = so.get_loss(args, batch, P, 30, True, ada, solar=(st, en, vec, tm))
+        for v in leaves:
+            v.grad = None
+        so.total_loss(L).backward()
+
+    for _ in range(a.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = n * a.steps / dt
+    sample = "%d image + %d solar rays per step, S=%d, Barron+solar loss, fwd+bwd, torch CPU fp32" % (n, n, S)
+    print(json.dumps({"impl": "reference", "metric": "training rays/s (4096-ray step, fwd+bwd)", "value": val, "unit": "rays/s",
+                      "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": "train step, 4096 synthetic OMA_281-shaped rays + 4096 solar rays per GPU, S=96, "
+                                             "Barron + solar losses (BASELINE.json configs[1]); reference arm: bounded sample"},
+                      "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+                      "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def cpu_baseline(n_rays=256):
+    """oracle train step timed on the host cores (rank 0, N=1): ~10-30 s of CPU work."""
+    import numpy as np
+    import torch as t
+    from oracle import barron_loss
+    from oracle import season_oracle as so
+    cores = os.cpu_count() or 1
+    t.set_num_threads(cores)
+    args = so.default_args()
+    P = so.init_params(seed=0)
+    leaves = [v.requires_grad_(True) for k, v in P.items() if v.is_floating_point() and "running" not in k]
+    ada = barron_loss.AdaptiveLossFunction(3, t.float32, "cpu", alpha_hi=2.99, alpha_init=2.0, scale_init=0.03, scale_lo=0.01)
+    batch = so.synthetic_batch(n_rays, seed=1)
+    st, en, vec, tm, _ = so.create_solar_rays_uniform(n_rays, so.OMA_W2C, so.oma_w2l_h(), np.random.RandomState(3),
+                                                      t.Generator().manual_seed(3))
+    best = None
+    for i in range(3):
+        t0 = time.perf_counter()
+        L, _ = so.get_loss(args, batch, P, 30, True, ada, solar=(st, en, vec, tm))
+        for v in leaves:
+            v.grad = None
+        so.total_loss(L).backward()
+        dt = time.perf_counter() - t0
+        if i > 0:
+            best = dt if best is None else min(best, dt)
+    return {"value": n_rays / best, "unit": "rays/s", "cores": cores, "kind": "port",
+            "sample": "%d image + %d solar rays, one train step (fwd+bwd), best of 2 after 1 warm-up, torch CPU fp32 oracle" % (n_rays, n_rays)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import numpy as np
+    import torch as t
+    import torch.distributed as dist
+    import season_nerf_b200 as snb
+    from season_nerf_b200 import _lib, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    t.cuda.set_device(local)
+    dev = t.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = _peaks()
+    args = bench_args()
+    n = a.rays
+    # OMA_281-like frame
+    W2C = np.array([41.2905, -95.8967, 315.0])
+    H = np.eye(4)
+    H[0, 0], H[1, 1], H[2, 2] = 2 / 0.0024, 2 / 0.0032, 2 / 70.0
+    H[0, 3], H[1, 3], H[2, 3] = -W2C[0] * H[0, 0], -W2C[1] * H[1, 1], -W2C[2] * H[2, 2]
+
+    t.manual_seed(0)
+    ts = snb.TrainStep(args, dev, H, W2C, world_size=world, precision=a.precision)
+    if world > 1:                                     # identical initial weights on every rank
+        for p_ in ts.params + ts.ada_params:
+            dist.broadcast(p_.data, 0)
+
+    g = t.Generator().manual_seed(1 + rank)
+    def make_batch(pinned):
+        xy = (t.rand(n, 2, generator=g) * 2 - 1) * 0.8
+        dxy = (t.rand(n, 2, generator=g) * 2 - 1) * 0.2
+        n_img = 41
+        el = t.deg2rad(20 + 50 * t.rand(n_img, generator=g))
+        az = 2 * np.pi * t.rand(n_img, generator=g)
+        sun = t.stack([t.cos(el) * t.sin(az), t.cos(el) * t.cos(az), t.sin(el)], 1)
+        f = t.rand(n_img, generator=g)
+        tim = t.stack([t.cos(2 * np.pi * f), t.sin(2 * np.pi * f), t.full_like(f, np.cos(2 * np.pi * .7)),
+                       t.full_like(f, np.sin(2 * np.pi * .7))], 1)
+        img = t.randint(0, n_img, (n,), generator=g)
+        b = {"Top": t.cat([xy, t.ones(n, 1)], 1), "Bot": t.cat([xy + dxy, -t.ones(n, 1)], 1), "Sun_Angle": sun[img],
+             "Time_Encoded": tim[img], "GT_Color": t.rand(n, 3, generator=g)}
+        return {k: (v.contiguous().pin_memory() if pinned else v.contiguous()) for k, v in b.items()}
+
+    host_batch = make_batch(True)
+    dev_batch = {k: v.to(dev) for k, v in host_batch.items()}
+    np.random.seed(3 + rank)
+    t.manual_seed(3 + rank)
+    st, en, vec, tm, _ = ts.eval_tool.solar_creation_tool(n, include_times=True)
+    dev_solar = tuple(x.to(dev) for x in (st, en, vec, tm))
+    jit = t.rand(S)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        t.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        l0 = _lib.launch_count()
+        e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as cs:
+            e0.record()
+            for i in range(steps):
+                fn(warmup + i)
+            e1.record()
+            barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tt = t.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt)
+        return ms, _lib.launch_count() - l0, cs.summary()
+
+    # ---- value: device-resident inputs ------------------------------------------------------------------
+    def step_dev(i):
+        ts.step(dev_batch, i, jitter=jit, solar=dev_solar, solar_jitter=jit)
+
+    ms, launches, clocks = timed(step_dev, a.steps, a.warmup)
+    value = world * n * a.steps / (ms * 1e-3)
+
+    # ---- e2e: public API with host tensors, loss read back every step ----------------------------------
+    h2d = sum(v.numel() * 4 for v in host_batch.values()) + n * (3 + 3 + 3 + 4) * 4
+    sink = []
+
+    def step_host(i):
+        loss = ts.step(host_batch, i)
+        sink.append(float(ts.last_loss))              # D2H read of the step's loss
+
+    ms_e, _, _ = timed(step_host, a.steps, max(a.warmup, 3))
+    e2e = world * n * a.steps / (ms_e * 1e-3)
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM): per-launch CUDA events on the launching stream --------------
+    ev = []
+    orig = ops.gemm
+
+    def gemm_timed(*args_, **kw):
+        s, e = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+        s.record()
+        r = orig(*args_, **kw)
+        e.record()
+        ev.append((s, e))
+        return r
+
+    import season_nerf_b200.network as netmod
+    netmod.ops.gemm = gemm_timed
+    prof_steps = 2
+    t.cuda.synchronize()
+    for i in range(prof_steps):
+        step_dev(a.warmup + a.steps + i)
+    t.cuda.synchronize()
+    netmod.ops.gemm = orig
+    gemm_ms = sum(s.elapsed_time(e) for s, e in ev) / prof_steps
+    n_gemm = len(ev) // prof_steps
+    flops_step = TRAIN_FLOP_PER_RAY * n
+    achieved = flops_step / (gemm_ms * 1e-3) / 1e12
+    peak = peaks["bf16_tflops_sustained"]
+    roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peaks["source"] + " sustained cuBLAS bf16",
+                "launches_per_step": n_gemm, "kernel_ms_per_step": gemm_ms, "step_ms": ms / a.steps,
+                "kernel_share_of_step": gemm_ms / (ms / a.steps),
+                "note": "achieved = algorithmic 2.086 GFLOP/ray-pair x rays per step / summed CUDA-event time of the GEMM launches of one step"}
+
+    # ---- secondary: fused render kernel, 512x512x96 view ----------------------------------------------------------------
+    render = None
+    if rank == 0 and not a.no_render:
+        render = bench_render(snb, ts.network, dev, H, W2C, peaks)
+        ts.network.train()
+
+    out = {"metric": "training rays/s (4096-ray step, fwd+bwd)", "value": value, "unit": "rays/s", "n_gpus": world,
+           "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "bf16" if a.precision == "bf16" else "f32", "data": "synthetic",
+           "config": {"workload": "train step, %d synthetic OMA_281-shaped rays + %d solar rays per GPU, S=96, Barron + solar "
+                                  "losses, Adam+OneCycle (BASELINE.json configs[1])" % (n, n),
+                      "rays_per_gpu": n, "samples_per_ray": S, "weights": "random-init T_NeRF(512,4)",
+                      "l2": "per-step working set (~10 GB of activations) far exceeds the 126 MB L2; no explicit flush"},
+           "clocks": clocks, "gpu_launches": int(launches),
+           "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+                   "ms_per_step": ms_e / a.steps},
+           "roofline": roofline}
+    if render is not None:
+        out["render"] = render
+    if rank == 0:
+        if world == 1 and not a.no_cpu:
+            out["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_render(snb, net, dev, H, W2C, peaks, size=512, reps=3):
+    """fused render kernel on a size x size x 96 view: kernel-only CUDA-event time + end-to-end component render."""
+    import numpy as np
+    import torch as t
+    from season_nerf_b200 import fused, ops
+    from season_nerf_b200.engine import sample_ts
+    net.eval()
+    vv = snb.world_angle_2_local_vec(80, 0, W2C, H)
+    XYZ = np.stack(np.meshgrid(np.linspace(1, -1, size), np.linspace(-1, 1, size), indexing="ij"), -1).reshape([-1, 2])
+    XYZ = np.concatenate([XYZ, np.zeros([XYZ.shape[0], 1])], 1)
+    tops = t.tensor(XYZ + vv / vv[2]).float().to(dev)
+    bots = t.tensor(XYZ - vv / vv[2]).float().to(dev)
+    ts_ = sample_ts(S, True, True).to(dev)
+    sun = t.tensor(snb.world_angle_2_local_vec(45, 135, W2C, H)).float().reshape(1, 3).to(dev)
+    N = tops.shape[0]
+    chunk = 65536
+    with t.no_grad():
+        pts, _ = ops.sample_rays(tops[:chunk], bots[:chunk], ts_, zero_oob=True)
+        p = pts.reshape(-1, 3)
+        for _ in range(2):
+            fused.run(net, p, sun, p.shape[0])
+        t.cuda.synchronize()
+        times = []
+        for _ in range(reps):
+            for i in range(0, N, chunk):
+                pts, _ = ops.sample_rays(tops[i:i + chunk], bots[i:i + chunk], ts_, zero_oob=True)
+                p = pts.reshape(-1, 3)
+                s, e = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+                s.record()
+                fused.run(net, p, sun, p.shape[0])
+                e.record()
+                times.append((s, e, p.shape[0]))
+        t.cuda.synchronize()
+        k_ms = sum(s.elapsed_time(e) for s, e, _ in times)
+        pts_total = sum(m for _, _, m in times)
+        achieved = pts_total * RENDER_FLOP_PER_POINT / (k_ms * 1e-3) / 1e12
+        # end to end through the public API (components + float64 composite + image D2H)
+        t.cuda.synchronize()
+        t0 = time.perf_counter()
+        D = snb.component_render_by_dir(net, [80, 0], [45, 135], 184 / 365, (size, size, S), W2C, H, dev, include_exact_solar=False)
+        imgs = snb.get_imgs_from_Img_Dict(D, (size, size, S), False)
+        _ = imgs["Season_Adj_Img"] * imgs["Shadow_Adjust"]
+        t.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+    peak = peaks["bf16_tflops"]
+    return {"workload": "%dx%dx%d view render, estimated shadows (BASELINE.json configs[2] without the exact march)" % (size, size, S),
+            "kernel_rays_per_s": pts_total / S / (k_ms * 1e-3), "e2e_rays_per_s": N / e2e_s,
+            "roofline": {"bound": "tensor", "kernel": "fused_eval_kernel (tcgen05)", "achieved": achieved, "peak": peak,
+                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peaks["source"] + " burst cuBLAS bf16", "launches": len(times),
+                         "ms_per_launch": k_ms / len(times)}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rays", type=int, default=4096)
+    ap.add_argument("--ref-rays", type=int, default=256, dest="ref_rays")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-render", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "ours" else max(a.warmup, 1)
+    if a.impl == "reference":
+        return run_reference(a)
+    run_ours(a)
+
+
+if __name__ == "__main__":
+    main()
