@@ -169,6 +169,187 @@ __global__ void __launch_bounds__(256) convert_kernel(const TS* __restrict__ src
   }
 }
 
+
+// ===================================================================================================
+// Vectorised variants (N % 8 == 0, 16-byte aligned rows): thread <-> 8 consecutive columns, so the per-column
+// BatchNorm constants live in registers and every global access is a 16/32-byte vector; rows are strided over
+// blockDim.y x gridDim.x.  bf16 build uses sin.approx / cos.approx (|argument| stays small after BatchNorm; the
+// result is rounded to bf16 anyway), the fp32 validation build keeps the accurate sinf / cosf.
+template <typename T> struct Vec8;
+template <> struct Vec8<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  static __device__ __forceinline__ float sin_(float x) { return sinf(x); }
+  static __device__ __forceinline__ float cos_(float x) { return cosf(x); }
+};
+template <> struct Vec8<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 t2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&t2);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  static __device__ __forceinline__ float sin_(float x) { return __sinf(x); }
+  static __device__ __forceinline__ float cos_(float x) { return __cosf(x); }
+};
+
+__device__ __forceinline__ void load8f(const float* p, float (&v)[8]) { Vec8<float>::load(p, v); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) sine_fwd_vec_kernel(const T* __restrict__ Z, int ldz, const float* __restrict__ a,
+                                                           const float* __restrict__ c, T* __restrict__ Y, int ldy,
+                                                           long long M, int N) {
+  const int col = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
+  if (col >= N) return;
+  float av[8], cv[8];
+  load8f(a + col, av);
+  load8f(c + col, cv);
+  for (long long r = blockIdx.x * (long long)blockDim.y + threadIdx.y; r < M; r += (long long)gridDim.x * blockDim.y) {
+    float z[8];
+    Vec8<T>::load(Z + r * ldz + col, z);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) z[i] = Vec8<T>::sin_(fmaf(av[i], z[i], cv[i]));
+    Vec8<T>::store(Y + r * ldy + col, z);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+sine_bwd_apply_vec_kernel(const T* __restrict__ dY, int ldd, const T* __restrict__ Z, int ldz, AffineCols p,
+                          const float* __restrict__ k1, const float* __restrict__ k2, T* __restrict__ dZ, int ldo,
+                          long long M, int N) {
+  const int col = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
+  if (col >= N) return;
+  float av[8], cv[8], mv[8], iv[8], k1v[8], k2v[8];
+  load8f(p.a + col, av);
+  load8f(p.c + col, cv);
+  const bool bn = k1 != nullptr;
+  if (bn) {
+    load8f(p.mean + col, mv);
+    load8f(p.invstd + col, iv);
+    load8f(k1 + col, k1v);
+    load8f(k2 + col, k2v);
+  }
+  for (long long r = blockIdx.x * (long long)blockDim.y + threadIdx.y; r < M; r += (long long)gridDim.x * blockDim.y) {
+    float z[8], d[8];
+    Vec8<T>::load(Z + r * ldz + col, z);
+    Vec8<T>::load(dY + r * ldd + col, d);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float g = d[i] * Vec8<T>::cos_(fmaf(av[i], z[i], cv[i]));
+      if (bn) g -= k1v[i] + (z[i] - mv[i]) * iv[i] * k2v[i];
+      d[i] = av[i] * g;
+    }
+    Vec8<T>::store(dZ + r * ldo + col, d);
+  }
+}
+
+// column reductions: two quantities per column accumulated in fp32 registers over <= 64 rows, then in fp64, then one
+// double atomicAdd per column per block-row.
+template <typename T, bool kBwd>
+__global__ void __launch_bounds__(256)
+col_reduce_vec_kernel(const T* __restrict__ X0, int ld0, const T* __restrict__ X1, int ld1, AffineCols p, long long M, int N,
+                      double* __restrict__ o0, double* __restrict__ o1) {
+  const int col = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
+  if (col >= N) return;
+  float av[8], cv[8], mv[8], iv[8];
+  if (kBwd) {
+    load8f(p.a + col, av);
+    load8f(p.c + col, cv);
+    load8f(p.mean + col, mv);
+    load8f(p.invstd + col, iv);
+  }
+  double s0[8], s1[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s0[i] = s1[i] = 0.0;
+  const long long stride = (long long)gridDim.x * blockDim.y;
+  long long r = blockIdx.x * (long long)blockDim.y + threadIdx.y;
+  while (r < M) {
+    float f0[8], f1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f0[i] = f1[i] = 0.f;
+    for (int it = 0; it < 64 && r < M; ++it, r += stride) {
+      float x[8];
+      Vec8<T>::load(X0 + r * ld0 + col, x);
+      if (kBwd) {
+        float z[8];
+        Vec8<T>::load(X1 + r * ld1 + col, z);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float g = x[i] * Vec8<T>::cos_(fmaf(av[i], z[i], cv[i]));
+          f0[i] += g;
+          f1[i] = fmaf(g, (z[i] - mv[i]) * iv[i], f1[i]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          f0[i] += x[i];
+          f1[i] = fmaf(x[i], x[i], f1[i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s0[i] += f0[i], s1[i] += f1[i];
+  }
+  // combine the blockDim.y row-lanes of this block through shared memory before touching global atomics
+  __shared__ double red[2][8][256 + 1];
+  const int t = threadIdx.y * blockDim.x + threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[0][i][t] = s0[i], red[1][i][t] = s1[i];
+  __syncthreads();
+  if (threadIdx.y == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      double a0 = 0, a1 = 0;
+      for (int y = 0; y < blockDim.y; ++y) a0 += red[0][i][y * blockDim.x + threadIdx.x], a1 += red[1][i][y * blockDim.x + threadIdx.x];
+      atomicAdd(o0 + col + i, a0);
+      atomicAdd(o1 + col + i, a1);
+    }
+  }
+}
+
+struct VecLaunch {
+  dim3 grid, block;
+  bool ok;
+};
+static inline VecLaunch vec_launch(long long M, int N, int ld0, int ld1, int ld2, const void* p0, const void* p1, const void* p2,
+                                   int elem_bytes, int max_waves) {
+  VecLaunch v;
+  v.ok = (N % 8 == 0) && (ld0 % 8 == 0) && (ld1 % 8 == 0) && (ld2 % 8 == 0) && ((((uintptr_t)p0) | ((uintptr_t)p1) | ((uintptr_t)p2)) % 16 == 0);
+  int tx = N / 8;
+  if (tx < 1) tx = 1;
+  int by = 1;
+  if (tx > 256) { by = (tx + 255) / 256; tx = 256; }
+  int ty = 256 / tx;
+  if (ty < 1) ty = 1;
+  v.block = dim3(tx, ty);
+  long long gx = (M + ty - 1) / ty;
+  long long cap = (long long)kNumSMs * max_waves;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  v.grid = dim3((unsigned)gx, by);
+  (void)elem_bytes;
+  return v;
+}
+
 }  // namespace snb
 
 using namespace snb;
@@ -204,6 +385,18 @@ extern "C" int snb_col_stats(const void* Z, int dtype, int ldz, long long M, int
   e = cudaMemsetAsync(sumsq, 0, sizeof(double) * N, st);
   if (e != cudaSuccess) return (int)e;
   if (M == 0) return SNB_OK;
+  {
+    VecLaunch v = vec_launch(M, N, ldz, 8, 8, Z, nullptr, nullptr, 0, 4);
+    if (v.ok && (N / 8) <= 256 && 256 % (N / 8) == 0) {
+      AffineCols none = {nullptr, nullptr, nullptr, nullptr};
+      if (dtype == SNB_F32) col_reduce_vec_kernel<float, false><<<v.grid, v.block, 0, st>>>((const float*)Z, ldz, nullptr, 0, none, M, N, sum, sumsq);
+      else if (dtype == SNB_BF16) col_reduce_vec_kernel<bf16, false><<<v.grid, v.block, 0, st>>>((const bf16*)Z, ldz, nullptr, 0, none, M, N, sum, sumsq);
+      else return SNB_ERR_ARG;
+      count_launch();
+      SNB_LAUNCH_CHECK();
+      return SNB_OK;
+    }
+  }
   const int grid = grid_for(M, 512, 4);
   if (dtype == SNB_F32) col_stats_kernel<float><<<grid, reduce_block(N), 0, st>>>((const float*)Z, ldz, M, N, sum, sumsq);
   else if (dtype == SNB_BF16) col_stats_kernel<bf16><<<grid, reduce_block(N), 0, st>>>((const bf16*)Z, ldz, M, N, sum, sumsq);
@@ -217,8 +410,19 @@ extern "C" int snb_sine_fwd(const void* Z, int ldz, const float* a, const float*
                             int dtype, void* stream) {
   SNB_CHECK_ARG(Z && a && c && Y && M >= 0 && N > 0 && ldz >= N && ldy >= N);
   if (M == 0) return SNB_OK;
-  const int grid = grid_for(M * ((N + 1) / 2), 256, 16);
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    VecLaunch v = vec_launch(M, N, ldz, ldy, 8, Z, Y, nullptr, 0, 8);
+    if (v.ok) {
+      if (dtype == SNB_F32) sine_fwd_vec_kernel<float><<<v.grid, v.block, 0, st>>>((const float*)Z, ldz, a, c, (float*)Y, ldy, M, N);
+      else if (dtype == SNB_BF16) sine_fwd_vec_kernel<bf16><<<v.grid, v.block, 0, st>>>((const bf16*)Z, ldz, a, c, (bf16*)Y, ldy, M, N);
+      else return SNB_ERR_ARG;
+      count_launch();
+      SNB_LAUNCH_CHECK();
+      return SNB_OK;
+    }
+  }
+  const int grid = grid_for(M * ((N + 1) / 2), 256, 16);
   if (dtype == SNB_F32) sine_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)Z, ldz, a, c, (float*)Y, ldy, M, N);
   else if (dtype == SNB_BF16) sine_fwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)Z, ldz, a, c, (bf16*)Y, ldy, M, N);
   else return SNB_ERR_ARG;
@@ -237,8 +441,19 @@ extern "C" int snb_sine_bwd_reduce(const void* dY, int ldd, const void* Z, int l
   e = cudaMemsetAsync(sgx, 0, sizeof(double) * N, st);
   if (e != cudaSuccess) return (int)e;
   if (M == 0) return SNB_OK;
-  const int grid = grid_for(M, 512, 4);
   AffineCols p = {a, c, mean, invstd};
+  {
+    VecLaunch v = vec_launch(M, N, ldd, ldz, 8, dY, Z, nullptr, 0, 4);
+    if (v.ok && (N / 8) <= 256 && 256 % (N / 8) == 0) {
+      if (dtype == SNB_F32) col_reduce_vec_kernel<float, true><<<v.grid, v.block, 0, st>>>((const float*)dY, ldd, (const float*)Z, ldz, p, M, N, sg, sgx);
+      else if (dtype == SNB_BF16) col_reduce_vec_kernel<bf16, true><<<v.grid, v.block, 0, st>>>((const bf16*)dY, ldd, (const bf16*)Z, ldz, p, M, N, sg, sgx);
+      else return SNB_ERR_ARG;
+      count_launch();
+      SNB_LAUNCH_CHECK();
+      return SNB_OK;
+    }
+  }
+  const int grid = grid_for(M, 512, 4);
   if (dtype == SNB_F32) sine_bwd_reduce_kernel<float><<<grid, reduce_block(N), 0, st>>>((const float*)dY, ldd, (const float*)Z, ldz, p, M, N, sg, sgx);
   else if (dtype == SNB_BF16) sine_bwd_reduce_kernel<bf16><<<grid, reduce_block(N), 0, st>>>((const bf16*)dY, ldd, (const bf16*)Z, ldz, p, M, N, sg, sgx);
   else return SNB_ERR_ARG;
@@ -254,9 +469,20 @@ extern "C" int snb_sine_bwd_apply(const void* dY, int ldd, const void* Z, int ld
   SNB_CHECK_ARG((k1 == nullptr) == (k2 == nullptr));
   SNB_CHECK_ARG(!k1 || (mean && invstd));
   if (M == 0) return SNB_OK;
-  const int grid = grid_for(M * N, 256, 16);
   cudaStream_t st = (cudaStream_t)stream;
   AffineCols p = {a, c, mean, invstd};
+  {
+    VecLaunch v = vec_launch(M, N, ldd, ldz, ldo, dY, Z, dZ, 0, 8);
+    if (v.ok) {
+      if (dtype == SNB_F32) sine_bwd_apply_vec_kernel<float><<<v.grid, v.block, 0, st>>>((const float*)dY, ldd, (const float*)Z, ldz, p, k1, k2, (float*)dZ, ldo, M, N);
+      else if (dtype == SNB_BF16) sine_bwd_apply_vec_kernel<bf16><<<v.grid, v.block, 0, st>>>((const bf16*)dY, ldd, (const bf16*)Z, ldz, p, k1, k2, (bf16*)dZ, ldo, M, N);
+      else return SNB_ERR_ARG;
+      count_launch();
+      SNB_LAUNCH_CHECK();
+      return SNB_OK;
+    }
+  }
+  const int grid = grid_for(M * N, 256, 16);
   if (dtype == SNB_F32) sine_bwd_apply_kernel<float><<<grid, 256, 0, st>>>((const float*)dY, ldd, (const float*)Z, ldz, p, k1, k2, (float*)dZ, ldo, M, N);
   else if (dtype == SNB_BF16) sine_bwd_apply_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dY, ldd, (const bf16*)Z, ldz, p, k1, k2, (bf16*)dZ, ldo, M, N);
   else return SNB_ERR_ARG;
