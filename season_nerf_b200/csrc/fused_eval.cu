@@ -232,6 +232,16 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_eval_kernel(const Fuse
             if (lane == 0) mbar_arrive(chunk_ready(dst0));
           }
         } else {
+          // bias values do not depend on the accumulator: fetch them BEFORE blocking on the commit barrier
+          float bv[64];
+          if (kind == K_SINE) {
+            const float4* bp4 = reinterpret_cast<const float4*>(p.bias + bias_off + 64 * h);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float4 q = __ldg(bp4 + e);
+              bv[4 * e] = q.x, bv[4 * e + 1] = q.y, bv[4 * e + 2] = q.z, bv[4 * e + 3] = q.w;
+            }
+          }
           mbar_wait(acc_full(region), (full_par >> region) & 1);
           full_par ^= 1u << region;
           if (also != 0xFF) mbar_wait(acc_full(also), (full_par >> also) & 1);
@@ -239,20 +249,20 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_eval_kernel(const Fuse
           const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + d_col;
           if (kind == K_SINE) {
             const uint32_t slot_addr = slots_base + (h ? dst1 : dst0) * kSlotBytes;
-            const float* bp = p.bias + bias_off + 64 * h;
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32(t_row + 64 * h, r0);
+            tmem_ld_32x32(t_row + 64 * h + 32, r1);
+            tmem_ld_wait();
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              uint32_t r[32];
-              tmem_ld_32x32(t_row + 64 * h + 32 * half, r);
-              tmem_ld_wait();
+            for (int u = 0; u < 8; ++u) {
+              float v[8];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                float v[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = __sinf(__uint_as_float(r[8 * u + e]) + __ldg(bp + 32 * half + 8 * u + e));
-                store_row_unit(slot_addr, row, 4 * half + u,
-                               make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
+              for (int e = 0; e < 8; ++e) {
+                const uint32_t a = u < 4 ? r0[8 * u + e] : r1[8 * (u - 4) + e];
+                v[e] = __sinf(__uint_as_float(a) + bv[8 * u + e]);
               }
+              store_row_unit(slot_addr, row, u,
+                             make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
             }
             fence_proxy_async_smem();
             tc_fence_before();

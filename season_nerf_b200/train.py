@@ -10,6 +10,46 @@ from .engine import All_in_One_Eval
 from .network import T_NeRF
 
 
+def flat_allreduce_mean_(tensors, world_size, flat=None):
+    """One flat fp32 bucket: pack -> all_reduce(SUM) -> /world_size -> unpack (in place).  Works for NCCL (CUDA) and
+    gloo (CPU, used by the host-logic tests).  Returns the bucket for reuse."""
+    n = sum(x.numel() for x in tensors)
+    if n == 0:
+        return flat
+    dev = tensors[0].device
+    if flat is None or flat.numel() != n or flat.device != dev:
+        flat = t.empty(n, device=dev, dtype=t.float32)
+    o = 0
+    for x in tensors:
+        flat[o:o + x.numel()].copy_(x.reshape(-1))
+        o += x.numel()
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat.div_(world_size)
+    o = 0
+    for x in tensors:
+        x.copy_(flat[o:o + x.numel()].reshape(x.shape))
+        o += x.numel()
+    return flat
+
+
+def shard_range(n, rank, world_size):
+    """contiguous ray range [lo, hi) of `rank` (render sharding; remainder rays go to the first ranks)."""
+    base, rem = divmod(n, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_rows(local, n_total, rank, world_size):
+    """all_gather of per-rank row blocks of unequal length (final gather of a ray-sharded render) -> [n_total, ...]."""
+    sizes = [shard_range(n_total, r, world_size)[1] - shard_range(n_total, r, world_size)[0] for r in range(world_size)]
+    mx = max(sizes)
+    pad = t.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    outs = [t.empty_like(pad) for _ in range(world_size)]
+    dist.all_gather(outs, pad)
+    return t.cat([o[:s] for o, s in zip(outs, sizes)], 0)
+
+
 class TrainStep:
     """One learning-mode section of T_NeRF_Net_Tool (learning_mode 2..4: free training, use_prior False) or the
     DSM-guided section (use_prior True, learning_mode 1 with jump_start)."""
@@ -47,20 +87,8 @@ class TrainStep:
 
     def _allreduce_grads(self):
         """one flat fp32 bucket (3.19 M network gradients + the adaptive-loss scalars), NCCL sum -> mean"""
-        ps = [p for p in self.params + self.ada_params if p.grad is not None]
-        n = sum(p.numel() for p in ps)
-        if self._flat is None or self._flat.numel() != n:
-            self._flat = t.empty(n, device=self.device, dtype=t.float32)
-        o = 0
-        for p in ps:
-            self._flat[o:o + p.numel()].copy_(p.grad.reshape(-1))
-            o += p.numel()
-        dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
-        self._flat.div_(self.world_size)
-        o = 0
-        for p in ps:
-            p.grad.copy_(self._flat[o:o + p.numel()].reshape(p.shape))
-            o += p.numel()
+        grads = [p.grad for p in self.params + self.ada_params if p.grad is not None]
+        self._flat = flat_allreduce_mean_(grads, self.world_size, self._flat)
 
     def step(self, data_dict, current_step, **inject):
         """mg_run_NeRF.py:288-326 without the per-term TensorBoard .item() syncs; returns the loss dict."""
