@@ -90,6 +90,14 @@ int snb_pe_encode(const float* x, int ldx, long long M, int D, int n_freq, void*
 int snb_gemm(const void* A, int lda, int a_t, const void* B, int ldb, int b_t, void* C, int ldc, const float* bias,
              float alpha, int accumulate, long long M, int N, int K, int dtype, int out_dtype, void* stream);
 
+/* bf16 GEMM (both operands K-contiguous, bf16 result) with the train-mode BatchNorm statistics of the result fused
+ * into the epilogue: stats[0..N) += column sums, stats[N..2N) += column sums of squares of the STORED bf16 values
+ * (caller zeroes stats).  Returns SNB_ERR_UNSUPPORTED (-2) for shapes the CTA-pair kernel does not take
+ * (M < 256, N < 128, N > 1024, unaligned C): the caller then uses snb_gemm + snb_col_stats.
+ * Replaces nn.Linear + the batch-statistics pass of nn.BatchNorm1d in misc.py:169-170,188-189. */
+int snb_gemm_stats(const void* A, int lda, const void* B, int ldb, void* C, int ldc, const float* bias, float alpha,
+                   long long M, int N, int K, float* stats, void* stream);
+
 /* column statistics for train-mode BatchNorm1d (misc.py:169-170): sum[n], sumsq[n] over M rows (float64 out). */
 int snb_col_stats(const void* Z, int dtype, int ldz, long long M, int N, double* sum, double* sumsq, void* stream);
 
@@ -122,6 +130,14 @@ int snb_convert(const void* src, int src_dtype, int lds, void* dst, int dst_dtyp
 int snb_fused_eval(const void* program, unsigned n_mma, unsigned n_epi, unsigned mma_off, unsigned epi_off,
                    unsigned bias_off, unsigned w_off, const float* pts, long long M, int S, const float* sun,
                    float* rho_raw, float* pos4, float* vis_raw, float* adj, void* stream);
+
+/* CTA-pair edition of the fused render kernel (the one the product dispatches to): two CTAs of a cluster render a
+ * tile of 256 points with tcgen05.mma.cta_group::2 and stage half of every weight tile each.  `program` is the device
+ * image built by season_nerf_b200/packing2.py: schedule tables, biases and the BatchNorm-folded bf16 weights as ONE
+ * row-major [w_rows, 64] matrix (TMA applies the 128-byte swizzle).  Same inputs / outputs as snb_fused_eval. */
+int snb_fused_eval2(const void* program, unsigned n_mma, unsigned n_epi, unsigned mma_off, unsigned epi_off,
+                    unsigned bias_off, unsigned w_off, unsigned w_rows, const float* pts, long long M, int S,
+                    const float* sun, float* rho_raw, float* pos4, float* vis_raw, float* adj, void* stream);
 
 #ifdef __cplusplus
 }

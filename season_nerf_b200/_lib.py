@@ -27,12 +27,14 @@ SIGNATURES = {
     "snb_year_sweep": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p],
     "snb_pe_encode": [_p, _i, _ll, _i, _i, _p, _i, _i, _i, _i, _p],
     "snb_gemm": [_p, _i, _i, _p, _i, _i, _p, _i, _p, _f, _i, _ll, _i, _i, _i, _i, _p],
+    "snb_gemm_stats": [_p, _i, _p, _i, _p, _i, _p, _f, _ll, _i, _i, _p, _p],
     "snb_col_stats": [_p, _i, _i, _ll, _i, _p, _p, _p],
     "snb_sine_fwd": [_p, _i, _p, _p, _p, _i, _ll, _i, _i, _p],
     "snb_sine_bwd_reduce": [_p, _i, _p, _i, _p, _p, _p, _p, _ll, _i, _i, _p, _p, _p],
     "snb_sine_bwd_apply": [_p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _ll, _i, _i, _p],
     "snb_convert": [_p, _i, _i, _p, _i, _i, _ll, _i, _p],
     "snb_fused_eval": [_p, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, _p, _ll, _i, _p, _p, _p, _p, _p, _p],
+    "snb_fused_eval2": [_p, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, _p, _ll, _i, _p, _p, _p, _p, _p, _p],
 }
 _RESTYPES = {"snb_launch_count": _ll, "snb_error_string": C.c_char_p}
 

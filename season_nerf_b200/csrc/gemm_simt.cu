@@ -84,6 +84,17 @@ gemm_f32_kernel(const float* __restrict__ A, long long sam, long long sak, const
 int snb_gemm_bf16_tc(const void* A, int lda, int a_t, const void* B, int ldb, int b_t, void* C, int ldc,
                      const float* bias, float alpha, int accumulate, long long M, int N, int K, int out_dtype,
                      cudaStream_t st);
+// implemented in gemm_tc2.cu (CTA-pair kernel; SNB_ERR_UNSUPPORTED = use the single-CTA kernel)
+int snb_gemm_bf16_tc2(const void* A, int lda, int a_t, const void* B, int ldb, int b_t, void* C, int ldc,
+                      const float* bias, float alpha, int accumulate, long long M, int N, int K, int out_dtype,
+                      float* stats, cudaStream_t st);
+
+extern "C" int snb_gemm_stats(const void* A, int lda, const void* B, int ldb, void* C, int ldc, const float* bias,
+                              float alpha, long long M, int N, int K, float* stats, void* stream) {
+  SNB_CHECK_ARG(A && B && C && stats && M >= 0 && N > 0 && K > 0 && ldc >= N);
+  if (M == 0) return SNB_OK;
+  return snb_gemm_bf16_tc2(A, lda, 0, B, ldb, 0, C, ldc, bias, alpha, 0, M, N, K, SNB_BF16, stats, (cudaStream_t)stream);
+}
 
 extern "C" int snb_gemm(const void* A, int lda, int a_t, const void* B, int ldb, int b_t, void* C, int ldc,
                         const float* bias, float alpha, int accumulate, long long M, int N, int K, int dtype,
@@ -91,7 +102,12 @@ extern "C" int snb_gemm(const void* A, int lda, int a_t, const void* B, int ldb,
   SNB_CHECK_ARG(A && B && C && M >= 0 && N > 0 && K > 0 && ldc >= N);
   if (M == 0) return SNB_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == SNB_BF16) return snb_gemm_bf16_tc(A, lda, a_t, B, ldb, b_t, C, ldc, bias, alpha, accumulate, M, N, K, out_dtype, st);
+  if (dtype == SNB_BF16) {
+    const int rc = snb_gemm_bf16_tc2(A, lda, a_t, B, ldb, b_t, C, ldc, bias, alpha, accumulate, M, N, K, out_dtype, nullptr, st);
+    if (rc != SNB_ERR_UNSUPPORTED) return rc;
+    return snb_gemm_bf16_tc(A, lda, a_t, B, ldb, b_t, C, ldc, bias, alpha, accumulate, M, N, K, out_dtype, st);
+  }
+
   if (dtype != SNB_F32 || out_dtype != SNB_F32) return SNB_ERR_UNSUPPORTED;
   const long long sam = a_t ? 1 : lda, sak = a_t ? lda : 1;
   const long long sbn = b_t ? 1 : ldb, sbk = b_t ? ldb : 1;

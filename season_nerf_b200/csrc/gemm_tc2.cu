@@ -1,0 +1,497 @@
+// CTA-pair bf16 GEMM for sm_100a (the large per-layer GEMMs of the TRAINING path: forward, input gradient, weight
+// gradient).  Two CTAs of a cluster (one TPC) cooperate on a 256 x 256 output tile with tcgen05.mma.cta_group::2:
+// each CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256 N-rows), so that per CTA the
+// tensor core reads 8 KB of shared memory per K=16 step instead of 12 KB and L2->SMEM traffic per flop halves
+// with respect to the single-CTA 128 x 256 tile of gemm_tc.cu.  5-stage TMA ring (32 KB / stage / CTA), two TMEM
+// accumulator stages (2 x 256 columns) so that the epilogue of tile i overlaps the main loop of tile i+1.
+//
+//   C[M,N] = alpha * (A[M,K] . B[N,K]^T + bias[N])   (+ C | atomically added for split-K)
+//
+// Epilogue (4 warps per CTA, warp q owns TMEM lanes 32q..32q+31 = 32 output rows):
+//   * bf16 store mode: TMEM -> registers -> (alpha, bias) -> bf16 -> 128B-swizzled shared staging (4 KB per warp,
+//     double buffered) -> TMA tensor store (fully coalesced 128-byte rows, M/N tails clipped by the tensor map).
+//     Optionally fused: per-column sum and sum of squares of the STORED (bf16-rounded) values - the train-mode
+//     BatchNorm statistics of the layer (misc.py:169-170,189) - accumulated in shared memory over all tiles of the
+//     CTA and flushed with one atomicAdd per column per CTA at the end.
+//   * direct mode (fp32 output, accumulate, split-K atomics): registers -> global, vectorised (red.global.add.v4.f32).
+//
+// Barrier protocol per CTA pair (leader = cluster rank 0):
+//   full[s]   leader only; 1 arrival (leader's expect_tx) + the TMA bytes of BOTH CTAs
+//   empty[s]  each CTA; released by tcgen05.commit multicast from the leader's MMA thread
+//   tfull[a]  each CTA; accumulator stage complete (commit multicast)
+//   tempty[a] leader only; 8 arrivals = 4 epilogue warps x 2 CTAs (remote mbarrier.arrive from the peer)
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "api.h"
+
+namespace snb {
+using namespace tc;
+
+int make_tmap_bf16(CUtensorMap* m, const void* ptr, long long rows, long long cols, long long ld, int box_cols, int box_rows);
+
+constexpr int k2BM = 128;                       // rows of A / C per CTA (pair tile: 256)
+constexpr int k2BK = 64;
+constexpr int k2Stages = 5;
+constexpr int k2Threads = 192;
+constexpr int k2MaxBN = 256;
+constexpr uint32_t k2ABytes = k2BM * k2BK * 2;                 // 16 KB
+constexpr uint32_t k2BBytes = (k2MaxBN / 2) * k2BK * 2;        // 16 KB (this CTA's half of the B tile)
+constexpr uint32_t k2StageBytes = k2ABytes + k2BBytes;         // 32 KB
+constexpr uint32_t k2CWarpBytes = 2 * 32 * 128;                // two 32-row x 128-byte staging buffers per epilogue warp
+constexpr uint32_t k2CBytes = 4 * k2CWarpBytes;                // 32 KB
+constexpr int k2MaxStatN = 1024;
+constexpr uint32_t k2StatBytes = 2 * k2MaxStatN * 4;           // 8 KB
+constexpr uint32_t k2Smem = 1024 + k2Stages * k2StageBytes + k2CBytes + k2StatBytes + 256;
+
+struct Gemm2Params {
+  long long M;
+  int N, K;
+  int block_n;                 // UMMA N of the pair (multiple of 32; 128 or 256 if B is MN-major)
+  int tiles_m, tiles_n, splits, kb_per_split;
+  void* C;
+  int ldc;
+  int out_bf16;
+  int mode;                    // 0 store, 1 accumulate, 2 atomic add (fp32)
+  int tma_store;               // bf16 store through shared memory + TMA
+  const float* bias;
+  float alpha;
+  float* stats;                // [2*N] column sum / sum of squares of the stored values, or null
+};
+
+template <bool kAT, bool kBT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
+                  const __grid_constant__ CUtensorMap tmapC, const Gemm2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t cstage_base = smem_base + k2Stages * k2StageBytes;
+  float* stat_smem = reinterpret_cast<float*>(smem_al + k2Stages * k2StageBytes + k2CBytes);
+  const uint32_t bar_base = cstage_base + k2CBytes + k2StatBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (k2Stages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * k2Stages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * k2Stages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * k2Stages + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_al + k2Stages * k2StageBytes + k2CBytes + k2StatBytes + 8u * (2 * k2Stages + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int total_items = p.tiles_m * p.tiles_n * p.splits;
+  const int num_kb_total = (p.K + k2BK - 1) / k2BK;
+  const int half_n = p.block_n >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < k2Stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 8);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmapA);
+    tma_prefetch_desc(&tmapB);
+    if (p.tma_store) tma_prefetch_desc(&tmapC);
+  }
+  if (p.stats) {
+    for (int i = threadIdx.x; i < 2 * k2MaxStatN; i += k2Threads) stat_smem[i] = 0.f;
+  }
+  if (warp == 1) tmem_alloc_cg2(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  // work item -> (tile_m, tile_n, split); tile_n fastest so that the pair reuses its A rows from L2
+  auto decode = [&](int t, int& tm, int& tn, int& ks) {
+    ks = t % p.splits;
+    tn = (t / p.splits) % p.tiles_n;
+    tm = t / (p.splits * p.tiles_n);
+  };
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs; bytes are credited to the leader's full barrier) =================
+    if (elect_one()) {
+      const uint32_t b_bytes = kBT ? (uint32_t)(((half_n + 63) / 64) * 64 * k2BK * 2) : (uint32_t)(half_n * k2BK * 2);
+      const uint32_t tx_pair = 2u * (k2ABytes + b_bytes);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < total_items; t += num_pairs) {
+        int tm, tn, ks;
+        decode(t, tm, tn, ks);
+        const int m0 = tm * (2 * k2BM) + (int)rank * k2BM;
+        const int n0 = tn * p.block_n + (int)rank * half_n;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, num_kb_total);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * k2StageBytes;
+          const uint32_t sb = sa + k2ABytes;
+          const uint32_t fb = mapa_shared(full_bar(stage), 0);
+          if (rank == 0) mbar_expect_tx(full_bar(stage), tx_pair);
+          const int k0 = kb * k2BK;
+          if (!kAT) {
+            tma_load_2d_cg2(sa, &tmapA, fb, k0, m0);                 // box {64 k, 128 m}
+          } else {
+            tma_load_2d_cg2(sa, &tmapA, fb, m0, k0);                 // box {64 m, 64 k} x 2
+            tma_load_2d_cg2(sa + 8192, &tmapA, fb, m0 + 64, k0);
+          }
+          if (!kBT) {
+            tma_load_2d_cg2(sb, &tmapB, fb, k0, n0);                 // box {64 k, half_n}
+          } else {
+            for (int j = 0; j * 64 < half_n; ++j) tma_load_2d_cg2(sb + j * 8192, &tmapB, fb, n0 + 64 * j, k0);
+          }
+          if (++stage == k2Stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA only) =================
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(2 * k2BM, p.block_n, kAT ? 1 : 0, kBT ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = pair; t < total_items; t += num_pairs) {
+        int tm, tn, ks;
+        decode(t, tm, tn, ks);
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, num_kb_total);
+        mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * k2MaxBN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t sa = smem_base + stage * k2StageBytes;
+            const uint32_t sb = sa + k2ABytes;
+#pragma unroll
+            for (int k = 0; k < k2BK / 16; ++k) {
+              const uint64_t adesc = kAT ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
+              const uint64_t bdesc = kBT ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
+              umma_f16_cg2(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit_cg2_mc(empty_bar(stage), 3);                   // frees the stage in both CTAs
+            if (kb == kb1 - 1) umma_commit_cg2_mc(tfull_bar(acc), 3);  // accumulator complete -> both epilogues
+          }
+          __syncwarp();
+          if (++stage == k2Stages) { stage = 0; phase ^= 1; }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ================= epilogue =================
+    const int q = warp & 3;                 // TMEM lane quarter of this warp
+    const uint32_t tempty_leader0 = mapa_shared(tempty_bar(0), 0);
+    const uint32_t tempty_leader1 = mapa_shared(tempty_bar(1), 0);
+    const uint32_t cbuf = cstage_base + (uint32_t)q * k2CWarpBytes;
+    uint32_t cpar = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    float st_acc[2][4][4];       // [tile column][64-column chunk][sum c0, sum c1, sumsq c0, sumsq c1]
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) st_acc[i][j][k] = 0.f;
+    for (int t = pair; t < total_items; t += num_pairs) {
+      int tm, tn, ks;
+      decode(t, tm, tn, ks);
+      const long long row0 = (long long)tm * (2 * k2BM) + (long long)rank * k2BM + q * 32;
+      const long long row = row0 + lane;
+      const int n0 = tn * p.block_n;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * k2MaxBN;
+      if (p.tma_store) {
+        int rows_valid = 0;
+        if (row0 < p.M) rows_valid = (int)min((long long)32, p.M - row0);
+        for (int c = 0; c < p.block_n; c += 64) {
+          const int cols_valid = min(64, p.N - (n0 + c));
+          if (cols_valid <= 0) break;
+          // bias of the 64 columns of this chunk: independent of the accumulator, issue before the TMEM load wait
+          float ab[64];
+#pragma unroll
+          for (int i = 0; i < 64; ++i) ab[i] = 0.f;
+          if (p.bias) {
+            if (cols_valid == 64) {
+              const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + c);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float4 v = __ldg(b4 + i);
+                ab[4 * i] = v.x, ab[4 * i + 1] = v.y, ab[4 * i + 2] = v.z, ab[4 * i + 3] = v.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 64; ++i)
+                if (i < cols_valid) ab[i] = __ldg(p.bias + n0 + c + i);
+            }
+          }
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32(t_addr + c, r0);
+          tmem_ld_32x32(t_addr + c + 32, r1);
+          const uint32_t buf = cbuf + (cpar ? 4096u : 0u);
+          if (lane == 0) bulk_wait_group_read<1>();      // the store that last read this buffer has drained it
+          __syncwarp();
+          tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const uint32_t a = u < 4 ? r0[8 * u + e] : r1[8 * (u - 4) + e];
+              v[e] = p.alpha * (__uint_as_float(a) + ab[8 * u + e]);
+            }
+            const uint32_t addr = buf + (uint32_t)lane * 128u + (uint32_t)((u ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(v[0], v[1])),
+                         "r"(pack_bf16x2(v[2], v[3])), "r"(pack_bf16x2(v[4], v[5])), "r"(pack_bf16x2(v[6], v[7]))
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && rows_valid > 0) {
+            if (p.mode == 1) tma_reduce_add_2d(&tmapC, buf, n0 + c, (int)row0);
+            else tma_store_2d(&tmapC, buf, n0 + c, (int)row0);
+            bulk_commit_group();
+          }
+          if (p.stats) {
+            // column statistics of the stored bf16 values: lane j owns columns (2j, 2j+1) of the chunk and keeps
+            // their partial sums in registers across all tiles of the CTA (N <= 512: 2 tile columns x 4 chunks)
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+            const uint32_t lbase = buf + (uint32_t)((lane & 3) << 2);
+            if (rows_valid == 32) {
+#pragma unroll
+              for (int r8 = 0; r8 < 32; r8 += 8) {
+                uint32_t w[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const int r = r8 + i;
+                  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w[i]) : "r"(lbase + (uint32_t)r * 128u + (uint32_t)(((lane >> 2) ^ (r & 7)) << 4)));
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float lo = __uint_as_float(w[i] << 16), hi = __uint_as_float(w[i] & 0xFFFF0000u);
+                  s0 += lo, s1 += hi;
+                  q0 = fmaf(lo, lo, q0), q1 = fmaf(hi, hi, q1);
+                }
+              }
+            } else {
+              for (int r = 0; r < rows_valid; ++r) {
+                uint32_t w;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(lbase + (uint32_t)r * 128u + (uint32_t)(((lane >> 2) ^ (r & 7)) << 4)));
+                const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xFFFF0000u);
+                s0 += lo, s1 += hi;
+                q0 = fmaf(lo, lo, q0), q1 = fmaf(hi, hi, q1);
+              }
+            }
+#pragma unroll
+            for (int tnn = 0; tnn < 2; ++tnn)
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc)
+                if (tn == tnn && c == 64 * cc) {
+                  st_acc[tnn][cc][0] += s0, st_acc[tnn][cc][1] += s1;
+                  st_acc[tnn][cc][2] += q0, st_acc[tnn][cc][3] += q1;
+                }
+            __syncwarp();
+          }
+          cpar ^= 1;
+        }
+      } else {
+        for (int c = 0; c < p.block_n; c += 32) {
+          const int ncol = min(32, p.N - (n0 + c));
+          if (ncol <= 0) break;
+          float ab[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) ab[i] = (p.bias && i < ncol) ? __ldg(p.bias + n0 + c + i) : 0.f;
+          uint32_t r[32];
+          tmem_ld_32x32(t_addr + c, r);
+          tmem_ld_wait();
+          if (row < p.M) {
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = p.alpha * (__uint_as_float(r[i]) + ab[i]);
+            if (p.out_bf16) {
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + n0 + c;
+              const bool vec = ncol == 32 && (p.ldc & 7) == 0 && ((n0 + c) & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+              if (vec) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                  if (p.mode == 1) {
+                    const uint4 o = *reinterpret_cast<const uint4*>(dst + i);
+                    const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      v[i + 2 * e] += __uint_as_float(ow[e] << 16);
+                      v[i + 2 * e + 1] += __uint_as_float(ow[e] & 0xFFFF0000u);
+                    }
+                  }
+                  *reinterpret_cast<uint4*>(dst + i) = make_uint4(pack_bf16x2(v[i], v[i + 1]), pack_bf16x2(v[i + 2], v[i + 3]),
+                                                                   pack_bf16x2(v[i + 4], v[i + 5]), pack_bf16x2(v[i + 6], v[i + 7]));
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (i < ncol) {
+                    float o = v[i];
+                    if (p.mode == 1) o += __bfloat162float(dst[i]);
+                    dst[i] = __float2bfloat16_rn(o);
+                  }
+              }
+            } else {
+              float* dst = reinterpret_cast<float*>(p.C) + row * p.ldc + n0 + c;
+              const bool vec = ncol == 32 && (p.ldc & 3) == 0 && ((n0 + c) & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+              if (p.mode == 2) {
+                if (vec) {
+#pragma unroll
+                  for (int i = 0; i < 32; i += 4)
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(v[i]), "f"(v[i + 1]),
+                                 "f"(v[i + 2]), "f"(v[i + 3])
+                                 : "memory");
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i)
+                    if (i < ncol) atomicAdd(dst + i, v[i]);
+                }
+              } else if (vec) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                  float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                  if (p.mode == 1) {
+                    const float4 old = *reinterpret_cast<const float4*>(dst + i);
+                    o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
+                  }
+                  *reinterpret_cast<float4*>(dst + i) = o;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (i < ncol) dst[i] = (p.mode == 1) ? dst[i] + v[i] : v[i];
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (p.tma_store && lane == 0) bulk_wait_group<0>();
+    if (p.stats) {
+      // flush the CTA's column statistics: combine the four warps in shared memory, then one atomic per column
+#pragma unroll
+      for (int tnn = 0; tnn < 2; ++tnn)
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const int col = tnn * p.block_n + 64 * cc + 2 * lane;
+          if (64 * cc < p.block_n && col + 1 < k2MaxStatN) {
+            atomicAdd(stat_smem + col, st_acc[tnn][cc][0]);
+            atomicAdd(stat_smem + col + 1, st_acc[tnn][cc][1]);
+            atomicAdd(stat_smem + k2MaxStatN + col, st_acc[tnn][cc][2]);
+            atomicAdd(stat_smem + k2MaxStatN + col + 1, st_acc[tnn][cc][3]);
+          }
+        }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int te = threadIdx.x - 64;
+      const int ncols = p.N < k2MaxStatN ? p.N : k2MaxStatN;
+      for (int i = te; i < ncols; i += 128) {
+        const float s = stat_smem[i], ss = stat_smem[k2MaxStatN + i];
+        if (s != 0.f || ss != 0.f) {
+          atomicAdd(p.stats + i, s);
+          atomicAdd(p.stats + p.N + i, ss);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();      // the peer must not exit while the leader's MMAs / commits still target its shared memory
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_cg2(tmem_base, 512);
+  }
+}
+
+}  // namespace snb
+
+using namespace snb;
+
+// returns SNB_ERR_UNSUPPORTED when the shape is better served by the single-CTA kernel (small M / N)
+int snb_gemm_bf16_tc2(const void* A, int lda, int a_t, const void* B, int ldb, int b_t, void* C, int ldc,
+                      const float* bias, float alpha, int accumulate, long long M, int N, int K, int out_dtype,
+                      float* stats, cudaStream_t st) {
+  if (M < 256 || N < 128) return SNB_ERR_UNSUPPORTED;
+  if (stats && (N > 512 || accumulate != 0 || out_dtype != SNB_BF16)) return SNB_ERR_UNSUPPORTED;
+  SNB_CHECK_ARG((lda % 8) == 0 && (ldb % 8) == 0 && (((uintptr_t)A) & 15) == 0 && (((uintptr_t)B) & 15) == 0);
+  SNB_CHECK_ARG(out_dtype == SNB_F32 || out_dtype == SNB_BF16);
+  SNB_CHECK_ARG(accumulate >= 0 && accumulate <= 2 && !(accumulate == 2 && out_dtype != SNB_F32));
+  Gemm2Params p;
+  p.M = M, p.N = N, p.K = K;
+  p.block_n = N >= 192 ? 256 : 128;
+  p.tiles_m = (int)((M + 2 * k2BM - 1) / (2 * k2BM));
+  p.tiles_n = (N + p.block_n - 1) / p.block_n;
+  const int num_pairs = kNumSMs / 2;
+  const int num_kb = (K + k2BK - 1) / k2BK;
+  int splits = 1;
+  if (accumulate == 2) {  // split-K for the (few output tiles, huge K) weight-gradient shape
+    const int tiles = p.tiles_m * p.tiles_n;
+    splits = (2 * num_pairs + tiles - 1) / tiles;
+    if (splits > num_kb) splits = num_kb;
+    if (splits < 1) splits = 1;
+  }
+  p.kb_per_split = (num_kb + splits - 1) / splits;
+  p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
+  p.C = C, p.ldc = ldc, p.out_bf16 = out_dtype == SNB_BF16, p.mode = accumulate, p.bias = bias, p.alpha = alpha;
+  p.stats = stats;
+  p.tma_store = (out_dtype == SNB_BF16 && accumulate <= 1 && (ldc % 8) == 0 && (((uintptr_t)C) & 15) == 0) ? 1 : 0;
+  if (stats && !p.tma_store) return SNB_ERR_UNSUPPORTED;
+
+  CUtensorMap ta, tb, tcm;
+  int rc;
+  const int half_n = p.block_n / 2;
+  if (!a_t) rc = make_tmap_bf16(&ta, A, M, K, lda, k2BK, k2BM);
+  else rc = make_tmap_bf16(&ta, A, K, M, lda, 64, k2BK);
+  if (rc) return rc;
+  if (!b_t) rc = make_tmap_bf16(&tb, B, N, K, ldb, k2BK, half_n);
+  else rc = make_tmap_bf16(&tb, B, K, N, ldb, 64, k2BK);
+  if (rc) return rc;
+  if (p.tma_store) {
+    rc = make_tmap_bf16(&tcm, C, M, N, ldc, 64, 32);
+    if (rc) return rc;
+  } else {
+    tcm = ta;
+  }
+  const int total = p.tiles_m * p.tiles_n * p.splits;
+  const int grid = 2 * (total < num_pairs ? total : num_pairs);
+#define SNB_LAUNCH_GEMM2(AT, BT)                                                                             \
+  do {                                                                                                       \
+    static bool attr_set = false;                                                                            \
+    if (!attr_set) {                                                                                         \
+      cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel<AT, BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2Smem); \
+      if (e != cudaSuccess) return (int)e;                                                                   \
+      attr_set = true;                                                                                       \
+    }                                                                                                        \
+    gemm2_bf16_kernel<AT, BT><<<grid, k2Threads, k2Smem, st>>>(ta, tb, tcm, p);                              \
+  } while (0)
+  if (!a_t && !b_t) SNB_LAUNCH_GEMM2(false, false);
+  else if (!a_t && b_t) SNB_LAUNCH_GEMM2(false, true);
+  else if (a_t && !b_t) SNB_LAUNCH_GEMM2(true, false);
+  else SNB_LAUNCH_GEMM2(true, true);
+#undef SNB_LAUNCH_GEMM2
+  count_launch();
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}

@@ -458,8 +458,12 @@ class _Pass:
                     self.saved[sp.name] = (Wc,)
                 continue
             Z = t.empty(rows, n_out, device=dev, dtype=self.dt)
-            ops.gemm(Xv, Wc, Z, bias=b, alpha=OMEGA_0)
-            a, c, mean, invstd = self._affine(sp.layer, Z, rows, training)
+            st = None
+            if training and sp.layer.has_bn:          # batch statistics fused into the GEMM epilogue (CTA-pair kernel)
+                st = ops.gemm_stats(Xv, Wc, Z, bias=b, alpha=OMEGA_0)
+            if st is None:
+                ops.gemm(Xv, Wc, Z, bias=b, alpha=OMEGA_0)
+            a, c, mean, invstd = self._affine(sp.layer, Z, rows, training, st)
             if sp.out in ("cat5", "cats1"):
                 Y = self.bufs[sp.out][:, sp.out_col0:sp.out_col0 + n_out]
             else:
@@ -482,7 +486,7 @@ class _Pass:
             self.bufs = {k: v for k, v in self.bufs.items() if k in ("pos", "vis", "adj", "sky", "cls", "y")}
         return res
 
-    def _affine(self, layer, Z, rows, training):
+    def _affine(self, layer, Z, rows, training, stats=None):
         """fold BatchNorm1d(momentum=.01, eps=1e-5) into y = a*z + c  (misc.py:169-170)."""
         dev = Z.device
         n = Z.shape[1]
@@ -490,7 +494,8 @@ class _Pass:
             return t.ones(n, device=dev), t.zeros(n, device=dev), None, None
         bn = layer.norm
         if training:
-            s, ss = ops.col_stats(Z)
+            s, ss = stats if stats is not None else ops.col_stats(Z)
+            s, ss = s.double(), ss.double()
             mean = s / rows
             var = t.clamp(ss / rows - mean * mean, min=0.0)
             with t.no_grad():
@@ -516,8 +521,10 @@ class _Pass:
         gbuf = {}   # activation-gradient buffers keyed by buffer name
 
         def gb(name, rows, width):
+            # every column that is ever read (the dY slice of the producing layer) is written by the first input-gradient
+            # GEMM (accumulate=0) or by a convert below: no zero fill of these M x width matrices
             if name not in gbuf:
-                gbuf[name] = t.zeros(rows, width, device=dev, dtype=dt)
+                gbuf[name] = t.empty(rows, width, device=dev, dtype=dt)
             return gbuf[name]
 
         gout = dict(zip(self.outs, gouts))

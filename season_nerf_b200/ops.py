@@ -178,6 +178,29 @@ def gemm(A, B, out, bias=None, alpha=1.0, accumulate=0, a_t=False, b_t=False):
     return out
 
 
+def gemm_stats(A, B, out, bias=None, alpha=1.0):
+    """out[M,N] (bf16) = alpha*(A.B^T + bias) with the column sum / sum of squares of the stored values fused into the
+    GEMM epilogue.  -> (sum[N], sumsq[N]) float32, or None when the CTA-pair kernel does not take the shape (the
+    caller then runs gemm + col_stats)."""
+    A, lda = _mat(A, "A")
+    B, ldb = _mat(B, "B")
+    out, ldc = _mat(out, "out")
+    M, N = out.shape
+    K = A.shape[1]
+    if A.dtype != torch.bfloat16 or B.dtype != torch.bfloat16 or out.dtype != torch.bfloat16:
+        return None
+    if B.shape[1] != K or A.shape[0] != M or B.shape[0] != N:
+        raise ValueError("gemm_stats shape mismatch: A%s B%s out%s" % (tuple(A.shape), tuple(B.shape), tuple(out.shape)))
+    if bias is not None:
+        _cuda(bias, torch.float32, "bias")
+    s = torch.zeros(2, N, device=out.device, dtype=torch.float32)
+    rc = _lib.load().snb_gemm_stats(_ptr(A), lda, _ptr(B), ldb, _ptr(out), ldc, _ptr(bias), float(alpha), M, N, K, _ptr(s), _stream())
+    if rc == -2:
+        return None
+    check(rc)
+    return s[0], s[1]
+
+
 def col_stats(Z):
     """-> (sum[N], sumsq[N]) float64 over the rows of Z."""
     Z, ldz = _mat(Z, "Z")

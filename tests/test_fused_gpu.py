@@ -17,7 +17,7 @@ def _pts(M, seed):
 @pytest.mark.parametrize("M,S", [(128, 1), (96 * 5, 96), (128 * 148 + 37, 1), (96 * 700, 96)])
 def test_fused_matches_program_interpreter_and_oracle(params0, M, S):
     from oracle import season_oracle as so
-    from season_nerf_b200 import fused, packing
+    from season_nerf_b200 import fused, packing2 as packing
     net = make_net(params0, "bf16")
     pts = _pts(M, M)
     nr = (M + S - 1) // S

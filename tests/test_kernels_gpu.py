@@ -152,6 +152,32 @@ def test_gemm_bf16_tcgen05(a_t, b_t, M, N, K):
     assert relerr(z, 2.0 * (A.float() @ B.float().T)) < 1e-5
 
 
+@pytest.mark.parametrize("M,N,K", [(5000, 512, 512), (256, 128, 64), (777, 256, 320), (2049, 192, 72), (4096, 576, 512)])
+def test_gemm_bf16_cta_pair_modes(M, N, K):
+    """CTA-pair (cta_group::2) kernel: TMA-store epilogue, bf16 accumulate, fused BatchNorm statistics."""
+    from season_nerf_b200 import ops
+    g = t.Generator().manual_seed(M + N + K)
+    A = (t.rand(M, K, generator=g) - .5).bfloat16().cuda()
+    B = (t.rand(N, K, generator=g) - .5).bfloat16().cuda()
+    bias = (t.rand(N, generator=g) - .5).cuda()
+    ref = 30.0 * (A.float() @ B.float().T + bias)
+    outb = t.full((M + 3, N + 8), 7.0, device="cuda", dtype=t.bfloat16)       # guard rows / columns must stay untouched
+    ops.gemm(A, B, outb[:M, :N], bias=bias, alpha=30.0)
+    assert relerr(outb[:M, :N], ref) < 6e-3
+    assert float((outb[M:] - 7).abs().max()) == 0 and float((outb[:, N:] - 7).abs().max()) == 0
+    acc = ref.bfloat16()
+    ops.gemm(A, B, acc, bias=bias, alpha=30.0, accumulate=1)
+    assert relerr(acc, 2 * ref) < 8e-3
+    Z = t.empty(M, N, device="cuda", dtype=t.bfloat16)
+    st = ops.gemm_stats(A, B, Z, bias=bias, alpha=30.0)
+    if N > 512:                       # statistics accumulators live in registers for N <= 512 only
+        assert st is None
+        return
+    assert st is not None
+    assert t.equal(Z, outb[:M, :N])
+    assert relerr(st[0], Z.double().sum(0)) < 2e-5 and relerr(st[1], (Z.double() ** 2).sum(0)) < 2e-5
+
+
 @pytest.mark.parametrize("a_t,b_t", [(False, False), (True, True), (False, True)])
 def test_gemm_fp32_simt(a_t, b_t):
     from season_nerf_b200 import ops

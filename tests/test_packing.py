@@ -17,9 +17,15 @@ def _inputs(n, seed=1):
     return X, sun, Time, enc, senc
 
 
-def test_program_matches_oracle_network(params0):
+import pytest
+from season_nerf_b200 import packing2
+
+
+@pytest.mark.parametrize("pk", [packing, packing2])
+def test_program_matches_oracle_network(params0, pk):
+    packing = pk
     blob, info = packing.build_program(params0)
-    assert info["n_mma"] == 370 and blob.nbytes % 128 == 0
+    assert info["n_mma"] == (370 if pk.__name__.endswith("packing") else 193) and blob.nbytes % 128 == 0
     hdr = blob[:packing.HEADER_DT.itemsize].view(packing.HEADER_DT)[0]
     assert int(hdr["magic"]) == packing.MAGIC and int(hdr["w_off"]) % 1024 == 0
     X, sun, Time, enc, senc = _inputs(192)
@@ -31,7 +37,9 @@ def test_program_matches_oracle_network(params0):
     assert float((outs[packing.OUT_ADJ] - adj.reshape(-1, 12)).abs().max()) < 3e-2
 
 
-def test_sigma_only_program(params0):
+@pytest.mark.parametrize("pk", [packing, packing2])
+def test_sigma_only_program(params0, pk):
+    packing = pk
     _, info = packing.build_program(params0, sigma_only=True)
     X, sun, Time, enc, senc = _inputs(64, seed=2)
     outs = packing.interpret(info, enc, senc)
@@ -41,7 +49,9 @@ def test_sigma_only_program(params0):
     assert all(int(e["kind"]) != packing.K_ENC_SUN for e in info["epi"])
 
 
-def test_schedule_checker_catches_hazards(params0):
+@pytest.mark.parametrize("pk", [packing, packing2])
+def test_schedule_checker_catches_hazards(params0, pk):
+    packing = pk
     _, info = packing.build_program(params0)
     mma, epi = info["mma"].copy(), info["epi"].copy()
     assert packing.check_schedule(mma, epi)
