@@ -30,10 +30,12 @@ def sample_ts(n_course, eval_mode, include_end_pt=False, jitter=None):
     return ts
 
 
-def sample_pt_coarse(pt_tops, pt_bots, n_course, eval_mode, include_end_pt=False, jitter=None, device=None):
-    """misc.py:234-247 -> pts [N,S,3], deltas [N,S,1] (on the device)."""
+def sample_pt_coarse(pt_tops, pt_bots, n_course, eval_mode, include_end_pt=False, jitter=None, device=None, ts=None):
+    """misc.py:234-247 -> pts [N,S,3], deltas [N,S,1] (on the device).  `ts` (device float32 [S]) overrides the host-built
+    sample fractions: the CUDA-graph training step keeps them in a static device buffer refreshed before each replay."""
     device = device or (pt_tops.device if pt_tops.is_cuda else t.device("cuda"))
-    ts = sample_ts(n_course, eval_mode, include_end_pt, jitter).to(device)
+    if ts is None:
+        ts = sample_ts(n_course, eval_mode, include_end_pt, jitter).to(device)
     pts, deltas = ops.sample_rays(_dev(pt_tops, device), _dev(pt_bots, device), ts)
     return pts, deltas.unsqueeze(-1)
 
@@ -124,11 +126,11 @@ class All_in_One_Eval():
                                                         Vis.reshape(N, S), Sky_ray, self.use_classic_solar)
         return PV.unsqueeze(-1), PE.unsqueeze(-1), PS.unsqueeze(-1), albedo, rendered
 
-    def eval(self, data_dict, Network, current_step, train_mode, jitter=None):
+    def eval(self, data_dict, Network, current_step, train_mode, jitter=None, ts=None):
         """Eval_Tools_2.py:165-252."""
         S = self.args.n_samples
         dev = self.device
-        Xs, deltas = sample_pt_coarse(data_dict["Top"], data_dict["Bot"], S, not train_mode, jitter=jitter, device=dev)
+        Xs, deltas = sample_pt_coarse(data_dict["Top"], data_dict["Bot"], S, not train_mode, jitter=jitter, device=dev, ts=ts)
         N = Xs.shape[0]
         sun, tim = _dev(data_dict["Sun_Angle"], dev), _dev(data_dict["Time_Encoded"], dev)
         pos, vis, adj, sky, cl = Network.forward_rays(Xs.reshape(-1, 3), sun, tim, S)
@@ -169,12 +171,12 @@ class All_in_One_Eval():
                 "Sky_Col": Sky.reshape(N, S, -1), "Classes": Cls.reshape(N, S, -1), "Adjust": Adj.reshape(N, S, -1),
                 "Rho": Rho, "Col": Base, "deltas": deltas, "sample_pts": Xs}
 
-    def eval_Rho_Only(self, data_dict, Network, train_mode, current_step=0, jitter=None):
+    def eval_Rho_Only(self, data_dict, Network, train_mode, current_step=0, jitter=None, ts=None):
         """Eval_Tools_2.py:297-337."""
         S = self.args.n_samples
         dev = self.device
         Xs, deltas = sample_pt_coarse(data_dict["Top"], data_dict["Bot"], S, not train_mode, include_end_pt=True,
-                                      jitter=jitter, device=dev)
+                                      jitter=jitter, device=dev, ts=ts)
         N = Xs.shape[0]
         sun = _dev(data_dict["Sun_Angle"], dev)
         rho_raw, vis_raw, sky_raw = Network.forward_rays(Xs.reshape(-1, 3), sun, None, S, mode="solar")
@@ -238,21 +240,22 @@ class All_in_One_Eval():
         return R
 
     # ---------------------------------------------------------------------------------------------------
-    def get_loss(self, data_dict, Network, current_step, train_mode, jitter=None, solar=None, solar_jitter=None):
+    def get_loss(self, data_dict, Network, current_step, train_mode, jitter=None, solar=None, solar_jitter=None,
+                 ts=None, solar_ts=None):
         """Eval_Tools_2.py:340-459."""
         n_rays = data_dict["Top"].shape[0]
         device = self.device
         args = self.args
         Loss = {}
         weight = {"Color": 1.0, "Solar_Correction": args.sc_lambda, "Alpha_Adjust": 1.}
-        out = self.eval(data_dict, Network, current_step, train_mode, jitter=jitter)
+        out = self.eval(data_dict, Network, current_step, train_mode, jitter=jitter, ts=ts)
         if args.Use_Solar:
             if solar is None:
                 starts, ends, svec, stime, _ = self.solar_creation_tool(n_rays, include_times=True)
             else:
                 starts, ends, svec, stime = solar
             sol = self.eval_Rho_Only({"Top": starts, "Bot": ends, "Sun_Angle": svec, "Time_Encoded": stime}, Network,
-                                     train_mode, current_step, jitter=solar_jitter)
+                                     train_mode, current_step, jitter=solar_jitter, ts=solar_ts)
             err = t.mean(t.sum((sol["Solar_Vis"] - sol["PV_Exact"].detach()) ** 2, 1))
             Loss["Solar_Correction"] = [err, weight["Solar_Correction"]]
             absorb = t.mean(1 - t.sum(sol["PE"].detach() * sol["PV_Exact"].detach() * sol["Solar_Vis"], 1))

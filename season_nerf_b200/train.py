@@ -6,7 +6,7 @@ import torch as t
 import torch.distributed as dist
 
 from .adaptive_loss import AdaptiveLossFunction
-from .engine import All_in_One_Eval
+from .engine import All_in_One_Eval, sample_ts
 from .network import T_NeRF
 
 
@@ -55,9 +55,19 @@ class TrainStep:
     DSM-guided section (use_prior True, learning_mode 1 with jump_start)."""
 
     def __init__(self, args, device, H, WC, network=None, training_DSM=None, use_prior=False, total_steps=None,
-                 world_size=1, precision="bf16"):
+                 world_size=1, precision="bf16", use_graph=False, graph_warmup=2):
+        """use_graph: after `graph_warmup` eager steps at a given batch size, the whole step (sampling, network forward,
+        losses, backward and - single GPU - both Adam updates) is captured once into a CUDA graph and replayed; inputs live
+        in static device buffers refreshed before each replay.  The arithmetic and kernel sequence are those of the eager
+        step; only the ~1300 per-step launches stop costing host time.  Not used for the DSM-guided section (use_prior:
+        the trust factor changes every step)."""
         self.args, self.device = args, t.device(device)
         self.world_size = world_size
+        self.use_graph = bool(use_graph) and not use_prior and self.device.type == "cuda"
+        self.graph_warmup = graph_warmup
+        self._graphs = {}
+        self._eager_calls = {}
+        self.launches_replayed = 0     # kernels of this library launched through graph replays (not seen by snb_launch_count)
         self.network = network if network is not None else T_NeRF(
             args.fc_units, n_classes=args.number_low_frequency_cases,
             **({} if training_DSM is None else {"HM": training_DSM}), precision=precision).to(self.device)
@@ -76,8 +86,13 @@ class TrainStep:
         self.eval_tool = All_in_One_Eval(args, self.device, total_steps, use_prior, ada, H, WC)
         self.params = [p for p in self.network.parameters()]
         self.ada_params = ada_params
-        self.optim = t.optim.Adam(self.params, lr=args.lr)                         # Net_Tool_2.py:110-119
-        self.optim2 = t.optim.Adam(ada_params, lr=args.lr * args.lr_alpha_scale) if ada_params else None
+        gk = {}
+        lr1, lr2 = args.lr, args.lr * args.lr_alpha_scale
+        if self.use_graph:       # graph-capturable Adam: step counters and learning rates are device tensors
+            gk = dict(capturable=True)
+            lr1, lr2 = t.tensor(lr1, device=self.device), t.tensor(lr2, device=self.device)
+        self.optim = t.optim.Adam(self.params, lr=lr1, **gk)                       # Net_Tool_2.py:110-119
+        self.optim2 = t.optim.Adam(ada_params, lr=lr2, **gk) if ada_params else None
         oc = dict(total_steps=total_steps, base_momentum=0.85, max_momentum=0.95, cycle_momentum=False)
         self.sched = t.optim.lr_scheduler.OneCycleLR(self.optim, max_lr=args.lr, **oc)
         self.sched2 = t.optim.lr_scheduler.OneCycleLR(self.optim2, max_lr=args.lr * args.lr_alpha_scale, **oc) \
@@ -90,8 +105,98 @@ class TrainStep:
         grads = [p.grad for p in self.params + self.ada_params if p.grad is not None]
         self._flat = flat_allreduce_mean_(grads, self.world_size, self._flat)
 
+    # ---- CUDA-graph step -----------------------------------------------------------------------------------
+    _BATCH_KEYS = ("Top", "Bot", "Sun_Angle", "Time_Encoded", "GT_Color")
+
+    def _draw_inputs(self, n, inject):
+        """host-side random draws of one step, in the reference's order (Eval_Tools_2.py:165-170 jitter, :350 solar rays,
+        :300-301 solar jitter) -> ts_img [S], solar 4-tuple, ts_solar [S] (CPU tensors unless injected on the device)."""
+        S = self.args.n_samples
+        ts_img = sample_ts(S, False, False, inject.get("jitter"))
+        solar = inject.get("solar")
+        if solar is None and self.args.Use_Solar:
+            solar = self.eval_tool.solar_creation_tool(n, include_times=True)[:4]
+        ts_sol = sample_ts(S, False, True, inject.get("solar_jitter")) if self.args.Use_Solar else None
+        return ts_img, solar, ts_sol
+
+    def _capture(self, data_dict, current_step, n):
+        dev = self.device
+        f32 = dict(device=dev, dtype=t.float32)
+        S = self.args.n_samples
+        st = {"batch": {k: t.empty(tuple(data_dict[k].shape), **f32) for k in self._BATCH_KEYS},
+              "ts_img": t.empty(S, **f32), "ts_sol": t.empty(S, **f32),
+              "solar": tuple(t.empty(n, w, **f32) for w in (3, 3, 3, 4)) if self.args.Use_Solar else None}
+        self._graphs[n] = st
+        return st
+
+    def _fill_static(self, st, data_dict, ts_img, solar, ts_sol):
+        for k in self._BATCH_KEYS:
+            st["batch"][k].copy_(data_dict[k], non_blocking=True)
+        st["ts_img"].copy_(ts_img, non_blocking=True)
+        if st["solar"] is not None:
+            st["ts_sol"].copy_(ts_sol, non_blocking=True)
+            for d, s_ in zip(st["solar"], solar):
+                d.copy_(s_, non_blocking=True)
+
+    def _fwd_bwd(self, st, current_step):
+        loss = self.eval_tool.get_loss(st["batch"], self.network, current_step, train_mode=True, solar=st["solar"],
+                                       ts=st["ts_img"], solar_ts=st["ts_sol"])
+        total = 0
+        for k in loss.keys():
+            total = total + loss[k][0] * loss[k][1]
+        total.backward()
+        return {k: [v[0].detach() if isinstance(v[0], t.Tensor) else v[0], v[1]] for k, v in loss.items()}, total.detach()
+
+    def _optim_step(self):
+        self.optim.step()
+        if self.optim2 is not None:
+            self.optim2.step()
+
+    def _step_graphed(self, data_dict, current_step, inject):
+        n = data_dict["Top"].shape[0]
+        ts_img, solar, ts_sol = self._draw_inputs(n, inject)
+        st = self._graphs.get(n)
+        if st is None:
+            st = self._capture(data_dict, current_step, n)
+        self._fill_static(st, data_dict, ts_img, solar, ts_sol)
+        if "g_fb" not in st:
+            # record: fwd + bwd (+ the optimiser updates when there is no all-reduce in between)
+            self.optim.zero_grad(set_to_none=True)
+            if self.optim2 is not None:
+                self.optim2.zero_grad(set_to_none=True)
+            t.cuda.synchronize()
+            from . import _lib
+            l0 = _lib.launch_count()
+            g_fb = t.cuda.CUDAGraph()
+            with t.cuda.graph(g_fb):
+                st["loss"], st["total"] = self._fwd_bwd(st, current_step)
+                if self.world_size == 1:
+                    self._optim_step()
+            st["g_fb"] = g_fb
+            st["launches"] = _lib.launch_count() - l0
+            if self.world_size > 1:
+                g_opt = t.cuda.CUDAGraph()
+                with t.cuda.graph(g_opt, pool=g_fb.pool()):
+                    self._optim_step()
+                st["g_opt"] = g_opt
+        st["g_fb"].replay()
+        self.launches_replayed += st["launches"]
+        if self.world_size > 1:
+            self._allreduce_grads()
+            st["g_opt"].replay()
+        self.sched.step()
+        if self.sched2 is not None:
+            self.sched2.step()
+        self.last_loss = st["total"]
+        return st["loss"]
+
     def step(self, data_dict, current_step, **inject):
         """mg_run_NeRF.py:288-326 without the per-term TensorBoard .item() syncs; returns the loss dict."""
+        if self.use_graph:
+            n = data_dict["Top"].shape[0]
+            if self._eager_calls.get(n, 0) >= self.graph_warmup:
+                return self._step_graphed(data_dict, current_step, inject)
+            self._eager_calls[n] = self._eager_calls.get(n, 0) + 1
         self.optim.zero_grad(set_to_none=True)
         if self.optim2 is not None:
             self.optim2.zero_grad(set_to_none=True)
@@ -109,4 +214,6 @@ class TrainStep:
         if self.sched2 is not None:
             self.sched2.step()
         self.last_loss = total.detach()
-        return loss
+        # the step has consumed the autograd graph: hand back plain values (a caller that kept graph-attached losses alive
+        # would also keep this iteration's AccumulateGrad nodes alive, which breaks a later CUDA-graph capture)
+        return {k: [v[0].detach() if isinstance(v[0], t.Tensor) else v[0], v[1]] for k, v in loss.items()}

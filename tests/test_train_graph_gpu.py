@@ -1,0 +1,77 @@
+"""The CUDA-graph training step (train.TrainStep(use_graph=True)) must be the eager step, replayed: same losses step by
+step and the same weights / BatchNorm running statistics after a few steps (identical kernels and inputs; the only
+non-determinism is the order of the split-K fp32 atomics of the weight-gradient GEMMs)."""
+import types
+
+import numpy as np
+import pytest
+import torch as t
+
+from gpu_util import maxabs, relerr
+
+pytestmark = pytest.mark.gpu
+S = 96
+
+
+def _args():
+    return types.SimpleNamespace(n_samples=S, Use_Reg=True, Solar_Type_2=False, Use_MSE_loss=False, sc_lambda=0.03,
+                                 Use_Solar=True, number_low_frequency_cases=4, fc_units=512, lr=10 ** -4.86,
+                                 lr_alpha_scale=1000.0, max_train_steps=1000)
+
+
+def _run(use_graph, n_steps, n=192):
+    import season_nerf_b200 as snb
+    from oracle import season_oracle as so
+    dev = t.device("cuda")
+    t.manual_seed(0)
+    ts = snb.TrainStep(_args(), dev, so.oma_w2l_h(), so.OMA_W2C, use_graph=use_graph, graph_warmup=1)
+    batch = so.synthetic_batch(n, seed=1, n_images=5)
+    losses = []
+    for i in range(n_steps):
+        rs = np.random.RandomState(10 + i)
+        g = t.Generator().manual_seed(10 + i)
+        st, en, vec, tm, _ = so.create_solar_rays_uniform(n, so.OMA_W2C, so.oma_w2l_h(), rs, g)
+        jit = t.rand(S, generator=g)
+        L = ts.step(batch, i, jitter=jit, solar=(st, en, vec, tm), solar_jitter=jit)
+        losses.append({k: float(v[0]) for k, v in L.items()} | {"total": float(ts.last_loss)})
+    sd = {k: v.detach().float().cpu().clone() for k, v in ts.network.state_dict().items()}
+    lr = float(ts.optim.param_groups[0]["lr"])
+    return losses, sd, lr, ts
+
+
+def test_graph_step_matches_eager():
+    n_steps = 5
+    le, sde, lre, _ = _run(False, n_steps)
+    lg, sdg, lrg, tsg = _run(True, n_steps)
+    assert tsg._graphs and tsg.launches_replayed > 0, "the graph path did not run"
+    assert abs(lre - lrg) < 1e-12 * max(1.0, abs(lre)) + 1e-9
+    for a, b in zip(le, lg):
+        for k in a:
+            assert abs(a[k] - b[k]) <= 2e-3 * max(abs(a[k]), 1e-3), (k, a[k], b[k])
+    for k in sde:
+        if "num_batches_tracked" in k:
+            assert t.equal(sde[k], sdg[k]), k
+        elif sde[k].numel() > 1 and float(sde[k].norm()) > 0:
+            # Adam moves every parameter by about lr per step whatever the gradient's magnitude: parameters that start at
+            # zero (BatchNorm biases) are compared on that scale, the others relative to their norm
+            assert relerr(sdg[k], sde[k]) < 2e-3 or maxabs(sdg[k], sde[k]) < 2 * lre, (k, relerr(sdg[k], sde[k]))
+
+
+def test_graph_step_accepts_host_batches_and_changes_inputs():
+    """static buffers are refreshed before every replay: two different batches give two different losses, and the same
+    batch replayed with the same draws gives (almost) the same loss as the first time modulo the weight update."""
+    import season_nerf_b200 as snb
+    from oracle import season_oracle as so
+    dev = t.device("cuda")
+    t.manual_seed(0)
+    ts = snb.TrainStep(_args(), dev, so.oma_w2l_h(), so.OMA_W2C, use_graph=True, graph_warmup=1)
+    b1 = so.synthetic_batch(128, seed=1, n_images=5)
+    b2 = so.synthetic_batch(128, seed=2, n_images=5)
+    np.random.seed(0)
+    t.manual_seed(1)
+    vals = []
+    for i, b in enumerate([b1, b1, b2, b1, b2]):
+        ts.step(b, i)
+        vals.append(float(ts.last_loss))
+    assert all(np.isfinite(v) for v in vals)
+    assert abs(vals[2] - vals[3]) > 1e-6
