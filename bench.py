@@ -276,7 +276,8 @@ def run_ours(a):
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM): per-launch CUDA events on the launching stream --------------
     ev = []
-    orig, orig_stats = ops.gemm, ops.gemm_stats
+    gemm_entry = ("gemm", "gemm_stats", "gemm_sine_fwd", "gemm_sine_bwd")      # every tcgen05 GEMM entry point of ops.py
+    orig = {k: getattr(ops, k) for k in gemm_entry}
 
     def _timed(fn):
         def wrapped(*args_, **kw):
@@ -288,20 +289,22 @@ def run_ours(a):
             return r
         return wrapped
 
-    ops.gemm, ops.gemm_stats = _timed(orig), _timed(orig_stats)     # every tcgen05 GEMM launch of the step (both entry points)
+    for k in gemm_entry:
+        setattr(ops, k, _timed(orig[k]))
     prof_steps = 2
     ts.use_graph = False                              # per-launch events need the eager launch sequence (same kernels)
     t.cuda.synchronize()
     for i in range(prof_steps):
         step_dev(a.warmup + a.steps + i)
     t.cuda.synchronize()
-    ops.gemm, ops.gemm_stats = orig, orig_stats
+    for k in gemm_entry:
+        setattr(ops, k, orig[k])
     gemm_ms = sum(s.elapsed_time(e) for s, e in ev) / prof_steps
     n_gemm = len(ev) // prof_steps
     flops_step = TRAIN_FLOP_PER_RAY * n
     achieved = flops_step / (gemm_ms * 1e-3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
-    roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+    roofline = {"bound": "tensor", "kernel": "gemm2_bf16_kernel (tcgen05 cta_group::2, fused SIREN epilogues)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peaks["source"] + " sustained cuBLAS bf16",
                 "launches_per_step": n_gemm, "kernel_ms_per_step": gemm_ms, "step_ms": ms / a.steps,
                 "kernel_share_of_step": gemm_ms / (ms / a.steps),

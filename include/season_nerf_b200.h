@@ -98,6 +98,29 @@ int snb_gemm(const void* A, int lda, int a_t, const void* B, int ldb, int b_t, v
 int snb_gemm_stats(const void* A, int lda, const void* B, int ldb, void* C, int ldc, const float* bias, float alpha,
                    long long M, int N, int K, float* stats, void* stream);
 
+/* Forward of a SIREN layer WITHOUT BatchNorm in one kernel (bf16 tcgen05 GEMM + activation epilogue):
+ *   Z[M,N] = alpha*(A[M,K].B[N,K]^T + bias)  (bf16, kept for the backward),   Y[M,N] = sin(Z)  (bf16).
+ * Replaces nn.Linear + torch.sin in misc.py:188-189 for layers whose norm is Identity.  Returns SNB_ERR_UNSUPPORTED (-2)
+ * for shapes the CTA-pair kernel does not take (M < 256, N < 128, N > 512, N % 64, unaligned): use snb_gemm + snb_sine_fwd. */
+int snb_gemm_sine_fwd(const void* A, int lda, const void* B, int ldb, void* Z, int ldz, void* Y, int ldy,
+                      const float* bias, float alpha, long long M, int N, int K, void* stream);
+
+/* Input-gradient GEMM of layer L+1 fused with the activation backward of layer L (autograd of misc.py:188-189):
+ *   dY[M,N] = alpha * dZn[M,K] . W[K,N]      (W = weight of layer L+1 stored [out=K, in=N], row pitch ldw)
+ *   G[M,N]  = dY * cos(a[n]*Z + c[n])        (Z = saved pre-activation of layer L, bf16; G bf16)
+ *   stats[0..N) += sum_m G,  stats[N..2N) += sum_m G*(Z-mean[n])*invstd[n]     (caller zeroes stats; float32)
+ * Without BatchNorm (a=1, c=0): G is dZ of layer L and stats[0..N) its bias gradient / alpha_L.  With train-mode
+ * BatchNorm the two sums are the BatchNorm bias / weight gradients and snb_bn_bwd_apply finishes dZ.
+ * SNB_ERR_UNSUPPORTED (-2) like snb_gemm_sine_fwd: the caller then runs snb_gemm + snb_sine_bwd_reduce/apply. */
+int snb_gemm_sine_bwd(const void* dZn, int lda, const void* W, int ldw, void* G, int ldg, const void* Z, int ldz,
+                      const float* a, const float* c, const float* mean, const float* invstd, float alpha,
+                      long long M, int N, int K, float* stats, void* stream);
+
+/* dZ = a[n]*(G - k1[n] - (Z-mean[n])*invstd[n]*k2[n])   (train-mode BatchNorm backward after snb_gemm_sine_bwd; dZ may alias G) */
+int snb_bn_bwd_apply(const void* G, int ldg, const void* Z, int ldz, const float* a, const float* mean,
+                     const float* invstd, const float* k1, const float* k2, void* dZ, int ldo, long long M, int N,
+                     int dtype, void* stream);
+
 /* column statistics for train-mode BatchNorm1d (misc.py:169-170): sum[n], sumsq[n] over M rows (float64 out). */
 int snb_col_stats(const void* Z, int dtype, int ldz, long long M, int N, double* sum, double* sumsq, void* stream);
 

@@ -262,6 +262,33 @@ sine_bwd_apply_vec_kernel(const T* __restrict__ dY, int ldd, const T* __restrict
   }
 }
 
+// dZ = a*(g - k1 - xhat*k2): second half of the train-mode BatchNorm backward when g = dY*cos(.) was already produced
+// (and reduced) by the fused input-gradient GEMM epilogue.  In place allowed (dZ == G).
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_vec_kernel(const T* G, int ldg, const T* __restrict__ Z, int ldz, const float* __restrict__ a,
+                        const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ k1,
+                        const float* __restrict__ k2, T* dZ, int ldo, long long M, int N) {
+  const int col = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
+  if (col >= N) return;
+  float av[8], mv[8], iv[8], k1v[8], k2v[8];
+  load8f(a + col, av);
+  load8f(mean + col, mv);
+  load8f(invstd + col, iv);
+  load8f(k1 + col, k1v);
+  load8f(k2 + col, k2v);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) k2v[i] *= iv[i];
+  for (long long r = blockIdx.x * (long long)blockDim.y + threadIdx.y; r < M; r += (long long)gridDim.x * blockDim.y) {
+    float z[8], g[8];
+    Vec8<T>::load(Z + r * ldz + col, z);
+    Vec8<T>::load(G + r * ldg + col, g);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = av[i] * (g[i] - k1v[i] - (z[i] - mv[i]) * k2v[i]);
+    Vec8<T>::store(dZ + r * ldo + col, g);
+  }
+}
+
 // column reductions: two quantities per column accumulated in fp32 registers over <= 64 rows, then in fp64, then one
 // double atomicAdd per column per block-row.
 template <typename T, bool kBwd>
@@ -485,6 +512,22 @@ extern "C" int snb_sine_bwd_apply(const void* dY, int ldd, const void* Z, int ld
   const int grid = grid_for(M * N, 256, 16);
   if (dtype == SNB_F32) sine_bwd_apply_kernel<float><<<grid, 256, 0, st>>>((const float*)dY, ldd, (const float*)Z, ldz, p, k1, k2, (float*)dZ, ldo, M, N);
   else if (dtype == SNB_BF16) sine_bwd_apply_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dY, ldd, (const bf16*)Z, ldz, p, k1, k2, (bf16*)dZ, ldo, M, N);
+  else return SNB_ERR_ARG;
+  count_launch();
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_bn_bwd_apply(const void* G, int ldg, const void* Z, int ldz, const float* a, const float* mean,
+                                const float* invstd, const float* k1, const float* k2, void* dZ, int ldo, long long M, int N,
+                                int dtype, void* stream) {
+  SNB_CHECK_ARG(G && Z && a && mean && invstd && k1 && k2 && dZ && M >= 0 && N > 0);
+  if (M == 0) return SNB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  VecLaunch v = vec_launch(M, N, ldg, ldz, ldo, G, Z, dZ, 0, 8);
+  if (!v.ok) return SNB_ERR_UNSUPPORTED;
+  if (dtype == SNB_F32) bn_bwd_apply_vec_kernel<float><<<v.grid, v.block, 0, st>>>((const float*)G, ldg, (const float*)Z, ldz, a, mean, invstd, k1, k2, (float*)dZ, ldo, M, N);
+  else if (dtype == SNB_BF16) bn_bwd_apply_vec_kernel<bf16><<<v.grid, v.block, 0, st>>>((const bf16*)G, ldg, (const bf16*)Z, ldz, a, mean, invstd, k1, k2, (bf16*)dZ, ldo, M, N);
   else return SNB_ERR_ARG;
   count_launch();
   SNB_LAUNCH_CHECK();

@@ -87,7 +87,26 @@ int snb_gemm_bf16_tc(const void* A, int lda, int a_t, const void* B, int ldb, in
 // implemented in gemm_tc2.cu (CTA-pair kernel; SNB_ERR_UNSUPPORTED = use the single-CTA kernel)
 int snb_gemm_bf16_tc2(const void* A, int lda, int a_t, const void* B, int ldb, int b_t, void* C, int ldc,
                       const float* bias, float alpha, int accumulate, long long M, int N, int K, int out_dtype,
-                      float* stats, cudaStream_t st);
+                      float* stats, cudaStream_t st, int epi = 0, const void* X = nullptr, int ldx = 0,
+                      const float* ea = nullptr, const float* ec = nullptr, const float* emean = nullptr,
+                      const float* einvstd = nullptr);
+
+extern "C" int snb_gemm_sine_fwd(const void* A, int lda, const void* B, int ldb, void* Z, int ldz, void* Y, int ldy,
+                                 const float* bias, float alpha, long long M, int N, int K, void* stream) {
+  SNB_CHECK_ARG(A && B && Z && Y && M >= 0 && N > 0 && K > 0 && ldz >= N && ldy >= N);
+  if (M == 0) return SNB_OK;
+  return snb_gemm_bf16_tc2(A, lda, 0, B, ldb, 0, Z, ldz, bias, alpha, 0, M, N, K, SNB_BF16, nullptr, (cudaStream_t)stream, 1,
+                           Y, ldy);
+}
+
+extern "C" int snb_gemm_sine_bwd(const void* dZn, int lda, const void* W, int ldw, void* G, int ldg, const void* Z, int ldz,
+                                 const float* a, const float* c, const float* mean, const float* invstd, float alpha,
+                                 long long M, int N, int K, float* stats, void* stream) {
+  SNB_CHECK_ARG(dZn && W && G && Z && a && c && mean && invstd && stats && M >= 0 && N > 0 && K > 0 && ldg >= N && ldz >= N);
+  if (M == 0) return SNB_OK;
+  return snb_gemm_bf16_tc2(dZn, lda, 0, W, ldw, 1, G, ldg, nullptr, alpha, 0, M, N, K, SNB_BF16, stats, (cudaStream_t)stream, 2,
+                           Z, ldz, a, c, mean, invstd);
+}
 
 extern "C" int snb_gemm_stats(const void* A, int lda, const void* B, int ldb, void* C, int ldc, const float* bias,
                               float alpha, long long M, int N, int K, float* stats, void* stream) {

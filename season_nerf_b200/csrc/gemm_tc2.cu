@@ -31,8 +31,11 @@ int make_tmap_bf16(CUtensorMap* m, const void* ptr, long long rows, long long co
 
 constexpr int k2BM = 128;                       // rows of A / C per CTA (pair tile: 256)
 constexpr int k2BK = 64;
-constexpr int k2Stages = 5;
-constexpr int k2Threads = 192;
+// warps: 0 = TMA producer, 1 = MMA issuer, 2.. = epilogue (4 warps; 8 for the input-gradient epilogue kEpi 2, whose
+// per-element work (cos, BatchNorm-backward sums) would otherwise outlast the main loop: two warps per TMEM lane quarter,
+// each taking half of the tile's 64-column chunks)
+__host__ __device__ constexpr int k2_epi_warps(int epi) { return epi == 2 ? 8 : 4; }
+__host__ __device__ constexpr int k2_threads(int epi) { return 64 + 32 * k2_epi_warps(epi); }
 constexpr int k2MaxBN = 256;
 constexpr uint32_t k2ABytes = k2BM * k2BK * 2;                 // 16 KB
 constexpr uint32_t k2BBytes = (k2MaxBN / 2) * k2BK * 2;        // 16 KB (this CTA's half of the B tile)
@@ -41,7 +44,14 @@ constexpr uint32_t k2CWarpBytes = 2 * 32 * 128;                // two 32-row x 1
 constexpr uint32_t k2CBytes = 4 * k2CWarpBytes;                // 32 KB
 constexpr int k2MaxStatN = 1024;
 constexpr uint32_t k2StatBytes = 2 * k2MaxStatN * 4;           // 8 KB
-constexpr uint32_t k2Smem = 1024 + k2Stages * k2StageBytes + k2CBytes + k2StatBytes + 256;
+// the fused SIREN epilogues need 64 KB of staging (kEpi 1: Z and Y tiles of 4 warps; kEpi 2: G tiles of 8 warps):
+// one ring stage less
+__host__ __device__ constexpr int k2_stages(int epi) { return epi ? 4 : 5; }
+__host__ __device__ constexpr uint32_t k2_cbytes(int epi) { return (uint32_t)k2_epi_warps(epi) * k2CWarpBytes; }
+__host__ __device__ constexpr uint32_t k2_xbytes(int epi) { return epi == 1 ? k2CBytes : 0u; }
+__host__ __device__ constexpr uint32_t k2_smem(int epi) {
+  return 1024 + k2_stages(epi) * k2StageBytes + k2_cbytes(epi) + k2_xbytes(epi) + k2StatBytes + 256;
+}
 
 struct Gemm2Params {
   long long M;
@@ -56,25 +66,42 @@ struct Gemm2Params {
   const float* bias;
   float alpha;
   float* stats;                // [2*N] column sum / sum of squares of the stored values, or null
+  // fused SIREN epilogues (tmapX = 4th tensor map, same shape and box as C):
+  //  kEpi 1 (forward, layer without BatchNorm):  C = z = alpha*(acc+bias) (bf16),  X = sin(z)              misc.py:189
+  //  kEpi 2 (input-gradient GEMM feeding a sine layer whose pre-activation Z = X[M,N] (row pitch ldx) was saved):
+  //          C = g = alpha*acc * cos(ea*z + ec);  stats[0..N) += sum g,  stats[N..2N) += sum g*(z-emean)*einvstd
+  const __nv_bfloat16* X;
+  int ldx;
+  const float* ea;
+  const float* ec;
+  const float* emean;
+  const float* einvstd;
 };
 
-template <bool kAT, bool kBT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
+template <bool kAT, bool kBT, int kEpi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2_threads(kEpi), 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
-                  const __grid_constant__ CUtensorMap tmapC, const Gemm2Params p) {
+                  const __grid_constant__ CUtensorMap tmapC, const __grid_constant__ CUtensorMap tmapX,
+                  const Gemm2Params p) {
+  constexpr int k2Stages = k2_stages(kEpi);
+  constexpr int kEpiWarps = k2_epi_warps(kEpi);
+  constexpr int k2Threads = k2_threads(kEpi);
+  constexpr uint32_t kCBytes = k2_cbytes(kEpi);
+  constexpr uint32_t kXBytes = k2_xbytes(kEpi);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t cstage_base = smem_base + k2Stages * k2StageBytes;
-  float* stat_smem = reinterpret_cast<float*>(smem_al + k2Stages * k2StageBytes + k2CBytes);
-  const uint32_t bar_base = cstage_base + k2CBytes + k2StatBytes;
+  const uint32_t xstage_base = cstage_base + kCBytes;
+  float* stat_smem = reinterpret_cast<float*>(smem_al + k2Stages * k2StageBytes + kCBytes + kXBytes);
+  const uint32_t bar_base = cstage_base + kCBytes + kXBytes + k2StatBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (k2Stages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * k2Stages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * k2Stages + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * k2Stages + 4);
   volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem_al + k2Stages * k2StageBytes + k2CBytes + k2StatBytes + 8u * (2 * k2Stages + 4));
+      reinterpret_cast<volatile uint32_t*>(smem_al + k2Stages * k2StageBytes + kCBytes + kXBytes + k2StatBytes + 8u * (2 * k2Stages + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -92,12 +119,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 8);
+      mbar_init(tempty_bar(s), 2 * kEpiWarps);
     }
     fence_barrier_init();
     tma_prefetch_desc(&tmapA);
     tma_prefetch_desc(&tmapB);
     if (p.tma_store) tma_prefetch_desc(&tmapC);
+    if (kEpi == 1) tma_prefetch_desc(&tmapX);
   }
   if (p.stats) {
     for (int i = threadIdx.x; i < 2 * k2MaxStatN; i += k2Threads) stat_smem[i] = 0.f;
@@ -195,8 +223,17 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     const int q = warp & 3;                 // TMEM lane quarter of this warp
     const uint32_t tempty_leader0 = mapa_shared(tempty_bar(0), 0);
     const uint32_t tempty_leader1 = mapa_shared(tempty_bar(1), 0);
-    const uint32_t cbuf = cstage_base + (uint32_t)q * k2CWarpBytes;
+    const int ew = warp - 2;                // epilogue warp index
+    const int eh = ew >> 2;                 // which half of the tile's chunks (kEpiWarps == 8), else 0
+    const uint32_t cbuf = cstage_base + (uint32_t)ew * k2CWarpBytes;
+    const uint32_t xbuf = xstage_base + (uint32_t)(ew & 3) * k2CWarpBytes;     // kEpi 1: Y tiles out
+    const int c_begin = kEpiWarps == 8 ? eh * (p.block_n >> 1) : 0;
+    const int c_end = kEpiWarps == 8 ? c_begin + (p.block_n >> 1) : p.block_n;
     uint32_t cpar = 0;
+    // kEpi 2: swizzled shared-memory offsets of this lane's column pair (2*lane, 2*lane+1) in rows r = k (mod 8)
+    uint32_t sw_off[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sw_off[k] = (uint32_t)((lane & 3) << 2) + (uint32_t)(((lane >> 2) ^ k) << 4);
     int acc = 0;
     uint32_t acc_phase = 0;
     float st_acc[2][4][4];       // [tile column][64-column chunk][sum c0, sum c1, sumsq c0, sumsq c1]
@@ -212,20 +249,35 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       const long long row0 = (long long)tm * (2 * k2BM) + (long long)rank * k2BM + q * 32;
       const long long row = row0 + lane;
       const int n0 = tn * p.block_n;
+      int rows_valid = 0;
+      if (row0 < p.M) rows_valid = (int)min((long long)32, p.M - row0);
+      // kEpi 2: the saved pre-activation Z in the column-pair layout (lane j <-> columns 2j, 2j+1; register r <-> row r):
+      // 32 coalesced 128-byte row reads per chunk, issued one chunk ahead - the first one while the MMAs still run
+      uint32_t zc[32];
+      auto load_z = [&](int c, uint32_t (&z)[32]) {
+        const uint32_t* zp = reinterpret_cast<const uint32_t*>(p.X + row0 * p.ldx + n0 + c + 2 * lane);
+        const long long ldw = p.ldx >> 1;
+        if (rows_valid == 32 && n0 + c + 64 <= p.N) {
+#pragma unroll
+          for (int r = 0; r < 32; ++r) z[r] = __ldg(zp + r * ldw);
+        } else {
+#pragma unroll
+          for (int r = 0; r < 32; ++r) z[r] = (r < rows_valid && n0 + c + 2 * lane < p.N) ? __ldg(zp + r * ldw) : 0u;
+        }
+      };
+      if (kEpi == 2) load_z(c_begin, zc);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * k2MaxBN;
       if (p.tma_store) {
-        int rows_valid = 0;
-        if (row0 < p.M) rows_valid = (int)min((long long)32, p.M - row0);
-        for (int c = 0; c < p.block_n; c += 64) {
+        for (int c = c_begin; c < c_end; c += 64) {
           const int cols_valid = min(64, p.N - (n0 + c));
           if (cols_valid <= 0) break;
           // bias of the 64 columns of this chunk: independent of the accumulator, issue before the TMEM load wait
           float ab[64];
 #pragma unroll
           for (int i = 0; i < 64; ++i) ab[i] = 0.f;
-          if (p.bias) {
+          if (kEpi != 2 && p.bias) {
             if (cols_valid == 64) {
               const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + c);
 #pragma unroll
@@ -252,21 +304,77 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const uint32_t a = u < 4 ? r0[8 * u + e] : r1[8 * (u - 4) + e];
-              v[e] = p.alpha * (__uint_as_float(a) + ab[8 * u + e]);
+              v[e] = kEpi == 2 ? p.alpha * __uint_as_float(a) : p.alpha * (__uint_as_float(a) + ab[8 * u + e]);
             }
-            const uint32_t addr = buf + (uint32_t)lane * 128u + (uint32_t)((u ^ (lane & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(v[0], v[1])),
-                         "r"(pack_bf16x2(v[2], v[3])), "r"(pack_bf16x2(v[4], v[5])), "r"(pack_bf16x2(v[6], v[7]))
+            const uint32_t soff = (uint32_t)lane * 128u + (uint32_t)((u ^ (lane & 7)) << 4);
+            const uint32_t addr = buf + soff;
+            uint32_t w4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) w4[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w4[0]), "r"(w4[1]), "r"(w4[2]), "r"(w4[3])
                          : "memory");
+            if (kEpi == 1) {
+              // Y = sin(z) of the STORED (bf16-rounded) pre-activation, like the stand-alone activation kernel
+              uint32_t y4[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                y4[e] = pack_bf16x2(__sinf(__uint_as_float(w4[e] << 16)), __sinf(__uint_as_float(w4[e] & 0xFFFF0000u)));
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(xbuf + (cpar ? 4096u : 0u) + soff), "r"(y4[0]),
+                           "r"(y4[1]), "r"(y4[2]), "r"(y4[3])
+                           : "memory");
+            }
+          }
+          if (kEpi == 2) {
+            // g = dY * cos(a*z + c) in the column-pair layout: the per-column constants live in registers, and the
+            // column sums  sum g, sum g*xhat  (BatchNorm backward; sum g alone is the bias gradient of a layer without
+            // BatchNorm) accumulate like the forward statistics.  Rows beyond M contribute zeros: their accumulator
+            // rows are zero (TMA zero-fills A) and there is no bias.
+            uint32_t zn[32];
+            const bool more = c + 64 < c_end && n0 + c + 64 < p.N;
+            if (more) load_z(c + 64, zn);
+            __syncwarp();
+            const int cg = n0 + c + 2 * lane;
+            const float2 a2 = __ldg(reinterpret_cast<const float2*>(p.ea + cg));
+            const float2 c2 = __ldg(reinterpret_cast<const float2*>(p.ec + cg));
+            const float2 m2 = __ldg(reinterpret_cast<const float2*>(p.emean + cg));
+            const float2 i2 = __ldg(reinterpret_cast<const float2*>(p.einvstd + cg));
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;     // sum g, sum g*z per column
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+              const uint32_t addr = buf + (uint32_t)r * 128u + sw_off[r & 7];
+              uint32_t dw;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(dw) : "r"(addr));
+              const float z0 = __uint_as_float(zc[r] << 16), z1 = __uint_as_float(zc[r] & 0xFFFF0000u);
+              const float g0 = __uint_as_float(dw << 16) * __cosf(fmaf(a2.x, z0, c2.x));
+              const float g1 = __uint_as_float(dw & 0xFFFF0000u) * __cosf(fmaf(a2.y, z1, c2.y));
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(pack_bf16x2(g0, g1)) : "memory");
+              s0 += g0, s1 += g1;
+              q0 = fmaf(g0, z0, q0), q1 = fmaf(g1, z1, q1);
+            }
+            // sum g*xhat = invstd * (sum g*z - mean * sum g)
+            q0 = i2.x * (q0 - m2.x * s0), q1 = i2.y * (q1 - m2.y * s1);
+#pragma unroll
+            for (int tnn = 0; tnn < 2; ++tnn)
+#pragma unroll
+              for (int cc = 0; cc < 2; ++cc)
+                if (tn == tnn && c == c_begin + 64 * cc) {
+                  st_acc[tnn][cc][0] += s0, st_acc[tnn][cc][1] += s1;
+                  st_acc[tnn][cc][2] += q0, st_acc[tnn][cc][3] += q1;
+                }
+            if (more) {
+#pragma unroll
+              for (int r = 0; r < 32; ++r) zc[r] = zn[r];
+            }
           }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0 && rows_valid > 0) {
             if (p.mode == 1) tma_reduce_add_2d(&tmapC, buf, n0 + c, (int)row0);
             else tma_store_2d(&tmapC, buf, n0 + c, (int)row0);
+            if (kEpi == 1) tma_store_2d(&tmapX, xbuf + (cpar ? 4096u : 0u), n0 + c, (int)row0);
             bulk_commit_group();
           }
-          if (p.stats) {
+          if (kEpi != 2 && p.stats) {
             // column statistics of the stored bf16 values: lane j owns columns (2j, 2j+1) of the chunk and keeps
             // their partial sums in registers across all tiles of the CTA (N <= 512: 2 tile columns x 4 chunks)
             float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
@@ -396,18 +504,18 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       for (int tnn = 0; tnn < 2; ++tnn)
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
-          const int col = tnn * p.block_n + 64 * cc + 2 * lane;
-          if (64 * cc < p.block_n && col + 1 < k2MaxStatN) {
+          const int col = tnn * p.block_n + c_begin + 64 * cc + 2 * lane;
+          if (c_begin + 64 * cc < c_end && col + 1 < k2MaxStatN) {
             atomicAdd(stat_smem + col, st_acc[tnn][cc][0]);
             atomicAdd(stat_smem + col + 1, st_acc[tnn][cc][1]);
             atomicAdd(stat_smem + k2MaxStatN + col, st_acc[tnn][cc][2]);
             atomicAdd(stat_smem + k2MaxStatN + col + 1, st_acc[tnn][cc][3]);
           }
         }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       const int te = threadIdx.x - 64;
       const int ncols = p.N < k2MaxStatN ? p.N : k2MaxStatN;
-      for (int i = te; i < ncols; i += 128) {
+      for (int i = te; i < ncols; i += 32 * kEpiWarps) {
         const float s = stat_smem[i], ss = stat_smem[k2MaxStatN + i];
         if (s != 0.f || ss != 0.f) {
           atomicAdd(p.stats + i, s);
@@ -430,11 +538,20 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
 using namespace snb;
 
 // returns SNB_ERR_UNSUPPORTED when the shape is better served by the single-CTA kernel (small M / N)
+// epi: 0 plain; 1 forward SIREN epilogue (X = second output Y [M,N] bf16); 2 input-gradient epilogue (X = saved Z [M,N] bf16)
 int snb_gemm_bf16_tc2(const void* A, int lda, int a_t, const void* B, int ldb, int b_t, void* C, int ldc,
                       const float* bias, float alpha, int accumulate, long long M, int N, int K, int out_dtype,
-                      float* stats, cudaStream_t st) {
+                      float* stats, cudaStream_t st, int epi, const void* X, int ldx, const float* ea, const float* ec,
+                      const float* emean, const float* einvstd) {
   if (M < 256 || N < 128) return SNB_ERR_UNSUPPORTED;
   if (stats && (N > 512 || accumulate != 0 || out_dtype != SNB_BF16)) return SNB_ERR_UNSUPPORTED;
+  if (epi) {
+    if (accumulate != 0 || out_dtype != SNB_BF16 || (N % 64) != 0 || N > 512 || !X || (ldx % 8) != 0 || (((uintptr_t)X) & 15) != 0)
+      return SNB_ERR_UNSUPPORTED;
+    if (epi == 1 && (a_t || b_t || stats)) return SNB_ERR_UNSUPPORTED;
+    if (epi == 2 && (a_t || !b_t || !stats || bias || !ea || !ec || !emean || !einvstd)) return SNB_ERR_UNSUPPORTED;
+    if (epi != 1 && epi != 2) return SNB_ERR_ARG;
+  }
   SNB_CHECK_ARG((lda % 8) == 0 && (ldb % 8) == 0 && (((uintptr_t)A) & 15) == 0 && (((uintptr_t)B) & 15) == 0);
   SNB_CHECK_ARG(out_dtype == SNB_F32 || out_dtype == SNB_BF16);
   SNB_CHECK_ARG(accumulate >= 0 && accumulate <= 2 && !(accumulate == 2 && out_dtype != SNB_F32));
@@ -456,10 +573,12 @@ int snb_gemm_bf16_tc2(const void* A, int lda, int a_t, const void* B, int ldb, i
   p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
   p.C = C, p.ldc = ldc, p.out_bf16 = out_dtype == SNB_BF16, p.mode = accumulate, p.bias = bias, p.alpha = alpha;
   p.stats = stats;
+  p.ea = ea, p.ec = ec, p.emean = emean, p.einvstd = einvstd;
+  p.X = reinterpret_cast<const __nv_bfloat16*>(X), p.ldx = ldx;
   p.tma_store = (out_dtype == SNB_BF16 && accumulate <= 1 && (ldc % 8) == 0 && (((uintptr_t)C) & 15) == 0) ? 1 : 0;
-  if (stats && !p.tma_store) return SNB_ERR_UNSUPPORTED;
+  if ((stats || epi) && !p.tma_store) return SNB_ERR_UNSUPPORTED;
 
-  CUtensorMap ta, tb, tcm;
+  CUtensorMap ta, tb, tcm, tx;
   int rc;
   const int half_n = p.block_n / 2;
   if (!a_t) rc = make_tmap_bf16(&ta, A, M, K, lda, k2BK, k2BM);
@@ -474,22 +593,31 @@ int snb_gemm_bf16_tc2(const void* A, int lda, int a_t, const void* B, int ldb, i
   } else {
     tcm = ta;
   }
+  if (epi == 1) {
+    rc = make_tmap_bf16(&tx, X, M, N, ldx, 64, 32);
+    if (rc) return rc;
+  } else {
+    tx = ta;
+  }
   const int total = p.tiles_m * p.tiles_n * p.splits;
   const int grid = 2 * (total < num_pairs ? total : num_pairs);
-#define SNB_LAUNCH_GEMM2(AT, BT)                                                                             \
+#define SNB_LAUNCH_GEMM2(AT, BT, EPI)                                                                        \
   do {                                                                                                       \
     static bool attr_set = false;                                                                            \
     if (!attr_set) {                                                                                         \
-      cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel<AT, BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2Smem); \
+      cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel<AT, BT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           k2_smem(EPI));                                                    \
       if (e != cudaSuccess) return (int)e;                                                                   \
       attr_set = true;                                                                                       \
     }                                                                                                        \
-    gemm2_bf16_kernel<AT, BT><<<grid, k2Threads, k2Smem, st>>>(ta, tb, tcm, p);                              \
+    gemm2_bf16_kernel<AT, BT, EPI><<<grid, k2_threads(EPI), k2_smem(EPI), st>>>(ta, tb, tcm, tx, p);         \
   } while (0)
-  if (!a_t && !b_t) SNB_LAUNCH_GEMM2(false, false);
-  else if (!a_t && b_t) SNB_LAUNCH_GEMM2(false, true);
-  else if (a_t && !b_t) SNB_LAUNCH_GEMM2(true, false);
-  else SNB_LAUNCH_GEMM2(true, true);
+  if (epi == 1) SNB_LAUNCH_GEMM2(false, false, 1);
+  else if (epi == 2) SNB_LAUNCH_GEMM2(false, true, 2);
+  else if (!a_t && !b_t) SNB_LAUNCH_GEMM2(false, false, 0);
+  else if (!a_t && b_t) SNB_LAUNCH_GEMM2(false, true, 0);
+  else if (a_t && !b_t) SNB_LAUNCH_GEMM2(true, false, 0);
+  else SNB_LAUNCH_GEMM2(true, true, 0);
 #undef SNB_LAUNCH_GEMM2
   count_launch();
   SNB_LAUNCH_CHECK();

@@ -19,6 +19,10 @@ from torch import nn
 from . import ops
 
 OMEGA_0 = 30.0
+# activation work fused into the tcgen05 GEMM epilogues (forward sin of layers without BatchNorm; cos / BatchNorm-backward
+# reductions in the input-gradient GEMM).  SNB_FUSE_EPILOGUES=0 keeps the stand-alone element-wise kernels (A/B tests).
+import os as _os
+FUSE_EPILOGUES = _os.environ.get("SNB_FUSE_EPILOGUES", "1") != "0"
 
 
 def _r8(x):
@@ -461,14 +465,17 @@ class _Pass:
             st = None
             if training and sp.layer.has_bn:          # batch statistics fused into the GEMM epilogue (CTA-pair kernel)
                 st = ops.gemm_stats(Xv, Wc, Z, bias=b, alpha=OMEGA_0)
-            if st is None:
-                ops.gemm(Xv, Wc, Z, bias=b, alpha=OMEGA_0)
-            a, c, mean, invstd = self._affine(sp.layer, Z, rows, training, st)
             if sp.out in ("cat5", "cats1"):
                 Y = self.bufs[sp.out][:, sp.out_col0:sp.out_col0 + n_out]
             else:
                 Y = self._buf(sp.out, rows, n_out)
-            ops.sine_fwd(Z, a, c, Y)
+            if not sp.layer.has_bn and FUSE_EPILOGUES and ops.gemm_sine_fwd(Xv, Wc, Z, Y, bias=b, alpha=OMEGA_0):
+                a, c, mean, invstd = self._affine(sp.layer, Z, rows, training, None)     # identity: sin already applied
+            else:
+                if st is None:
+                    ops.gemm(Xv, Wc, Z, bias=b, alpha=OMEGA_0)
+                a, c, mean, invstd = self._affine(sp.layer, Z, rows, training, st)
+                ops.sine_fwd(Z, a, c, Y)
             if keep and sp.grad:
                 self.saved[sp.name] = (Wc, Z, a, c, mean, invstd)
         res = []
@@ -533,11 +540,18 @@ class _Pass:
         if gout.get("cats1") is not None:   # forward_Position's X_Encode output carries a gradient
             G = gb("cats1", self.M, self.bufs["cats1"].shape[1])
             ops.convert(gout["cats1"].float().contiguous(), G[:, :net.layer_width // 2])
+        fused_bwd = {}      # sine layer name -> (sum g, sum g*xhat) left by the consumer's fused input-gradient GEMM
+        producers = {(s_.out, s_.out_col0): s_ for s_ in self.specs if s_.kind == "sine"}
+        n_readers = {}
+        for s_ in self.specs:
+            if s_.grad and s_.name in self.saved and ((s_.need_dx and s_.inp != "x") or (s_.inp == "x" and self.x_requires_grad)):
+                n_readers[s_.inp] = n_readers.get(s_.inp, 0) + 1
         for sp in reversed(self.specs):
             if not sp.grad or sp.name not in self.saved:
                 continue
             rows = self.N if sp.out in _RAY_BUFS else self.M
             n_out = sp.n_out
+            fused_db = None
             Xv = self.bufs[sp.inp][:, sp.in_col0:sp.in_col0 + sp.kp]
             if sp.kind == "linear":
                 g = gout.get(sp.out)
@@ -554,9 +568,22 @@ class _Pass:
                     continue
                 Wc, Z, a, c, mean, invstd = self.saved[sp.name]
                 dY = gbuf[sp.out][:, sp.out_col0:sp.out_col0 + n_out]
-                dZ = t.empty(rows, n_out, device=dev, dtype=dt)
                 bn_train = sp.layer.has_bn and training
-                if bn_train:
+                fused = fused_bwd.pop(sp.name, None)
+                if fused is not None:
+                    # the input-gradient GEMM that produced dY already multiplied by cos(.) and reduced the columns
+                    sg, sgx = fused
+                    dZ = dY
+                    if sp.layer.has_bn:
+                        self._acc(grads, sp.layer.norm.weight, sgx)
+                        self._acc(grads, sp.layer.norm.bias, sg)
+                        zero = t.zeros_like(sg)
+                        ops.bn_bwd_apply(dY, Z, a, mean, invstd, (sg / rows) if bn_train else zero,
+                                         (sgx / rows) if bn_train else zero, dZ)
+                    else:
+                        fused_db = sg
+                elif bn_train:
+                    dZ = t.empty(rows, n_out, device=dev, dtype=dt)
                     sg, sgx = ops.sine_bwd_reduce(dY, Z, a, c, mean, invstd)
                     bn = sp.layer.norm
                     self._acc(grads, bn.weight, sgx.float())
@@ -564,6 +591,7 @@ class _Pass:
                     ops.sine_bwd_apply(dY, Z, a, c, dZ, mean, invstd, (sg / rows).float().contiguous(),
                                        (sgx / rows).float().contiguous())
                 else:
+                    dZ = t.empty(rows, n_out, device=dev, dtype=dt)
                     if sp.layer.has_bn:  # eval-mode BN: plain affine, parameters still get gradients
                         sg, sgx = ops.sine_bwd_reduce(dY, Z, a, c, mean, invstd)
                         self._acc(grads, sp.layer.norm.weight, sgx.float())
@@ -574,6 +602,8 @@ class _Pass:
             # bias gradient: alpha * column sums of dZ (analytically zero in front of a train-mode BatchNorm)
             if bn_train:
                 db = t.zeros(n_out, device=dev)
+            elif fused_db is not None:
+                db = alpha * fused_db
             else:
                 db = alpha * ops.col_stats(dZv)[0].float()
             # weight gradient dW[n_out, kp] = alpha * dZ^T . X   (split-K, fp32 atomics into zeros)
@@ -591,7 +621,19 @@ class _Pass:
                 first = sp.inp not in gbuf
                 width = self.bufs[sp.inp].shape[1]
                 G = gb(sp.inp, rows, width)
-                ops.gemm(dZv, Wc[:, :kin], G[:, sp.in_col0:sp.in_col0 + kin], alpha=alpha, accumulate=0 if first else 1, b_t=True)
+                pr = producers.get((sp.inp, sp.in_col0))
+                st = None
+                if (FUSE_EPILOGUES and first and pr is not None and pr.grad and pr.name in self.saved and pr.n_out == kin
+                        and n_readers.get(sp.inp, 0) == 1 and dt == t.bfloat16):
+                    # sole consumer of a sine layer's output: its cos / BatchNorm-backward column sums ride in this epilogue
+                    _, Zp, ap, cp, meanp, invstdp = self.saved[pr.name]
+                    if meanp is None:
+                        meanp, invstdp = t.zeros_like(ap), t.ones_like(ap)
+                    st = ops.gemm_sine_bwd(dZv, Wc[:, :kin], G[:, sp.in_col0:sp.in_col0 + kin], Zp, ap, cp, meanp, invstdp, alpha=alpha)
+                    if st is not None:
+                        fused_bwd[pr.name] = st
+                if st is None:
+                    ops.gemm(dZv, Wc[:, :kin], G[:, sp.in_col0:sp.in_col0 + kin], alpha=alpha, accumulate=0 if first else 1, b_t=True)
         self.gbuf = gbuf
         return grads
 

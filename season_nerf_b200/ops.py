@@ -201,6 +201,64 @@ def gemm_stats(A, B, out, bias=None, alpha=1.0):
     return s[0], s[1]
 
 
+def gemm_sine_fwd(A, B, Z, Y, bias=None, alpha=1.0):
+    """Z = alpha*(A.B^T + bias), Y = sin(Z) in ONE kernel (SIREN layer without BatchNorm, bf16).  -> False when the
+    CTA-pair kernel does not take the shape (caller: gemm + sine_fwd)."""
+    A, lda = _mat(A, "A")
+    B, ldb = _mat(B, "B")
+    Z, ldz = _mat(Z, "Z")
+    Y, ldy = _mat(Y, "Y")
+    if not (A.dtype == B.dtype == Z.dtype == Y.dtype == torch.bfloat16):
+        return False
+    M, N = Z.shape
+    K = A.shape[1]
+    if B.shape[1] != K or A.shape[0] != M or B.shape[0] != N or tuple(Y.shape) != (M, N):
+        raise ValueError("gemm_sine_fwd shape mismatch: A%s B%s Z%s Y%s" % (tuple(A.shape), tuple(B.shape), tuple(Z.shape), tuple(Y.shape)))
+    if bias is not None:
+        _cuda(bias, torch.float32, "bias")
+    rc = _lib.load().snb_gemm_sine_fwd(_ptr(A), lda, _ptr(B), ldb, _ptr(Z), ldz, _ptr(Y), ldy, _ptr(bias), float(alpha), M, N, K,
+                                       _stream())
+    if rc == -2:
+        return False
+    check(rc)
+    return True
+
+
+def gemm_sine_bwd(dZn, W, G, Z, a, c, mean, invstd, alpha=1.0):
+    """G = alpha*(dZn . W) * cos(a*Z + c) with the column sums (sum G, sum G*xhat) fused into the epilogue of the
+    input-gradient GEMM.  dZn [M,K]; W [K,N] (the next layer's weight, rows = its outputs); G, Z [M,N] bf16.
+    -> (sum_g [N], sum_g_xhat [N]) float32, or None when the CTA-pair kernel does not take the shape."""
+    dZn, lda = _mat(dZn, "dZn")
+    W, ldw = _mat(W, "W")
+    G, ldg = _mat(G, "G")
+    Z, ldz = _mat(Z, "Z")
+    if not (dZn.dtype == W.dtype == G.dtype == Z.dtype == torch.bfloat16):
+        return None
+    M, N = G.shape
+    K = dZn.shape[1]
+    if W.shape[0] != K or W.shape[1] != N or dZn.shape[0] != M or tuple(Z.shape) != (M, N):
+        raise ValueError("gemm_sine_bwd shape mismatch: dZn%s W%s G%s Z%s" % (tuple(dZn.shape), tuple(W.shape), tuple(G.shape), tuple(Z.shape)))
+    for v in (a, c, mean, invstd):
+        _cuda(v, torch.float32, "column vector")
+    s = torch.zeros(2, N, device=G.device, dtype=torch.float32)
+    rc = _lib.load().snb_gemm_sine_bwd(_ptr(dZn), lda, _ptr(W), ldw, _ptr(G), ldg, _ptr(Z), ldz, _ptr(a), _ptr(c), _ptr(mean),
+                                       _ptr(invstd), float(alpha), M, N, K, _ptr(s), _stream())
+    if rc == -2:
+        return None
+    check(rc)
+    return s[0], s[1]
+
+
+def bn_bwd_apply(G, Z, a, mean, invstd, k1, k2, dZ):
+    """dZ = a*(G - k1 - xhat*k2) (may alias G)."""
+    G, ldg = _mat(G, "G")
+    Z, ldz = _mat(Z, "Z")
+    dZ, ldo = _mat(dZ, "dZ")
+    check(_lib.load().snb_bn_bwd_apply(_ptr(G), ldg, _ptr(Z), ldz, _ptr(a), _ptr(mean), _ptr(invstd), _ptr(k1), _ptr(k2),
+                                       _ptr(dZ), ldo, Z.shape[0], Z.shape[1], _DT[Z.dtype], _stream()))
+    return dZ
+
+
 def col_stats(Z):
     """-> (sum[N], sumsq[N]) float64 over the rows of Z."""
     Z, ldz = _mat(Z, "Z")

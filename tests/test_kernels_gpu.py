@@ -216,3 +216,56 @@ def test_sine_and_stats_kernels(dt):
     dZ = t.empty_like(Z)
     ops.sine_bwd_apply(dY, Z, aa, cc, dZ, mean.detach().contiguous(), invstd.contiguous(), (sg / M).float(), (sgx / M).float())
     assert relerr(dZ, Zf.grad) < (1e-4 if dt == t.float32 else 1e-2)
+
+
+# ---- fused SIREN epilogues of the CTA-pair GEMM (csrc/gemm_tc2.cu kEpi 1 / 2) ----------------------------------
+@pytest.mark.parametrize("M,N,K", [(1000, 512, 512), (4096, 256, 288), (777, 128, 64), (2048, 512, 64)])
+def test_gemm_sine_fwd_epilogue(M, N, K):
+    from season_nerf_b200 import ops
+    g = t.Generator().manual_seed(5)
+    A = (t.rand(M, K, generator=g) * 2 - 1).cuda().bfloat16()
+    B = ((t.rand(N, K, generator=g) * 2 - 1) * (6 / K) ** 0.5 / 30).cuda().bfloat16()
+    bias = ((t.rand(N, generator=g) * 2 - 1) * 0.05).cuda()
+    Z = t.empty(M, N, device="cuda", dtype=t.bfloat16)
+    Ybuf = t.zeros(M, N + 64, device="cuda", dtype=t.bfloat16)           # output with a row pitch (slice of a wider buffer)
+    assert ops.gemm_sine_fwd(A, B, Z, Ybuf[:, :N], bias=bias, alpha=30.0)
+    zref = 30.0 * (A.float() @ B.float().T + bias)
+    assert maxabs(Z, zref) < 0.02 * float(zref.abs().max())
+    yref = t.sin(Z.float())                                              # sin of the STORED pre-activation
+    assert maxabs(Ybuf[:, :N], yref) < 1e-2
+    assert float(Ybuf[:, N:].abs().max()) == 0.0                         # nothing written past the slice
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(1000, 512, 512, True), (4096, 256, 256, False), (3000, 512, 16, False), (515, 512, 512, True)])
+def test_gemm_sine_bwd_epilogue(M, N, K, bn):
+    from season_nerf_b200 import ops
+    g = t.Generator().manual_seed(6)
+    dZn = (t.randn(M, K, generator=g) * 1e-3).cuda().bfloat16()
+    W = ((t.rand(K, N, generator=g) * 2 - 1) * 0.1).cuda().bfloat16()
+    Z = (t.randn(M, N, generator=g) * 3).cuda().bfloat16()
+    if bn:
+        a = (0.5 + t.rand(N, generator=g)).cuda()
+        c = (t.rand(N, generator=g) - 0.5).cuda()
+        mean = (t.randn(N, generator=g) * 0.1).cuda()
+        invstd = (0.3 + 0.1 * t.rand(N, generator=g)).cuda()
+    else:
+        a, c, mean, invstd = t.ones(N).cuda(), t.zeros(N).cuda(), t.zeros(N).cuda(), t.ones(N).cuda()
+    Gbuf = t.zeros(M, N + 64, device="cuda", dtype=t.bfloat16)
+    st = ops.gemm_sine_bwd(dZn, W, Gbuf[:, :N], Z, a, c, mean, invstd, alpha=30.0)
+    assert st is not None
+    dY = (30.0 * (dZn.float() @ W.float())).bfloat16().float()           # the unfused path stores dY in bf16 first
+    gref = dY * t.cos(a * Z.float() + c)
+    G = Gbuf[:, :N].float()
+    assert relerr(G, gref) < 6e-3
+    assert float(Gbuf[:, N:].abs().max()) == 0.0
+    xhat = (Z.float() - mean) * invstd
+    # the epilogue sums g in fp32 BEFORE the bf16 rounding of the stored tile: |difference| ~ 2^-9 |g| sqrt(M) per column
+    s0, s1 = G.sum(0), (G * xhat).sum(0)
+    assert maxabs(st[0], s0) < 1e-3 * float(G.abs().sum(0).max())
+    assert maxabs(st[1], s1) < 1e-3 * float((G * xhat).abs().sum(0).max())
+    assert maxabs(st[0], gref.sum(0)) < 1e-3 * float(gref.abs().sum(0).max())
+    # second half of the train-mode BatchNorm backward, in place
+    k1, k2 = (st[0] / M).contiguous(), (st[1] / M).contiguous()
+    ref = a * (G - k1 - xhat * k2)
+    ops.bn_bwd_apply(Gbuf[:, :N], Z, a, mean, invstd, k1, k2, Gbuf[:, :N])
+    assert relerr(Gbuf[:, :N], ref) < 6e-3

@@ -54,7 +54,7 @@ def test_graph_step_matches_eager():
         elif sde[k].numel() > 1 and float(sde[k].norm()) > 0:
             # Adam moves every parameter by about lr per step whatever the gradient's magnitude: parameters that start at
             # zero (BatchNorm biases) are compared on that scale, the others relative to their norm
-            assert relerr(sdg[k], sde[k]) < 2e-3 or maxabs(sdg[k], sde[k]) < 2 * lre, (k, relerr(sdg[k], sde[k]))
+            assert relerr(sdg[k], sde[k]) < 2e-3 or maxabs(sdg[k], sde[k]) < n_steps * lre, (k, relerr(sdg[k], sde[k]))
 
 
 def test_graph_step_accepts_host_batches_and_changes_inputs():
