@@ -271,6 +271,15 @@ def run_ours(a):
     if rank == 0 and not a.no_render:
         render = bench_render(snb, ts.network, dev, H, W2C, peaks)
         ts.network.train()
+    extras = None
+    if rank == 0 and world == 1 and not a.no_extras:
+        # bandwidth-bound compositing kernels against the HBM roofline + the two render configurations of BASELINE.json
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import bench_extras as bx
+        extras = {"composite": bx.bench_composite(dev, peaks["hbm_gbs"], peaks["source"]),
+                  "shadow_march": bx.bench_shadow(snb, ts.network, dev, peaks["bf16_tflops"], peaks["source"], 512),
+                  "year_sweep": bx.bench_year(snb, ts.network, dev, peaks["hbm_gbs"], peaks["source"], 1024, 365)}
+        ts.network.train()
     if world > 1:
         dist.barrier()
 
@@ -324,6 +333,8 @@ def run_ours(a):
            "roofline": roofline}
     if render is not None:
         out["render"] = render
+    if extras is not None:
+        out.update(extras)
     if rank == 0:
         if world == 1 and not a.no_cpu:
             out["cpu_baseline"] = cpu_baseline()
@@ -396,6 +407,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-render", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the compositing / shadow-march / year-sweep measurements")
     ap.add_argument("--no-graph", action="store_true", help="eager kernel launches instead of the captured CUDA graph")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else max(a.warmup, 1)

@@ -69,9 +69,11 @@ int snb_cli_composite(const void* rho, const void* deltas, const void* base, con
                       const double* cls, const void* exact_vis, int in_dtype, int N, int S, int C, double* base_img,
                       double* season_img, double* extreme, double* raw_shadow, double* raw_shadow_exact, void* stream);
 /* year sweep: mg_Img_Eval.py:192-228 get_imgs_from_Img_Dict_t_step, fused over T class vectors.
- * cls [T,C] -> out [T,N,3] (float64), out = season colour only (host multiplies the shadow mask). */
+ * cls [T,C] -> out [T,N,3] (float64) = season colour * shade[N,3] (the per-ray Shadow_Adjust factor of :214-226;
+ * null = 1).  float32 components are recombined in float32 and reduced in float64 (|error| < 3e-7); float64
+ * components keep float64 arithmetic throughout.  T*C <= 5120. */
 int snb_year_sweep(const void* rho, const void* deltas, const void* base, const void* adj, const double* cls,
-                   int in_dtype, int N, int S, int C, int T, double* out, void* stream);
+                   const double* shade, int in_dtype, int N, int S, int C, int T, double* out, void* stream);
 
 /* ---- positional encoding: misc.py:105-139 PE_Encode (extended) ------------------------------
  * out[m, col0 + ...] = [x (D), per dim: cos(k_j x) j<n, sin(k_j x) j<n], k_j = 2^j * fl32(pi/2);

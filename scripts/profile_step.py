@@ -51,3 +51,15 @@ tot = sum(v[1] for v in agg.values())
 print("total kernel time %.3f ms in %d launches" % (tot / 1e3, sum(v[0] for v in agg.values())))
 for k, (c, d) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
     print("%9.3f ms %5d %5.1f%%  %s" % (d / 1e3, c, 100 * d / tot, k))
+
+# per-launch durations of the dense kernels, in launch order (forward image pass, solar pass, backward)
+print("\nper-launch durations (us) of the tcgen05 GEMM / activation kernels, in launch order:")
+evs = sorted((e for e in ev if "snb::" in e.name), key=lambda e: e.time_range.start)
+line = []
+for e in evs:
+    nm = e.name.split("snb::")[1].split("(")[0]
+    nm = nm.replace("gemm2_bf16_kernel", "g2").replace("_vec_kernel", "").replace("_kernel", "").replace("__nv_bfloat16", "bf16")
+    d = e.device_time if hasattr(e, "device_time") else e.cuda_time
+    line.append("%s:%.0f" % (nm, d))
+for i in range(0, len(line), 8):
+    print("  " + "  ".join(line[i:i + 8]))

@@ -24,7 +24,7 @@ SIGNATURES = {
     "snb_composite_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "snb_march_transmittance": [_p, _p, _ll, _i, _p, _p],
     "snb_cli_composite": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p],
-    "snb_year_sweep": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p],
+    "snb_year_sweep": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p],
     "snb_pe_encode": [_p, _i, _ll, _i, _i, _p, _i, _i, _i, _i, _p],
     "snb_gemm": [_p, _i, _i, _p, _i, _i, _p, _i, _p, _f, _i, _ll, _i, _i, _i, _i, _p],
     "snb_gemm_stats": [_p, _i, _p, _i, _p, _i, _p, _f, _ll, _i, _i, _p, _p],

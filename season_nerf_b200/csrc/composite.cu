@@ -17,6 +17,72 @@ struct RayAcc {
   float k0, k1, k2;  // sum_s sky (per-sample sky)
 };
 
+// Unrolled forward (S <= 32*kChunks): every load of the ray (6 per sample chunk) is issued before the first scan, so
+// one warp keeps 6*kChunks 128-byte requests in flight instead of waiting on each chunk's shuffle chain in turn.
+template <bool kClassic, int kChunks>
+__global__ void __launch_bounds__(256)
+composite_fwd_unrolled_kernel(const float* __restrict__ rho, const float* __restrict__ deltas, const float* __restrict__ col,
+                              const float* __restrict__ vis, const float* __restrict__ sky, int N, int S,
+                              float* __restrict__ PV, float* __restrict__ PE, float* __restrict__ PS,
+                              float* __restrict__ albedo, float* __restrict__ rendered, float* __restrict__ vis_sum) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int n = blockIdx.x * wpb + (threadIdx.x >> 5); n < N; n += gridDim.x * wpb) {
+    const long long base = (long long)n * S;
+    float y[kChunks], c0[kChunks], c1[kChunks], c2[kChunks], v[kChunks];
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      const int s = c * 32 + lane;
+      const bool ok = s < S;
+      const long long o = base + s;
+      const float r = ok ? __ldg(rho + o) : 0.f, d = ok ? __ldg(deltas + o) : 0.f;
+      c0[c] = ok ? __ldg(col + 3 * o) : 0.f, c1[c] = ok ? __ldg(col + 3 * o + 1) : 0.f, c2[c] = ok ? __ldg(col + 3 * o + 2) : 0.f;
+      v[c] = ok ? __ldg(vis + o) : 0.f;
+      y[c] = r * d;
+    }
+    const float ks0 = __ldg(sky + 3 * n), ks1 = __ldg(sky + 3 * n + 1), ks2 = __ldg(sky + 3 * n + 2);
+    float carry = 0.f, a0 = 0, a1 = 0, a2 = 0, vs = 0, r0 = 0, r1 = 0, r2 = 0;
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      const int s = c * 32 + lane;
+      const long long o = base + s;
+      const float incl = warp_scan_incl(y[c], lane);
+      float prev = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (lane == 0) prev = 0.f;
+      const float pv = expf(-(carry + prev));
+      const float pe = 1.f - expf(-y[c]);
+      const float ps = pv * pe;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+      if (s < S) {
+        if (PV) PV[o] = pv;
+        if (PE) PE[o] = pe;
+        if (PS) PS[o] = ps;
+        a0 += ps * c0[c], a1 += ps * c1[c], a2 += ps * c2[c];
+        vs += v[c] * ps;
+        if (kClassic) {
+          r0 += ps * c0[c] * (v[c] + (1.f - v[c]) * ks0);
+          r1 += ps * c1[c] * (v[c] + (1.f - v[c]) * ks1);
+          r2 += ps * c2[c] * (v[c] + (1.f - v[c]) * ks2);
+        }
+      }
+    }
+    a0 = warp_sum(a0), a1 = warp_sum(a1), a2 = warp_sum(a2), vs = warp_sum(vs);
+    if (kClassic) r0 = warp_sum(r0), r1 = warp_sum(r1), r2 = warp_sum(r2);
+    if (lane == 0) {
+      albedo[3 * n] = a0, albedo[3 * n + 1] = a1, albedo[3 * n + 2] = a2;
+      if (vis_sum) vis_sum[n] = vs;
+      if (kClassic) {
+        rendered[3 * n] = r0, rendered[3 * n + 1] = r1, rendered[3 * n + 2] = r2;
+      } else {
+        const float sv3 = sigmoidf_((vs - .2f) * 30.f);  // Eval_Tools_2.py:214
+        rendered[3 * n] = a0 * (sv3 + (1.f - sv3) * ks0);
+        rendered[3 * n + 1] = a1 * (sv3 + (1.f - sv3) * ks1);
+        rendered[3 * n + 2] = a2 * (sv3 + (1.f - sv3) * ks2);
+      }
+    }
+  }
+}
+
 template <bool kClassic, bool kSkyPerSample>
 __global__ void __launch_bounds__(256)
 composite_fwd_kernel(const float* __restrict__ rho, const float* __restrict__ deltas, const float* __restrict__ col,
@@ -101,6 +167,7 @@ composite_bwd_kernel(const float* __restrict__ rho, const float* __restrict__ de
   for (int n = blockIdx.x * wpb + (threadIdx.x >> 5); n < N; n += gridDim.x * wpb) {
     const long long base = (long long)n * S;
     float pv[kChunks], pe[kChunks];
+    float cc0[kChunks], cc1[kChunks], cc2[kChunks], vv[kChunks], dd[kChunks];   // colour / vis / delta of sweep 1, reused by sweep 2
     float carry = 0.f, a0 = 0, a1 = 0, a2 = 0, vs = 0, k0 = 0, k1 = 0, k2 = 0;
     if (!kSkyPerSample) k0 = __ldg(sky + 3 * n), k1 = __ldg(sky + 3 * n + 1), k2 = __ldg(sky + 3 * n + 2);
 #pragma unroll
@@ -108,7 +175,10 @@ composite_bwd_kernel(const float* __restrict__ rho, const float* __restrict__ de
       const int s = c * 32 + lane;
       const bool ok = s < S;
       const long long o = base + s;
-      const float y = ok ? __ldg(rho + o) * __ldg(deltas + o) : 0.f;
+      dd[c] = ok ? __ldg(deltas + o) : 0.f;
+      cc0[c] = ok ? __ldg(col + 3 * o) : 0.f, cc1[c] = ok ? __ldg(col + 3 * o + 1) : 0.f, cc2[c] = ok ? __ldg(col + 3 * o + 2) : 0.f;
+      vv[c] = ok ? __ldg(vis + o) : 0.f;
+      const float y = ok ? __ldg(rho + o) * dd[c] : 0.f;
       const float incl = warp_scan_incl(y, lane);
       float prev = __shfl_up_sync(0xffffffffu, incl, 1);
       if (lane == 0) prev = 0.f;
@@ -117,8 +187,8 @@ composite_bwd_kernel(const float* __restrict__ rho, const float* __restrict__ de
       carry += __shfl_sync(0xffffffffu, incl, 31);
       if (ok && !kClassic) {
         const float ps = pv[c] * pe[c];
-        a0 += ps * __ldg(col + 3 * o), a1 += ps * __ldg(col + 3 * o + 1), a2 += ps * __ldg(col + 3 * o + 2);
-        vs += __ldg(vis + o) * ps;
+        a0 += ps * cc0[c], a1 += ps * cc1[c], a2 += ps * cc2[c];
+        vs += vv[c] * ps;
         if (kSkyPerSample) k0 += __ldg(sky + 3 * o), k1 += __ldg(sky + 3 * o + 1), k2 += __ldg(sky + 3 * o + 2);
       }
     }
@@ -148,11 +218,11 @@ composite_bwd_kernel(const float* __restrict__ rho, const float* __restrict__ de
       const long long o = base + s;
       float q = 0.f, dpe_tot = 0.f;
       if (ok) {
-        const float c0 = __ldg(col + 3 * o), c1 = __ldg(col + 3 * o + 1), c2 = __ldg(col + 3 * o + 2);
+        const float c0 = cc0[c], c1 = cc1[c], c2 = cc2[c];
         const float ps = pv[c] * pe[c];
         float dps = dPS ? __ldg(dPS + o) : 0.f;
         if (kClassic) {
-          const float v = __ldg(vis + o);
+          const float v = vv[c];
           float q0 = k0, q1 = k1, q2 = k2;
           if (kSkyPerSample) q0 = __ldg(sky + 3 * o), q1 = __ldg(sky + 3 * o + 1), q2 = __ldg(sky + 3 * o + 2);
           const float sh0 = v + (1.f - v) * q0, sh1 = v + (1.f - v) * q1, sh2 = v + (1.f - v) * q2;
@@ -166,7 +236,7 @@ composite_bwd_kernel(const float* __restrict__ rho, const float* __restrict__ de
             dsk0 += t0, dsk1 += t1, dsk2 += t2;
           }
         } else {
-          dps += dA0 * c0 + dA1 * c1 + dA2 * c2 + dvs * __ldg(vis + o);
+          dps += dA0 * c0 + dA1 * c1 + dA2 * c2 + dvs * vv[c];
           d_col[3 * o] = ps * dA0, d_col[3 * o + 1] = ps * dA1, d_col[3 * o + 2] = ps * dA2;
           if (kSkyPerSample && d_sky) d_sky[3 * o] = dk0, d_sky[3 * o + 1] = dk1, d_sky[3 * o + 2] = dk2;
         }
@@ -185,7 +255,7 @@ composite_bwd_kernel(const float* __restrict__ rho, const float* __restrict__ de
       suffix += __shfl_sync(0xffffffffu, incl, 0);
       if (ok) {
         const float dy = dpe_tot * (1.f - pe[c]) - excl;
-        d_rho[o] = dy * __ldg(deltas + o);
+        d_rho[o] = dy * dd[c];
       }
     }
     if (kClassic && !kSkyPerSample && d_sky) {
@@ -287,46 +357,62 @@ cli_composite_kernel(const T* __restrict__ rho, const T* __restrict__ deltas, co
 
 // mg_Img_Eval.py:192-228 fused over the T class vectors: PS, base and adjust are read ONCE per ray and kept
 // in registers (3 samples per lane at S=96); the T recombinations run out of registers.
+//   out[t, n, :] = shade[n, :] * sum_s PS[n,s] * sigmoid(base[n,s,:] + sum_c cls[t,c] * adj[n,s,c,:])
+// Arithmetic type of the T-loop = element type of the components: float32 network outputs are recombined in float32
+// (class mix, sigmoid and the three per-lane terms; |error| < 3e-7 on a [0,1] colour) and reduced across the warp in
+// float64; float64 components (arrays a caller modified on the host) keep the reference's float64 numpy arithmetic.
+// The transmittance scan is float64 in both cases.
+template <typename CT> __device__ __forceinline__ CT sig_ct(CT x);
+template <> __device__ __forceinline__ double sig_ct<double>(double x) { return 1.0 / (1.0 + exp(-x)); }
+template <> __device__ __forceinline__ float sig_ct<float>(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+
 template <typename TI, int kChunks>
 __global__ void __launch_bounds__(128)
 year_sweep_kernel(const TI* __restrict__ rho, const TI* __restrict__ deltas, const TI* __restrict__ base,
-                  const TI* __restrict__ adj, const double* __restrict__ cls, int N, int S, int C, int T,
-                  double* __restrict__ out) {
+                  const TI* __restrict__ adj, const double* __restrict__ cls, const double* __restrict__ shade, int N,
+                  int S, int C, int T, double* __restrict__ out) {
+  typedef TI CT;
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
+  extern __shared__ double cls_s[];          // [T*C] class vectors, converted once per block
+  CT* wsm = reinterpret_cast<CT*>(cls_s);
+  for (int i = threadIdx.x; i < T * C; i += blockDim.x) wsm[i] = (CT)cls[i];
+  __syncthreads();
   for (int n = blockIdx.x * wpb + (threadIdx.x >> 5); n < N; n += gridDim.x * wpb) {
     double carry = 0.0;
-    double ps[kChunks], bc[kChunks][3], ad[kChunks][4][3];
+    CT ps[kChunks], bc[kChunks][3], ad[kChunks][4][3];
 #pragma unroll
     for (int c = 0; c < kChunks; ++c) {
       const int s = c * 32 + lane;
       const bool ok = s < S;
       const long long o = (long long)n * S + s;
-      ps[c] = ps_chunk_d(ok ? (double)rho[o] * (double)deltas[o] : 0.0, lane, carry);
-      if (!ok) ps[c] = 0.0;
+      const double psd = ps_chunk_d(ok ? (double)rho[o] * (double)deltas[o] : 0.0, lane, carry);
+      ps[c] = ok ? (CT)psd : (CT)0;
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        bc[c][d] = ok ? (double)base[3 * o + d] : 0.0;
+        bc[c][d] = ok ? (CT)base[3 * o + d] : (CT)0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ad[c][k][d] = (ok && k < C) ? (double)adj[(o * C + k) * 3 + d] : 0.0;
+        for (int k = 0; k < 4; ++k) ad[c][k][d] = (ok && k < C) ? (CT)adj[(o * C + k) * 3 + d] : (CT)0;
       }
     }
+    double sh[3] = {1.0, 1.0, 1.0};
+    if (shade) sh[0] = shade[3 * (long long)n], sh[1] = shade[3 * (long long)n + 1], sh[2] = shade[3 * (long long)n + 2];
     for (int t = 0; t < T; ++t) {
-      double w[4];
+      CT w[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) w[k] = k < C ? cls[t * C + k] : 0.0;
-      double acc[3] = {0, 0, 0};
+      for (int k = 0; k < 4; ++k) w[k] = k < C ? wsm[t * C + k] : (CT)0;
+      CT acc[3] = {0, 0, 0};
 #pragma unroll
       for (int c = 0; c < kChunks; ++c)
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-          const double mix = w[0] * ad[c][0][d] + w[1] * ad[c][1][d] + w[2] * ad[c][2][d] + w[3] * ad[c][3][d];
-          acc[d] += ps[c] * sigd(bc[c][d] + mix);
+          const CT mix = w[0] * ad[c][0][d] + w[1] * ad[c][1][d] + w[2] * ad[c][2][d] + w[3] * ad[c][3][d];
+          acc[d] += ps[c] * sig_ct<CT>(bc[c][d] + mix);
         }
+      double r[3];
 #pragma unroll
-      for (int d = 0; d < 3; ++d) acc[d] = warp_sum_d(acc[d]);
-      if (lane == 0)
-        for (int d = 0; d < 3; ++d) out[((long long)t * N + n) * 3 + d] = acc[d];
+      for (int d = 0; d < 3; ++d) r[d] = warp_sum_d((double)acc[d]);
+      if (lane < 3) out[((long long)t * N + n) * 3 + lane] = (lane == 0 ? r[0] : lane == 1 ? r[1] : r[2]) * sh[lane];
     }
   }
 }
@@ -344,9 +430,16 @@ extern "C" int snb_composite_fwd(const float* rho, const float* deltas, const fl
   cudaStream_t st = (cudaStream_t)stream;
 #define SNB_FWD(C_, K_) \
   composite_fwd_kernel<C_, K_><<<grid, 256, 0, st>>>(rho, deltas, col, vis, sky, N, S, PV, PE, PS, albedo, rendered, vis_sum)
-  if (classic) { if (sky_per_sample) SNB_FWD(true, true); else SNB_FWD(true, false); }
+#define SNB_FWDU(C_, CH) \
+  composite_fwd_unrolled_kernel<C_, CH><<<grid, 256, 0, st>>>(rho, deltas, col, vis, sky, N, S, PV, PE, PS, albedo, rendered, vis_sum)
+  const int chunks = (S + 31) / 32;
+  if (!sky_per_sample && chunks <= 4) {
+    if (classic) { if (chunks == 1) SNB_FWDU(true, 1); else if (chunks == 2) SNB_FWDU(true, 2); else if (chunks == 3) SNB_FWDU(true, 3); else SNB_FWDU(true, 4); }
+    else { if (chunks == 1) SNB_FWDU(false, 1); else if (chunks == 2) SNB_FWDU(false, 2); else if (chunks == 3) SNB_FWDU(false, 3); else SNB_FWDU(false, 4); }
+  } else if (classic) { if (sky_per_sample) SNB_FWD(true, true); else SNB_FWD(true, false); }
   else { if (sky_per_sample) SNB_FWD(false, true); else SNB_FWD(false, false); }
 #undef SNB_FWD
+#undef SNB_FWDU
   count_launch();
   SNB_LAUNCH_CHECK();
   return SNB_OK;
@@ -425,24 +518,26 @@ extern "C" int snb_cli_composite(const void* rho, const void* deltas, const void
 
 template <typename TI>
 static void launch_sweep(int chunks, int grid, cudaStream_t st, const void* rho, const void* deltas, const void* base,
-                         const void* adj, const double* cls, int N, int S, int C, int T, double* out) {
+                         const void* adj, const double* cls, const double* shade, int N, int S, int C, int T, double* out) {
   const TI *r = (const TI*)rho, *d = (const TI*)deltas, *b = (const TI*)base, *a = (const TI*)adj;
-  if (chunks <= 1) year_sweep_kernel<TI, 1><<<grid, 128, 0, st>>>(r, d, b, a, cls, N, S, C, T, out);
-  else if (chunks == 2) year_sweep_kernel<TI, 2><<<grid, 128, 0, st>>>(r, d, b, a, cls, N, S, C, T, out);
-  else if (chunks == 3) year_sweep_kernel<TI, 3><<<grid, 128, 0, st>>>(r, d, b, a, cls, N, S, C, T, out);
-  else year_sweep_kernel<TI, 4><<<grid, 128, 0, st>>>(r, d, b, a, cls, N, S, C, T, out);
+  const size_t sm = (size_t)T * C * sizeof(double);
+  if (chunks <= 1) year_sweep_kernel<TI, 1><<<grid, 128, sm, st>>>(r, d, b, a, cls, shade, N, S, C, T, out);
+  else if (chunks == 2) year_sweep_kernel<TI, 2><<<grid, 128, sm, st>>>(r, d, b, a, cls, shade, N, S, C, T, out);
+  else if (chunks == 3) year_sweep_kernel<TI, 3><<<grid, 128, sm, st>>>(r, d, b, a, cls, shade, N, S, C, T, out);
+  else year_sweep_kernel<TI, 4><<<grid, 128, sm, st>>>(r, d, b, a, cls, shade, N, S, C, T, out);
 }
 
 extern "C" int snb_year_sweep(const void* rho, const void* deltas, const void* base, const void* adj,
-                              const double* cls, int in_dtype, int N, int S, int C, int T, double* out, void* stream) {
+                              const double* cls, const double* shade, int in_dtype, int N, int S, int C, int T, double* out,
+                              void* stream) {
   SNB_CHECK_ARG(rho && deltas && base && adj && cls && out && N >= 0 && S > 0 && T >= 0);
   SNB_CHECK_ARG(in_dtype == SNB_F32 || in_dtype == SNB_F64);
-  if (C < 1 || C > 4 || S > 128) return SNB_ERR_UNSUPPORTED;
+  if (C < 1 || C > 4 || S > 128 || (long long)T * C * 8 > 40 * 1024) return SNB_ERR_UNSUPPORTED;
   if (N == 0 || T == 0) return SNB_OK;
   const int grid = grid_for(N, 4, 16);
   const int chunks = (S + 31) / 32;
-  if (in_dtype == SNB_F64) launch_sweep<double>(chunks, grid, (cudaStream_t)stream, rho, deltas, base, adj, cls, N, S, C, T, out);
-  else launch_sweep<float>(chunks, grid, (cudaStream_t)stream, rho, deltas, base, adj, cls, N, S, C, T, out);
+  if (in_dtype == SNB_F64) launch_sweep<double>(chunks, grid, (cudaStream_t)stream, rho, deltas, base, adj, cls, shade, N, S, C, T, out);
+  else launch_sweep<float>(chunks, grid, (cudaStream_t)stream, rho, deltas, base, adj, cls, shade, N, S, C, T, out);
   count_launch();
   SNB_LAUNCH_CHECK();
   return SNB_OK;

@@ -135,14 +135,18 @@ def cli_composite(rho, deltas, base, vis, adj, cls, exact_vis=None):
     return base_img, season, extreme, raw, raw_e
 
 
-def year_sweep(rho, deltas, base, adj, cls):
-    """mg_Img_Eval.py:192-228 recombination for T class vectors at once -> [T,N,3] f64."""
+def year_sweep(rho, deltas, base, adj, cls, shade=None, out=None):
+    """mg_Img_Eval.py:192-228 recombination for T class vectors at once -> [T,N,3] f64 (times shade [N,3] f64 if given)."""
     N, S = rho.shape[0], rho.shape[1]
     Cn, T = adj.shape[2], cls.shape[0]
-    out = torch.empty(T, N, 3, device=rho.device, dtype=torch.float64)
+    if out is None:
+        out = torch.empty(T, N, 3, device=rho.device, dtype=torch.float64)
     ins = [x.contiguous() for x in (rho, deltas, base, adj)]
     cls = _cuda(cls, torch.float64).contiguous()
-    check(_lib.load().snb_year_sweep(*[_ptr(x) for x in ins], _ptr(cls), _DT[rho.dtype], N, S, Cn, T, _ptr(out), _stream()))
+    if shade is not None:
+        shade = _cuda(shade, torch.float64, "shade").contiguous()
+    check(_lib.load().snb_year_sweep(*[_ptr(x) for x in ins], _ptr(cls), _ptr(shade), _DT[rho.dtype], N, S, Cn, T, _ptr(out),
+                                     _stream()))
     return out
 
 

@@ -200,20 +200,29 @@ def get_imgs_from_Img_Dict(Img_Dict, out_img_size: tuple, use_classic_shadows: b
     return R
 
 
+def _is_raster_grid(ip, H, W):
+    """Image_Points of component_render_by_dir: every pixel once, in row-major order."""
+    return ip.shape[0] == H * W and bool((ip[:, 0] * W + ip[:, 1] == np.arange(H * W)).all())
+
+
 def get_imgs_from_Img_Dict_t_step(Img_Dict, out_img_size: tuple, class_vecs_array):
-    """mg_Img_Eval.py:192-228: T seasonal recombinations in one fused pass (components read once)."""
+    """mg_Img_Eval.py:192-228: T seasonal recombinations in one fused pass (components read once).  The shadow factor
+    (:214-226) rides in the kernel and the images leave the device once, already in [T,H,W,3] order."""
     has_exact = "Exact_Solar" in Img_Dict.keys()
     vkey = "Exact_Solar" if has_exact else "Est_Solar_Vis"
     rho, dl, base, vis, adj, skyc = _device_components(Img_Dict, ["Rho", "Deltas", "Base_Col", vkey, "Adjust_col", "Sky_Col"])
     N, S = rho.shape[0], rho.shape[1]
-    Sky_Col = skyc[0, 0].double().cpu().numpy()
+    H, W = out_img_size[0], out_img_size[1]
+    sky0 = skyc[0, 0].double()
     cls = t.as_tensor(np.asarray(class_vecs_array), dtype=t.float64).to(rho.device).contiguous()
+    T = cls.shape[0]
     _, _, _, raw, _ = ops.cli_composite(rho.reshape(N, S), dl.reshape(N, S), base, vis.reshape(N, S), adj, cls[0].contiguous())
-    Raw = _scatter(Img_Dict, out_img_size, raw)
-    Mask = sig((Raw - .2) * 30)
-    Shadow_Adjust = np.expand_dims(Mask, -1) + np.expand_dims(1 - Mask, -1) * Sky_Col.reshape([1, 1, 3])
-    cols = ops.year_sweep(rho.reshape(N, S), dl.reshape(N, S), base, adj, cls).cpu().numpy()       # [T,N,3]
-    ip = Img_Dict["Image_Points"]
-    imgs = np.zeros([cols.shape[0], out_img_size[0], out_img_size[1], 3]) * np.nan
-    imgs[:, ip[:, 0], ip[:, 1]] = cols
-    return imgs * Shadow_Adjust[None]
+    mask = t.sigmoid((raw - .2) * 30).unsqueeze(1)                                 # [N,1] float64
+    shade = (mask + (1 - mask) * sky0.reshape(1, 3)).contiguous()                  # Shadow_Adjust per ray
+    cols = ops.year_sweep(rho.reshape(N, S), dl.reshape(N, S), base, adj, cls, shade=shade)        # [T,N,3]
+    ip = np.asarray(Img_Dict["Image_Points"])
+    if _is_raster_grid(ip, H, W):
+        return cols.cpu().numpy().reshape(T, H, W, 3)
+    imgs = t.full((T, H * W, 3), float("nan"), device=cols.device, dtype=t.float64)
+    imgs[:, t.as_tensor(ip[:, 0] * W + ip[:, 1], device=cols.device)] = cols
+    return imgs.cpu().numpy().reshape(T, H, W, 3)
