@@ -123,6 +123,14 @@ int snb_bn_bwd_apply(const void* G, int ldg, const void* Z, int ldz, const float
                      const float* invstd, const float* k1, const float* k2, void* dZ, int ldo, long long M, int N,
                      int dtype, void* stream);
 
+/* Train-mode nn.BatchNorm1d(momentum, eps) bookkeeping of one SineLayer in one launch (misc.py:169-170,189): from the
+ * column sums (float32 or float64, stats_dtype) of the M = rows pre-activations: batch mean / biased variance, the
+ * running_mean / running_var update (unbiased variance, in place), num_batches_tracked += 1 (may be null), and the
+ * folded affine a = gamma*invstd, c = beta - mean*a plus mean, invstd for the backward (all float32 [N]). */
+int snb_bn_finalize(const void* sum, const void* sumsq, int stats_dtype, long long rows, int N, const float* gamma,
+                    const float* beta, float* running_mean, float* running_var, long long* num_batches, float momentum,
+                    float eps, float* a, float* c, float* mean, float* invstd, void* stream);
+
 /* column statistics for train-mode BatchNorm1d (misc.py:169-170): sum[n], sumsq[n] over M rows (float64 out). */
 int snb_col_stats(const void* Z, int dtype, int ldz, long long M, int N, double* sum, double* sumsq, void* stream);
 

@@ -38,6 +38,87 @@ __global__ void __launch_bounds__(256) pe_encode_kernel(const float* __restrict_
   }
 }
 
+
+// Warp-per-row variant for D = 3 with an output row of at most 64 columns (position: 63 -> 64, sun: 27 -> 32): lane l < 3n
+// evaluates ONE sincosf (dimension l / n, frequency l % n), the row is assembled with two shuffles per output column pair
+// and written as one contiguous 4-byte-per-lane store (bf16) - instead of 2-byte stores scattered over the row pitch.
+template <typename TO>
+__global__ void __launch_bounds__(256) pe_encode_row_kernel(const float* __restrict__ x, int ldx, long long M, int n,
+                                                            TO* __restrict__ out, int ldo, int col0, int pad_to) {
+  const float kPiHalf = 1.57079637050628662109375f;  // float32(pi/2)
+  const int lane = threadIdx.x & 31;
+  const int width = 3 * (2 * n + 1);
+  // lane -> (dim, freq) it evaluates
+  const int d_l = lane / n, j_l = lane - d_l * n;
+  float k = kPiHalf;
+  for (int j = 0; j < j_l; ++j) k = __fmul_rn(k, 2.0f);
+  // output columns 2*lane, 2*lane+1 -> source lane and sin/cos selector (column c >= 3: d = (c-3)/(2n), r = (c-3)%(2n))
+  int src[2], is_sin[2], kind[2];   // kind 0: raw x, 1: trig, 2: zero pad
+  for (int h = 0; h < 2; ++h) {
+    const int c = 2 * lane + h;
+    if (c < 3) kind[h] = 0, src[h] = c, is_sin[h] = 0;
+    else if (c < width) {
+      const int d = (c - 3) / (2 * n), r = (c - 3) - d * 2 * n;
+      kind[h] = 1, is_sin[h] = r >= n, src[h] = d * n + (r >= n ? r - n : r);
+    } else kind[h] = 2, src[h] = 0, is_sin[h] = 0;
+  }
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long m = warp0; m < M; m += nwarps) {
+    const float xv = lane < 3 ? __ldg(x + m * ldx + lane) : 0.f;
+    const float xd = __shfl_sync(0xffffffffu, xv, d_l < 3 ? d_l : 0);
+    float sv = 0.f, cv = 0.f;
+    if (lane < 3 * n) sincosf(__fmul_rn(k, xd), &sv, &cv);
+    float o[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float s_ = __shfl_sync(0xffffffffu, sv, src[h]), c_ = __shfl_sync(0xffffffffu, cv, src[h]);
+      const float r_ = __shfl_sync(0xffffffffu, xv, src[h] < 3 ? src[h] : 0);
+      o[h] = kind[h] == 0 ? r_ : (kind[h] == 1 ? (is_sin[h] ? s_ : c_) : 0.f);
+    }
+    if (2 * lane < pad_to) {
+      TO* dst = out + m * ldo + col0 + 2 * lane;
+      if (2 * lane + 1 < pad_to) {
+        if (sizeof(TO) == 2) {
+          __nv_bfloat162 v2 = __floats2bfloat162_rn(o[0], o[1]);
+          *reinterpret_cast<__nv_bfloat162*>(dst) = v2;
+        } else {
+          dst[0] = from_f32<TO>(o[0]), dst[1] = from_f32<TO>(o[1]);
+        }
+      } else {
+        dst[0] = from_f32<TO>(o[0]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Train-mode BatchNorm1d bookkeeping of one layer in ONE launch (misc.py:169-170; nn.BatchNorm1d(momentum, eps)):
+// batch mean / biased variance from the column sums, running-statistics update (unbiased variance), and the folded
+// affine  y = a*z + c  with  a = gamma*invstd, c = beta - mean*a  that the activation kernels consume.
+template <typename TS>
+__global__ void bn_finalize_kernel(const TS* __restrict__ sum, const TS* __restrict__ sumsq, long long rows, int N,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float* running_mean,
+                                   float* running_var, long long* num_batches, float momentum, float eps, float* __restrict__ a,
+                                   float* __restrict__ c, float* __restrict__ mean_out, float* __restrict__ invstd_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && num_batches) *num_batches += 1;
+  if (i >= N) return;
+  const double mean = (double)sum[i] / (double)rows;
+  double var = (double)sumsq[i] / (double)rows - mean * mean;
+  if (var < 0.0) var = 0.0;
+  running_mean[i] = running_mean[i] * (1.f - momentum) + (float)mean * momentum;
+  const double unb = var * ((double)rows / (double)(rows > 1 ? rows - 1 : 1));
+  running_var[i] = running_var[i] * (1.f - momentum) + (float)unb * momentum;
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float meanf = (float)mean;
+  const float av = gamma[i] * invstd;
+  a[i] = av;
+  c[i] = beta[i] - meanf * av;
+  mean_out[i] = meanf;
+  invstd_out[i] = invstd;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Column sums over M rows (float64 results through double atomics; inner accumulation in float32 over
 // at most 128 rows per flush).  Threads own column pairs -> 4/8-byte loads, fully coalesced per row.
@@ -387,8 +468,18 @@ extern "C" int snb_pe_encode(const float* x, int ldx, long long M, int D, int n_
   SNB_CHECK_ARG(x && out && M >= 0 && D > 0 && n_freq >= 0 && ldx >= D && ldo >= col0 + D * (2 * n_freq + 1));
   SNB_CHECK_ARG(pad_to <= ldo - col0);
   if (M == 0) return SNB_OK;
-  const int grid = grid_for(M * D, 256, 16);
   cudaStream_t st = (cudaStream_t)stream;
+  if (D == 3 && n_freq >= 1 && 3 * n_freq <= 32 && pad_to <= 64 && pad_to >= D * (2 * n_freq + 1) && (ldo % 2) == 0 && (col0 % 2) == 0 &&
+      ((uintptr_t)out % 4) == 0 && M >= 64) {
+    const int grid_r = grid_for(M, 8, 16);
+    if (out_dtype == SNB_F32) pe_encode_row_kernel<float><<<grid_r, 256, 0, st>>>(x, ldx, M, n_freq, (float*)out, ldo, col0, pad_to);
+    else if (out_dtype == SNB_BF16) pe_encode_row_kernel<bf16><<<grid_r, 256, 0, st>>>(x, ldx, M, n_freq, (bf16*)out, ldo, col0, pad_to);
+    else return SNB_ERR_ARG;
+    count_launch();
+    SNB_LAUNCH_CHECK();
+    return SNB_OK;
+  }
+  const int grid = grid_for(M * D, 256, 16);
   if (out_dtype == SNB_F32) pe_encode_kernel<float><<<grid, 256, 0, st>>>(x, ldx, M, D, n_freq, (float*)out, ldo, col0, pad_to);
   else if (out_dtype == SNB_BF16) pe_encode_kernel<bf16><<<grid, 256, 0, st>>>(x, ldx, M, D, n_freq, (bf16*)out, ldo, col0, pad_to);
   else return SNB_ERR_ARG;
@@ -528,6 +619,24 @@ extern "C" int snb_bn_bwd_apply(const void* G, int ldg, const void* Z, int ldz, 
   if (!v.ok) return SNB_ERR_UNSUPPORTED;
   if (dtype == SNB_F32) bn_bwd_apply_vec_kernel<float><<<v.grid, v.block, 0, st>>>((const float*)G, ldg, (const float*)Z, ldz, a, mean, invstd, k1, k2, (float*)dZ, ldo, M, N);
   else if (dtype == SNB_BF16) bn_bwd_apply_vec_kernel<bf16><<<v.grid, v.block, 0, st>>>((const bf16*)G, ldg, (const bf16*)Z, ldz, a, mean, invstd, k1, k2, (bf16*)dZ, ldo, M, N);
+  else return SNB_ERR_ARG;
+  count_launch();
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_bn_finalize(const void* sum, const void* sumsq, int stats_dtype, long long rows, int N, const float* gamma,
+                               const float* beta, float* running_mean, float* running_var, long long* num_batches,
+                               float momentum, float eps, float* a, float* c, float* mean, float* invstd, void* stream) {
+  SNB_CHECK_ARG(sum && sumsq && gamma && beta && running_mean && running_var && a && c && mean && invstd && rows > 0 && N > 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = (N + 127) / 128;
+  if (stats_dtype == SNB_F32)
+    bn_finalize_kernel<float><<<grid, 128, 0, st>>>((const float*)sum, (const float*)sumsq, rows, N, gamma, beta, running_mean,
+                                                    running_var, num_batches, momentum, eps, a, c, mean, invstd);
+  else if (stats_dtype == SNB_F64)
+    bn_finalize_kernel<double><<<grid, 128, 0, st>>>((const double*)sum, (const double*)sumsq, rows, N, gamma, beta, running_mean,
+                                                     running_var, num_batches, momentum, eps, a, c, mean, invstd);
   else return SNB_ERR_ARG;
   count_launch();
   SNB_LAUNCH_CHECK();

@@ -137,11 +137,22 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  // work item -> (tile_m, tile_n, split); tile_n fastest so that the pair reuses its A rows from L2
+  // work item -> (tile_m, tile_n, split).  Without split-K: tile_n fastest, so that the pair reuses its A rows from L2.
+  // Split-K (weight gradient: few output tiles, K = all rows of the batch): the output tile is the fastest index, so that
+  // the pairs that run at the same time share one K range and both operand slabs are fetched from HBM once (the four
+  // 256 x 256 tiles of a 512 x 512 weight gradient would otherwise read each operand twice).
   auto decode = [&](int t, int& tm, int& tn, int& ks) {
-    ks = t % p.splits;
-    tn = (t / p.splits) % p.tiles_n;
-    tm = t / (p.splits * p.tiles_n);
+    if (p.splits > 1) {
+      const int tiles = p.tiles_m * p.tiles_n;
+      ks = t / tiles;
+      const int tile = t - ks * tiles;
+      tn = tile % p.tiles_n;
+      tm = tile / p.tiles_n;
+    } else {
+      ks = 0;
+      tn = t % p.tiles_n;
+      tm = t / p.tiles_n;
+    }
   };
 
   if (warp == 0) {
@@ -339,18 +350,24 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
             const float2 m2 = __ldg(reinterpret_cast<const float2*>(p.emean + cg));
             const float2 i2 = __ldg(reinterpret_cast<const float2*>(p.einvstd + cg));
             float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;     // sum g, sum g*z per column
+            // three phases (all loads, all arithmetic, all stores): the volatile shared-memory accesses keep their
+            // program order, so interleaving them with the arithmetic would serialise the 32 rows
+            uint32_t dw[32];
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(dw[r]) : "r"(buf + (uint32_t)r * 128u + sw_off[r & 7]));
 #pragma unroll
             for (int r = 0; r < 32; ++r) {
-              const uint32_t addr = buf + (uint32_t)r * 128u + sw_off[r & 7];
-              uint32_t dw;
-              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(dw) : "r"(addr));
               const float z0 = __uint_as_float(zc[r] << 16), z1 = __uint_as_float(zc[r] & 0xFFFF0000u);
-              const float g0 = __uint_as_float(dw << 16) * __cosf(fmaf(a2.x, z0, c2.x));
-              const float g1 = __uint_as_float(dw & 0xFFFF0000u) * __cosf(fmaf(a2.y, z1, c2.y));
-              asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(pack_bf16x2(g0, g1)) : "memory");
+              const float g0 = __uint_as_float(dw[r] << 16) * __cosf(fmaf(a2.x, z0, c2.x));
+              const float g1 = __uint_as_float(dw[r] & 0xFFFF0000u) * __cosf(fmaf(a2.y, z1, c2.y));
+              dw[r] = pack_bf16x2(g0, g1);
               s0 += g0, s1 += g1;
               q0 = fmaf(g0, z0, q0), q1 = fmaf(g1, z1, q1);
             }
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(buf + (uint32_t)r * 128u + sw_off[r & 7]), "r"(dw[r]) : "memory");
             // sum g*xhat = invstd * (sum g*z - mean * sum g)
             q0 = i2.x * (q0 - m2.x * s0), q1 = i2.y * (q1 - m2.y * s1);
 #pragma unroll

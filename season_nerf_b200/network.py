@@ -394,11 +394,23 @@ class _Pass:
 
     # -- weights in compute dtype, K padded to the buffer width (zero columns) --
     def _wc(self, spec):
+        """(weight in the compute dtype, K zero-padded to the operand width; float32 bias).  Staged once per parameter
+        version: the image pass and the solar pass of one training step share it (the cache lives on the first nn.Linear
+        of the spec; a CUDA-graph replay bumps the version counters, see train.TrainStep)."""
+        key = (tuple((l.weight._version, l.bias._version, l.weight.data_ptr()) for l in spec.lin), self.dt, spec.kp)
+        hit = spec.lin[0].__dict__.get("_snb_wc")
+        if hit is not None and hit[0] == key:
+            return hit[1], hit[2]
         W = t.cat([l.weight for l in spec.lin], 0) if len(spec.lin) > 1 else spec.lin[0].weight
-        Wc = t.zeros(W.shape[0], spec.kp, device=W.device, dtype=self.dt)
+        if spec.kp == W.shape[1]:
+            Wc = t.empty(W.shape[0], spec.kp, device=W.device, dtype=self.dt)
+        else:
+            Wc = t.zeros(W.shape[0], spec.kp, device=W.device, dtype=self.dt)
         ops.convert(W.detach(), Wc[:, :W.shape[1]])
         b = t.cat([l.bias for l in spec.lin], 0) if len(spec.lin) > 1 else spec.lin[0].bias
-        return Wc, b.detach().float().contiguous()
+        b = b.detach().float().contiguous()
+        spec.lin[0].__dict__["_snb_wc"] = (key, Wc, b)
+        return Wc, b
 
     def _buf(self, name, rows, width, dtype=None, zero=False):
         if name not in self.bufs:
@@ -439,8 +451,13 @@ class _Pass:
             self._buf("cats1", M, self._width("cats1"))
         if "fc_solar_1" in names:
             sun = sun.float().contiguous()
-            sun_pts = sun if S == 1 else sun.repeat_interleave(S, 0)
-            ops.pe_encode(sun_pts, net.G_NeRF_net._expand_size_solar_angle, self.bufs["cats1"], col0=net.layer_width // 2, pad_to=32)
+            lw2 = net.layer_width // 2
+            if S == 1:
+                ops.pe_encode(sun, net.G_NeRF_net._expand_size_solar_angle, self.bufs["cats1"], col0=lw2, pad_to=32)
+            else:   # the direction is per ray: encode N rows, broadcast over the S samples of each ray
+                senc_ray = t.empty(N, 32, device=dev, dtype=self.dt)
+                ops.pe_encode(sun, net.G_NeRF_net._expand_size_solar_angle, senc_ray, pad_to=32)
+                self.bufs["cats1"].view(N, S, -1)[:, :, lw2:lw2 + 32] = senc_ray.unsqueeze(1)
         if "fc_sky_color_1" in names:
             sun = sun.float().contiguous()
             if X is None:
@@ -502,16 +519,8 @@ class _Pass:
         bn = layer.norm
         if training:
             s, ss = stats if stats is not None else ops.col_stats(Z)
-            s, ss = s.double(), ss.double()
-            mean = s / rows
-            var = t.clamp(ss / rows - mean * mean, min=0.0)
             with t.no_grad():
-                m = bn.momentum
-                bn.running_mean.mul_(1 - m).add_(mean.float() * m)
-                bn.running_var.mul_(1 - m).add_((var * (rows / max(rows - 1, 1))).float() * m)
-                bn.num_batches_tracked += 1
-            invstd = (1.0 / t.sqrt(var + bn.eps)).float()
-            mean = mean.float()
+                return ops.bn_finalize(s, ss, rows, bn)      # one launch: batch statistics, running update, folded affine
         else:
             mean = bn.running_mean.detach().float()
             invstd = 1.0 / t.sqrt(bn.running_var.detach().float() + bn.eps)
@@ -540,6 +549,9 @@ class _Pass:
         if gout.get("cats1") is not None:   # forward_Position's X_Encode output carries a gradient
             G = gb("cats1", self.M, self.bufs["cats1"].shape[1])
             ops.convert(gout["cats1"].float().contiguous(), G[:, :net.layer_width // 2])
+        dw_total = sum(s_.n_out * s_.kp for s_ in self.specs if s_.grad and s_.name in self.saved)
+        dw_flat = t.zeros(dw_total, device=dev, dtype=t.float32)      # ONE fill for all split-K weight-gradient targets
+        dw_off = 0
         fused_bwd = {}      # sine layer name -> (sum g, sum g*xhat) left by the consumer's fused input-gradient GEMM
         producers = {(s_.out, s_.out_col0): s_ for s_ in self.specs if s_.kind == "sine"}
         n_readers = {}
@@ -559,10 +571,12 @@ class _Pass:
                     continue
                 (Wc,) = self.saved[sp.name]
                 dZ = t.zeros(rows, 16 if n_out <= 16 else _r8(n_out), device=dev, dtype=dt)
-                ops.convert(g.float().contiguous(), dZ[:, :n_out])
+                g = g.float().contiguous()
+                ops.convert(g, dZ[:, :n_out])
                 dZv = dZ[:, :n_out]
                 alpha = 1.0
                 bn_train = False
+                fused_db = g.sum(0)                # bias gradient of a head: column sums of the incoming float32 gradient
             else:
                 if sp.out not in gbuf:
                     continue
@@ -607,7 +621,8 @@ class _Pass:
             else:
                 db = alpha * ops.col_stats(dZv)[0].float()
             # weight gradient dW[n_out, kp] = alpha * dZ^T . X   (split-K, fp32 atomics into zeros)
-            dW = t.zeros(n_out, sp.kp, device=dev, dtype=t.float32)
+            dW = dw_flat[dw_off:dw_off + n_out * sp.kp].view(n_out, sp.kp)
+            dw_off += n_out * sp.kp
             ops.gemm(dZv, Xv, dW, alpha=alpha, accumulate=2, a_t=True, b_t=True)
             r0 = 0
             for lin in sp.lin:

@@ -263,6 +263,19 @@ def bn_bwd_apply(G, Z, a, mean, invstd, k1, k2, dZ):
     return dZ
 
 
+def bn_finalize(s, ss, rows, bn):
+    """train-mode BatchNorm1d bookkeeping in one launch -> (a, c, mean, invstd) float32 [N]; updates the module's running
+    statistics and batch counter in place (misc.py:169-170)."""
+    N = s.shape[0]
+    out = torch.empty(4, N, device=s.device, dtype=torch.float32)
+    nb = bn.num_batches_tracked
+    check(_lib.load().snb_bn_finalize(_ptr(s), _ptr(ss), _DT[s.dtype], int(rows), N, _ptr(bn.weight.detach()), _ptr(bn.bias.detach()),
+                                      _ptr(bn.running_mean), _ptr(bn.running_var), _ptr(nb) if nb is not None and nb.is_cuda else None,
+                                      float(bn.momentum), float(bn.eps), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]),
+                                      _stream()))
+    return out[0], out[1], out[2], out[3]
+
+
 def col_stats(Z):
     """-> (sum[N], sumsq[N]) float64 over the rows of Z."""
     Z, ldz = _mat(Z, "Z")

@@ -99,6 +99,7 @@ class TrainStep:
             if self.optim2 is not None else None
         self._flat = None
         self.last_loss = None
+        self._versioned = [v for v in self.network.state_dict(keep_vars=True).values()] + list(ada_params)
 
     def _allreduce_grads(self):
         """one flat fp32 bucket (3.19 M network gradients + the adaptive-loss scalars), NCCL sum -> mean"""
@@ -181,6 +182,9 @@ class TrainStep:
                 st["g_opt"] = g_opt
         st["g_fb"].replay()
         self.launches_replayed += st["launches"]
+        # a replay rewrites parameters and BatchNorm buffers behind autograd's back: bump their version counters so that
+        # every derived cache (packed render program, staged bf16 weights) sees the change
+        t.autograd.graph.increment_version(self._versioned)
         if self.world_size > 1:
             self._allreduce_grads()
             st["g_opt"].replay()
