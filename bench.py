@@ -41,17 +41,20 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  The sampler process is
+    started once, well before the timed region (nvidia-smi needs a few hundred ms to come up); every line is stamped on
+    arrival and `summary(t0, t1)` keeps the samples that fell inside the region."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index=0):
-        self.index, self.lines, self.proc = index, [], None
+    def __init__(self, index=0, period_ms=25):
+        self.index, self.lines, self.proc, self.period_ms = index, [], None, period_ms
 
-    def __enter__(self):
+    def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
+                                         stdout=subprocess.PIPE, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
         except Exception:
@@ -60,19 +63,22 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
 
-    def __exit__(self, *a):
+    def stop(self):
         if self.proc is not None:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
+            self.proc = None
 
-    def summary(self):
+    def summary(self, t0=None, t1=None):
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ts_, ln in self.lines:
+            if t0 is not None and not (t0 <= ts_ <= t1 + 0.05):
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -188,6 +194,7 @@ def run_ours(a):
     peaks = _peaks()
     args = bench_args()
     n = a.rays
+    sampler = ClockSampler(local).start()
     # OMA_281-like frame
     W2C = np.array([41.2905, -95.8967, 315.0])
     H = np.eye(4)
@@ -235,18 +242,19 @@ def run_ours(a):
         barrier()
         l0 = _lib.launch_count() + ts.launches_replayed
         e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
-        with ClockSampler(local) as cs:
-            e0.record()
-            for i in range(steps):
-                fn(warmup + i)
-            e1.record()
-            barrier()
+        w0 = time.time()
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        barrier()
+        w1 = time.time()
         ms = e0.elapsed_time(e1)
         if world > 1:
             tt = t.tensor([ms], device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms = float(tt)
-        return ms, _lib.launch_count() + ts.launches_replayed - l0, cs.summary()
+        return ms, _lib.launch_count() + ts.launches_replayed - l0, sampler.summary(w0, w1)
 
     # ---- value: device-resident inputs ------------------------------------------------------------------
     def step_dev(i):
@@ -265,12 +273,37 @@ def run_ours(a):
 
     ms_e, _, _ = timed(step_host, a.steps, max(a.warmup, 3))
     e2e = world * n * a.steps / (ms_e * 1e-3)
+    sampler.stop()
 
     # ---- secondary: fused render kernel, 512x512x96 view ----------------------------------------------------------------
     render = None
     if rank == 0 and not a.no_render:
         render = bench_render(snb, ts.network, dev, H, W2C, peaks)
         ts.network.train()
+    # ---- ray-sharded render at N GPUs (strong scaling of one fixed 1024x1024 view; final gather of 12 B/ray) -------------
+    sharded = None
+    if not a.no_render:
+        ts.network.eval()
+        size_s = (1024, 1024, S)
+        snb.render_image_sharded(ts.network, [80, 0], [45, 135], 184 / 365, (64, 64, S), W2C, H, dev, rank, world)   # warm-up
+        barrier()
+        e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+        e0.record()
+        img, _ = snb.render_image_sharded(ts.network, [80, 0], [45, 135], 184 / 365, size_s, W2C, H, dev, rank, world)
+        e1.record()
+        barrier()
+        ms_r = e0.elapsed_time(e1)
+        if world > 1:
+            tt = t.tensor([ms_r], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms_r = float(tt)
+        sharded = {"workload": "1024x1024x96 novel view (estimated shadows), rays sharded over %d GPU(s), float64 composite, "
+                               "final gather of the image (season_nerf_b200.render_image_sharded)" % world,
+                   "rays": size_s[0] * size_s[1], "ms": ms_r, "rays_per_s": size_s[0] * size_s[1] / (ms_r * 1e-3),
+                   "scaling": "strong", "finite": bool((img == img).all()),
+                   "mlp_tflops_algorithmic": size_s[0] * size_s[1] * RENDER_FLOP_PER_RAY / (ms_r * 1e-3) / 1e12}
+        ts.network.train()
+
     extras = None
     if rank == 0 and world == 1 and not a.no_extras:
         # bandwidth-bound compositing kernels against the HBM roofline + the two render configurations of BASELINE.json
@@ -333,6 +366,8 @@ def run_ours(a):
            "roofline": roofline}
     if render is not None:
         out["render"] = render
+    if sharded is not None:
+        out["render_sharded"] = sharded
     if extras is not None:
         out.update(extras)
     if rank == 0:

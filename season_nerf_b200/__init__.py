@@ -17,7 +17,7 @@ from .geometry import LLA_get_vec, encode_time, world_angle_2_local_vec
 from .network import G_NeRF_Net_Classic, PE_Encode, SineLayer, T_NeRF
 from .quick_run import Quick_Run_Net
 from .render import (DeviceImgDict, _internal_render, component_render_by_dir, component_render_by_P,
-                     get_imgs_from_Img_Dict, get_imgs_from_Img_Dict_t_step)
+                     get_imgs_from_Img_Dict, get_imgs_from_Img_Dict_t_step, render_image_sharded, render_shard)
 from .train import TrainStep
 
 __version__ = "0.1.0"

@@ -226,3 +226,58 @@ def get_imgs_from_Img_Dict_t_step(Img_Dict, out_img_size: tuple, class_vecs_arra
     imgs = t.full((T, H * W, 3), float("nan"), device=cols.device, dtype=t.float64)
     imgs[:, t.as_tensor(ip[:, 0] * W + ip[:, 1], device=cols.device)] = cols
     return imgs.cpu().numpy().reshape(T, H, W, 3)
+
+
+# ---- ray-sharded rendering over the GPUs of one box (the reference is single-device) ---------------------------
+def view_rays(view_el_az, out_img_size, W2C, W2L_H):
+    """tops / bots [H*W,3] float32 of component_render_by_dir's pixel grid (mg_Img_Eval.py:98-106)."""
+    H, W = out_img_size[0], out_img_size[1]
+    XYZ = np.stack(np.meshgrid(np.linspace(1, -1, H), np.linspace(-1, 1, W), indexing="ij"), -1).reshape([-1, 2])
+    XYZ = np.concatenate([XYZ, np.zeros([XYZ.shape[0], 1])], 1)
+    view_vec = world_angle_2_local_vec(view_el_az[0], view_el_az[1], W2C, W2L_H)
+    tops = t.tensor(XYZ + np.expand_dims(view_vec / view_vec[2], 0)).float()
+    bots = t.tensor(XYZ - np.expand_dims(view_vec / view_vec[2], 0)).float()
+    return tops, bots
+
+
+def render_shard(the_network, view_el_az, sun_el_az, time_frac, out_img_size, W2C, W2L_H, device, rank=0, world_size=1,
+                 include_exact_solar=False, class_vecs=None):
+    """This rank's contiguous range of the H*W rays of a novel view, rendered and composited on the device:
+    -> (lo, hi, rgb [hi-lo,3] float64, shadow_mask [hi-lo] float64) with rgb = Season_Adj_Img * Shadow_Adjust(_Exact)
+    exactly as main_run_Season_NeRF.py:90-92 forms the output image; with `class_vecs` [T,C]: rgb is the [T,hi-lo,3] year
+    sweep of get_imgs_from_Img_Dict_t_step.  No communication: rays are independent."""
+    from .train import shard_range
+    tops, bots = view_rays(view_el_az, out_img_size, W2C, W2L_H)
+    lo, hi = shard_range(tops.shape[0], rank, world_size)
+    sun_vec = world_angle_2_local_vec(sun_el_az[0], sun_el_az[1], W2C, W2L_H)
+    with t.no_grad():
+        D = _internal_render(the_network, tops[lo:hi], bots[lo:hi], sun_vec, time_frac, out_img_size, 150000,
+                             include_exact_solar, device)
+        keys = ["Rho", "Deltas", "Base_Col", "Est_Solar_Vis", "Adjust_col", "Output_class", "Sky_Col"]
+        rho, dl, base, vis, adj, ocl, skyc = [D.dev[k] for k in keys]
+        n, S = rho.shape[0], rho.shape[1]
+        ev = D.dev["Exact_Solar"].reshape(n, S) if include_exact_solar else None
+        sky0 = skyc[0, 0].double()
+        cls0 = ocl[0, 0].double().contiguous() if class_vecs is None else \
+            t.as_tensor(np.asarray(class_vecs), dtype=t.float64).to(rho.device)[0].contiguous()
+        _, season, _, raw, raw_e = ops.cli_composite(rho.reshape(n, S), dl.reshape(n, S), base, vis.reshape(n, S), adj, cls0, ev)
+        mask = t.sigmoid(((raw_e if include_exact_solar else raw) - .2) * 30)
+        shade = (mask.unsqueeze(1) + (1 - mask.unsqueeze(1)) * sky0.reshape(1, 3)).contiguous()
+        if class_vecs is None:
+            return lo, hi, season * shade, mask
+        cls = t.as_tensor(np.asarray(class_vecs), dtype=t.float64).to(rho.device).contiguous()
+        return lo, hi, ops.year_sweep(rho.reshape(n, S), dl.reshape(n, S), base, adj, cls, shade=shade), mask
+
+
+def render_image_sharded(the_network, view_el_az, sun_el_az, time_frac, out_img_size, W2C, W2L_H, device, rank=0,
+                         world_size=1, include_exact_solar=False):
+    """Ray-sharded novel-view render with the final gather (12 bytes of colour + a mask value per ray): every rank returns
+    the full [H,W,3] float64 image and the [H,W] shadow mask.  world_size 1 needs no process group."""
+    from .train import gather_rows
+    H, W = out_img_size[0], out_img_size[1]
+    lo, hi, rgb, mask = render_shard(the_network, view_el_az, sun_el_az, time_frac, out_img_size, W2C, W2L_H, device, rank,
+                                     world_size, include_exact_solar)
+    if world_size > 1:
+        rgb = gather_rows(rgb, H * W, rank, world_size)
+        mask = gather_rows(mask, H * W, rank, world_size)
+    return rgb.reshape(H, W, 3).cpu().numpy(), mask.reshape(H, W).cpu().numpy()

@@ -70,3 +70,25 @@ def test_fused_is_deterministic(params0):
         b = fused.run(net, pts, sun, pts.shape[0])
     for x, y in zip(a[1:], b[1:]):
         assert t.equal(x, y)
+
+
+def test_ray_sharded_render_equals_unsharded(params0):
+    """rays shard with no data-path exchange; shards rendered independently (here: both 'ranks' on one GPU) and
+    concatenated must reproduce the single-device image of main_run_Season_NeRF.py:90-92."""
+    import season_nerf_b200 as snb
+    from oracle import season_oracle as so
+    net = make_net(params0, "bf16")
+    size = (12, 10, 96)
+    dev = t.device("cuda")
+    D = snb.component_render_by_dir(net, [80, 0], [45, 135], 184 / 365, size, so.OMA_W2C, so.oma_w2l_h(), dev,
+                                    include_exact_solar=True)
+    imgs = snb.get_imgs_from_Img_Dict(D, size, False)
+    ref = imgs["Season_Adj_Img"] * imgs["Shadow_Adjust_Exact"]
+    full, mask = snb.render_image_sharded(net, [80, 0], [45, 135], 184 / 365, size, so.OMA_W2C, so.oma_w2l_h(), dev,
+                                          include_exact_solar=True)
+    assert maxabs(full, ref) < 1e-6 and maxabs(mask, imgs["Shadow_Mask_Exact"]) < 1e-6
+    parts = [snb.render_shard(net, [80, 0], [45, 135], 184 / 365, size, so.OMA_W2C, so.oma_w2l_h(), dev, r, 3,
+                              include_exact_solar=True) for r in range(3)]
+    assert parts[0][0] == 0 and parts[-1][1] == 120 and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+    cat = t.cat([p[2] for p in parts], 0).reshape(12, 10, 3).cpu().numpy()
+    assert maxabs(cat, ref) < 1e-6
