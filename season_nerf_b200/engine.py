@@ -248,14 +248,42 @@ class All_in_One_Eval():
         args = self.args
         Loss = {}
         weight = {"Color": 1.0, "Solar_Correction": args.sc_lambda, "Alpha_Adjust": 1.}
-        out = self.eval(data_dict, Network, current_step, train_mode, jitter=jitter, ts=ts)
+        from . import network as _nw
+        overlap = (_nw.OVERLAP and args.Use_Solar and train_mode and not self.use_prior and n_rays >= 64
+                   and hasattr(Network, "stage_weights") and getattr(Network, "precision", None) == "bf16")
+        if overlap:
+            # The image pass and the solar pass are independent until the losses: they run on two streams, so the
+            # tensor-bound GEMMs of one overlap the HBM-bound activation passes of the other.  The solar pass is enqueued
+            # second (BatchNorm running statistics keep the reference's update order through per-module events) but only
+            # waits for the point where the weights were staged.
+            Network.stage_weights()
+            Network._bn_order = {}
+            main = t.cuda.current_stream()
+            fork = t.cuda.Event()
+            fork.record(main)
+        try:
+            out = self.eval(data_dict, Network, current_step, train_mode, jitter=jitter, ts=ts)
+            if args.Use_Solar:
+                if solar is None:
+                    starts, ends, svec, stime, _ = self.solar_creation_tool(n_rays, include_times=True)
+                else:
+                    starts, ends, svec, stime = solar
+                sdict = {"Top": starts, "Bot": ends, "Sun_Angle": svec, "Time_Encoded": stime}
+                if overlap:
+                    side = _nw.side_stream(("solar", main.cuda_stream))
+                    side.wait_event(fork)
+                    with t.cuda.stream(side):
+                        sol = self.eval_Rho_Only(sdict, Network, train_mode, current_step, jitter=solar_jitter, ts=solar_ts)
+                    main.wait_stream(side)
+                    for v in sol.values():
+                        if isinstance(v, t.Tensor):
+                            v.record_stream(main)
+                else:
+                    sol = self.eval_Rho_Only(sdict, Network, train_mode, current_step, jitter=solar_jitter, ts=solar_ts)
+        finally:
+            if overlap:
+                Network._bn_order = None
         if args.Use_Solar:
-            if solar is None:
-                starts, ends, svec, stime, _ = self.solar_creation_tool(n_rays, include_times=True)
-            else:
-                starts, ends, svec, stime = solar
-            sol = self.eval_Rho_Only({"Top": starts, "Bot": ends, "Sun_Angle": svec, "Time_Encoded": stime}, Network,
-                                     train_mode, current_step, jitter=solar_jitter, ts=solar_ts)
             err = t.mean(t.sum((sol["Solar_Vis"] - sol["PV_Exact"].detach()) ** 2, 1))
             Loss["Solar_Correction"] = [err, weight["Solar_Correction"]]
             absorb = t.mean(1 - t.sum(sol["PE"].detach() * sol["PV_Exact"].detach() * sol["Solar_Vis"], 1))

@@ -23,6 +23,20 @@ OMEGA_0 = 30.0
 # reductions in the input-gradient GEMM).  SNB_FUSE_EPILOGUES=0 keeps the stand-alone element-wise kernels (A/B tests).
 import os as _os
 FUSE_EPILOGUES = _os.environ.get("SNB_FUSE_EPILOGUES", "1") != "0"
+# Optional: independent work on parallel CUDA streams (weight-gradient GEMMs next to the input-gradient chain; the solar
+# pass next to the image pass, see engine.get_loss).  Measured on B200 (scripts/overlap_probe.py, bench.py): a trunk GEMM
+# and an activation pass that share the SMs finish in 290 us instead of 303 us back to back - both stream 403 MB matrices
+# and the step is HBM-bound - and the whole step gains 0.6 %.  Off by default (SNB_OVERLAP=1 enables).
+OVERLAP = _os.environ.get("SNB_OVERLAP", "0") == "1"
+_side_streams = {}
+
+
+def side_stream(key):
+    """one lazily created side stream per (purpose, parent stream)"""
+    st = _side_streams.get(key)
+    if st is None:
+        st = _side_streams[key] = t.cuda.Stream()
+    return st
 
 
 def _r8(x):
@@ -222,6 +236,14 @@ class T_NeRF(nn.Module):
         if time is not None and time.shape[0] == 1 and N > 1:
             time = time.expand(N, time.shape[1])
         return _run(self, mode, pts, sun, time, S)
+
+    def stage_weights(self, modes=("full", "solar")):
+        """bf16 copies of every weight the given passes use, staged on the current stream (before passes fork onto
+        parallel streams, so that all of them find the cache filled)."""
+        for mode in modes:
+            run = _Pass(self, mode, self.precision)
+            for sp in run.specs:
+                run._wc(sp)
 
     def _fused_ready(self):
         from . import fused
@@ -520,7 +542,20 @@ class _Pass:
         if training:
             s, ss = stats if stats is not None else ops.col_stats(Z)
             with t.no_grad():
-                return ops.bn_finalize(s, ss, rows, bn)      # one launch: batch statistics, running update, folded affine
+                # two passes of one step may run on parallel streams: the running statistics of a module are updated in
+                # program order (image pass, then solar pass - misc.py:169-170 is not commutative in the momentum update)
+                order = getattr(self.net, "_bn_order", None)
+                if order is not None:
+                    cur = t.cuda.current_stream()
+                    ev = order.get(id(bn))
+                    if ev is not None:
+                        cur.wait_event(ev)
+                res = ops.bn_finalize(s, ss, rows, bn)       # one launch: batch statistics, running update, folded affine
+                if order is not None:
+                    ev = t.cuda.Event()
+                    ev.record(cur)
+                    order[id(bn)] = ev
+                return res
         else:
             mean = bn.running_mean.detach().float()
             invstd = 1.0 / t.sqrt(bn.running_var.detach().float() + bn.eps)
@@ -552,6 +587,10 @@ class _Pass:
         dw_total = sum(s_.n_out * s_.kp for s_ in self.specs if s_.grad and s_.name in self.saved)
         dw_flat = t.zeros(dw_total, device=dev, dtype=t.float32)      # ONE fill for all split-K weight-gradient targets
         dw_off = 0
+        cur = t.cuda.current_stream()
+        wstream = side_stream(("wgrad", cur.cuda_stream)) if (OVERLAP and self.M >= 4096) else None
+        if wstream is not None:
+            wstream.wait_stream(cur)
         fused_bwd = {}      # sine layer name -> (sum g, sum g*xhat) left by the consumer's fused input-gradient GEMM
         producers = {(s_.out, s_.out_col0): s_ for s_ in self.specs if s_.kind == "sine"}
         n_readers = {}
@@ -623,7 +662,15 @@ class _Pass:
             # weight gradient dW[n_out, kp] = alpha * dZ^T . X   (split-K, fp32 atomics into zeros)
             dW = dw_flat[dw_off:dw_off + n_out * sp.kp].view(n_out, sp.kp)
             dw_off += n_out * sp.kp
-            ops.gemm(dZv, Xv, dW, alpha=alpha, accumulate=2, a_t=True, b_t=True)
+            if wstream is not None:
+                # the weight gradient only feeds the optimiser: it runs beside the input-gradient chain of the next layers
+                ev = t.cuda.Event()
+                ev.record(cur)
+                wstream.wait_event(ev)
+                with t.cuda.stream(wstream):
+                    ops.gemm(dZv, Xv, dW, alpha=alpha, accumulate=2, a_t=True, b_t=True)
+            else:
+                ops.gemm(dZv, Xv, dW, alpha=alpha, accumulate=2, a_t=True, b_t=True)
             r0 = 0
             for lin in sp.lin:
                 r1 = r0 + lin.out_features
@@ -649,6 +696,8 @@ class _Pass:
                         fused_bwd[pr.name] = st
                 if st is None:
                     ops.gemm(dZv, Wc[:, :kin], G[:, sp.in_col0:sp.in_col0 + kin], alpha=alpha, accumulate=0 if first else 1, b_t=True)
+        if wstream is not None:
+            cur.wait_stream(wstream)
         self.gbuf = gbuf
         return grads
 
