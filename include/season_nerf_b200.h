@@ -75,6 +75,17 @@ int snb_cli_composite(const void* rho, const void* deltas, const void* base, con
 int snb_year_sweep(const void* rho, const void* deltas, const void* base, const void* adj, const double* cls,
                    const double* shade, int in_dtype, int N, int S, int C, int T, double* out, void* stream);
 
+/* ---- camera rays ("next" row of the scope table): P_img_Pinhole.invert_P, pre_NeRF/P_Img.py:133-147 -------------
+ * For n pixels - explicit (rows[i], cols[i]) int32 device arrays, or the raster grid (i / W * ds, i % W * ds) when both
+ * are null - the closed-form inversion of the 3x4 affine-approximated RPC projection P (HOST pointer, 12 doubles,
+ * row-major, already normalised/scaled) at heights z_top and z_bot, in float64 in numpy's evaluation order:
+ *   tops[i] = (x(z_top), y(z_top), z_top), bots[i] = (x(z_bot), y(z_bot), z_bot)     float32 (the reference's .float())
+ *   xy64[i] = (x_top, y_top, x_bot, y_bot) float64 (optional), good[i] = all four inside bounds = (x_min, x_max, y_min,
+ *   y_max) inclusive (HOST pointer; optional) - the filters of mg_Pt_holder.py:180-187 and mg_Img_Eval.py:83-84. */
+int snb_camera_rays(const double* P, const int* rows, const int* cols, long long n, int W, int ds, double z_top,
+                    double z_bot, const double* bounds, float* tops, float* bots, double* xy64, unsigned char* good,
+                    void* stream);
+
 /* ---- positional encoding: misc.py:105-139 PE_Encode (extended) ------------------------------
  * out[m, col0 + ...] = [x (D), per dim: cos(k_j x) j<n, sin(k_j x) j<n], k_j = 2^j * fl32(pi/2);
  * width D*(2n+1), zero padded up to pad_to columns.  x: [M,D] float32, ldx elements. out dtype f32/bf16. */

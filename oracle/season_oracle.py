@@ -633,6 +633,45 @@ def get_imgs_from_img_dict_t_step(D, size, class_vecs):
 OMA_W2C = np.array([41.2905, -95.8967, 315.0])
 
 
+def synthetic_camera_P(seed=7):
+    """A 3x4 projection shaped like the reference's affine-approximated RPC camera after scale_P (pre_NeRF/P_Img.py:168-201):
+    pixel (row, col) of a 2048 x 2048 image from normalised scene coordinates in [-1,1]^3, off-nadir by a few degrees,
+    with a small perspective row (the least-squares fit of compute_Approx_RPC, P_Img.py:331-371, is not exactly affine)."""
+    g = np.random.RandomState(seed)
+    P = np.array([[1180.0, 35.0, -140.0, 1023.5],
+                  [-28.0, 1175.0, 95.0, 1023.5],
+                  [0.0, 0.0, 0.0, 1.0]])
+    P[0:2, 0:3] += g.uniform(-5, 5, (2, 3))
+    P[2, 0:3] = g.uniform(-2e-3, 2e-3, 3)
+    return P
+
+
+def invert_P(P, row, col, h=0):
+    """P_img_Pinhole.invert_P, pre_NeRF/P_Img.py:133-147 (float64 numpy, same evaluation order)."""
+    row, col = np.asarray(row), np.asarray(col)
+    A = P[1, 2] * h + P[1, 3] - P[2, 2] * h * col - P[2, 3] * col
+    B = P[0, 2] * h + P[0, 3] - P[2, 2] * h * row - P[2, 3] * row
+    P11mP31x = P[0, 0] - P[2, 0] * row
+    P22mP32y = P[1, 1] - P[2, 1] * col
+    P12mP32x = P[0, 1] - P[2, 1] * row
+    P21mP31y = P[1, 0] - P[2, 0] * col
+    den = P11mP31x * P22mP32y - P12mP32x * P21mP31y
+    x = (P12mP32x * A - P22mP32y * B) / den
+    y = (-P11mP31x * A + P21mP31y * B) / den
+    return x, y, h
+
+
+def camera_rays(P, rows, cols, z_top=1.0, z_bot=-1.0, bounds=(-1.0, 1.0, -1.0, 1.0)):
+    """tops / bots (float64 [n,3]) and the inside-bounds mask of mg_Img_Eval.py:78-84 / mg_Pt_holder.py:176-187."""
+    xt, yt, _ = invert_P(P, rows, cols, z_top)
+    xb, yb, _ = invert_P(P, rows, cols, z_bot)
+    tops = np.stack([xt, yt, np.full_like(xt, z_top)], -1)
+    bots = np.stack([xb, yb, np.full_like(xb, z_bot)], -1)
+    x0, x1, y0, y1 = bounds
+    good = (xt <= x1) & (x0 <= xt) & (yt <= y1) & (y0 <= yt) & (xb <= x1) & (x0 <= xb) & (yb <= y1) & (y0 <= yb)
+    return tops, bots, good
+
+
 def oma_w2l_h():
     """diag scale mapping a ~0.0024 deg x 0.0032 deg x 70 m box to [-1,1]^3 (pre_NeRF/P_Img.py:168-176)."""
     H = np.eye(4)

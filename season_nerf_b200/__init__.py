@@ -13,7 +13,7 @@ Public surface mirrors the reference's Python API for this path (SURVEY.md secti
 from .adaptive_loss import AdaptiveLossFunction
 from .engine import (All_in_One_Eval, create_solor_rays_uniform, get_PV, sample_pt_coarse, sample_ts,
                      zero_invalid_pts)
-from .geometry import LLA_get_vec, encode_time, world_angle_2_local_vec
+from .geometry import LLA_get_vec, encode_time, ray_table_from_P, world_angle_2_local_vec
 from .network import G_NeRF_Net_Classic, PE_Encode, SineLayer, T_NeRF
 from .quick_run import Quick_Run_Net
 from .render import (DeviceImgDict, _internal_render, component_render_by_dir, component_render_by_P,

@@ -19,6 +19,8 @@ SIGNATURES = {
     "snb_launch_count": [],
     "snb_error_string": [_i],
     "snb_sample_rays": [_p, _p, _p, _i, _i, _i, _p, _p, _p],
+    "snb_camera_rays": [C.POINTER(C.c_double), _p, _p, _ll, _i, _i, C.c_double, C.c_double, C.POINTER(C.c_double), _p, _p, _p,
+                        _p, _p],
     "snb_solar_tops": [_p, _ll, C.POINTER(C.c_double), _i, _p, _p],
     "snb_composite_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
     "snb_composite_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],

@@ -71,6 +71,55 @@ __global__ void __launch_bounds__(256) solar_tops_kernel(const float* __restrict
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Rays of an affine-approximated RPC camera on the device: the closed-form 2x2 solve of P_img_Pinhole.invert_P
+// (pre_NeRF/P_Img.py:133-147) for every pixel at z = z_top and z = z_bot, plus the bounds filter of
+// mg_Pt_holder.py:180-187 / mg_Img_Eval.py:83-84.  float64 with explicit round-to-nearest intrinsics in numpy's
+// evaluation order (no FMA contraction), so x, y are bit-identical to the reference's float64 arrays; the float32
+// cast is the reference's `t.tensor(...).float()`.
+struct CamP {
+  double p[12];        // row-major 3x4 projection (already normalised / scaled by the caller)
+  double bounds[4];    // x_min, x_max, y_min, y_max (inclusive)
+};
+
+__device__ __forceinline__ void invert_P_d(const CamP& c, double row, double col, double h, double& x, double& y) {
+  const double* P = c.p;
+  // P[1,2]*h + P[1,3] - P[2,2]*h*col - P[2,3]*col
+  const double A = __dsub_rn(__dsub_rn(__dadd_rn(__dmul_rn(P[6], h), P[7]), __dmul_rn(__dmul_rn(P[10], h), col)),
+                             __dmul_rn(P[11], col));
+  // P[0,2]*h + P[0,3] - P[2,2]*h*row - P[2,3]*row
+  const double B = __dsub_rn(__dsub_rn(__dadd_rn(__dmul_rn(P[2], h), P[3]), __dmul_rn(__dmul_rn(P[10], h), row)),
+                             __dmul_rn(P[11], row));
+  const double P11mP31x = __dsub_rn(P[0], __dmul_rn(P[8], row));
+  const double P22mP32y = __dsub_rn(P[5], __dmul_rn(P[9], col));
+  const double P12mP32x = __dsub_rn(P[1], __dmul_rn(P[9], row));
+  const double P21mP31y = __dsub_rn(P[4], __dmul_rn(P[8], col));
+  const double den = __dsub_rn(__dmul_rn(P11mP31x, P22mP32y), __dmul_rn(P12mP32x, P21mP31y));
+  x = __ddiv_rn(__dsub_rn(__dmul_rn(P12mP32x, A), __dmul_rn(P22mP32y, B)), den);
+  y = __ddiv_rn(__dadd_rn(__dmul_rn(-P11mP31x, A), __dmul_rn(P21mP31y, B)), den);
+}
+
+// pixel i: explicit (rows[i], cols[i]) or the raster grid (i / W * ds, i % W * ds)
+__global__ void __launch_bounds__(256) camera_rays_kernel(CamP cam, const int* __restrict__ rows, const int* __restrict__ cols,
+                                                          long long n, int W, int ds, double z_top, double z_bot,
+                                                          float* __restrict__ tops, float* __restrict__ bots,
+                                                          double* __restrict__ xy64, unsigned char* __restrict__ good) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double row = rows ? (double)rows[i] : (double)((i / W) * ds);
+    const double col = cols ? (double)cols[i] : (double)((i % W) * ds);
+    double tx, ty, bx, by;
+    invert_P_d(cam, row, col, z_top, tx, ty);
+    invert_P_d(cam, row, col, z_bot, bx, by);
+    tops[3 * i] = (float)tx, tops[3 * i + 1] = (float)ty, tops[3 * i + 2] = (float)z_top;
+    bots[3 * i] = (float)bx, bots[3 * i + 1] = (float)by, bots[3 * i + 2] = (float)z_bot;
+    if (xy64) xy64[4 * i] = tx, xy64[4 * i + 1] = ty, xy64[4 * i + 2] = bx, xy64[4 * i + 3] = by;
+    if (good) {
+      const double x0 = cam.bounds[0], x1 = cam.bounds[1], y0 = cam.bounds[2], y1 = cam.bounds[3];
+      good[i] = (tx <= x1) && (x0 <= tx) && (ty <= y1) && (y0 <= ty) && (bx <= x1) && (x0 <= bx) && (by <= y1) && (y0 <= by);
+    }
+  }
+}
+
 }  // namespace snb
 
 extern "C" int snb_sample_rays(const float* top, const float* bot, const float* ts, int N, int S, int zero_oob,
@@ -92,6 +141,22 @@ extern "C" int snb_solar_tops(const float* pts, long long M, const double* sun3_
   int grid = snb::grid_for(M, 256, 16);
   snb::solar_tops_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pts, M, sun3_host[0], sun3_host[1], sun3_host[2],
                                                                   f64, tops);
+  snb::count_launch();
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_camera_rays(const double* P, const int* rows, const int* cols, long long n, int W, int ds, double z_top,
+                               double z_bot, const double* bounds, float* tops, float* bots, double* xy64,
+                               unsigned char* good, void* stream) {
+  SNB_CHECK_ARG(P && tops && bots && n >= 0 && ((rows == nullptr) == (cols == nullptr)) && (rows || (W > 0 && ds > 0)));
+  SNB_CHECK_ARG(!good || bounds);
+  if (n == 0) return SNB_OK;
+  snb::CamP cam;
+  for (int i = 0; i < 12; ++i) cam.p[i] = P[i];           // host pointers: 16 doubles travel as a kernel argument
+  for (int i = 0; i < 4; ++i) cam.bounds[i] = bounds ? bounds[i] : 0.0;
+  snb::camera_rays_kernel<<<snb::grid_for(n, 256, 16), 256, 0, (cudaStream_t)stream>>>(cam, rows, cols, n, W, ds, z_top, z_bot, tops,
+                                                                                      bots, xy64, good);
   snb::count_launch();
   SNB_LAUNCH_CHECK();
   return SNB_OK;

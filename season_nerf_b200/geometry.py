@@ -31,3 +31,19 @@ def encode_time(time_frac_year, time_frac_day=0):
     """Quick_Run.py:9-12."""
     return np.array([np.cos(time_frac_year * 2 * np.pi), np.sin(time_frac_year * 2 * np.pi),
                      np.cos(time_frac_day * 2 * np.pi), np.sin(time_frac_day * 2 * np.pi)])
+
+
+def ray_table_from_P(P, img_shape, downscale, bounds_model, device):
+    """The per-image ray cache of mg_Pt_holder.setup_quick_loader (mg_Pt_holder.py:169-187) built on the device: every
+    (down-scaled) pixel of an image with the affine-approximated RPC camera `P` (P_img_Pinhole.P after scale_P), its ray
+    end points at z = bounds_model[2,1] / [2,0], filtered to the model bounds.
+    -> valid_img_pts [n,2] int64 (down-scaled pixel indices), tops [n,3], bots [n,3] float32 (device tensors)."""
+    import torch as t
+    from . import ops
+    H, W = int(img_shape[0]) // downscale, int(img_shape[1]) // downscale
+    b = np.asarray(bounds_model, dtype=np.float64)
+    tops, bots, good, _ = ops.camera_rays(P, t.device(device), grid=(H, W, downscale), z_top=b[2, 1], z_bot=b[2, 0],
+                                          bounds=(b[0, 0], b[0, 1], b[1, 0], b[1, 1]))
+    keep = good.nonzero().squeeze(1)
+    pts = t.stack([keep // W, keep % W], 1)
+    return pts, tops[keep], bots[keep]

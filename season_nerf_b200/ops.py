@@ -51,6 +51,30 @@ def sample_rays(top, bot, ts, zero_oob=False, want_pts=True):
     return pts, deltas
 
 
+def camera_rays(P, device, rows=None, cols=None, grid=None, z_top=1.0, z_bot=-1.0, bounds=None, want_xy64=False):
+    """P_img_Pinhole.invert_P (pre_NeRF/P_Img.py:133-147) at z_top / z_bot for a pixel list (rows, cols: int arrays) or
+    the raster `grid=(H, W, ds)`; -> tops, bots [n,3] f32, good [n] bool (None without bounds), xy64 [n,4] f64 or None."""
+    import numpy as np
+    Pm = np.ascontiguousarray(np.asarray(P, dtype=np.float64).reshape(12))
+    Pp = (C.c_double * 12)(*Pm.tolist())
+    if rows is not None:
+        r = torch.as_tensor(np.asarray(rows), dtype=torch.int32).to(device).contiguous()
+        c = torch.as_tensor(np.asarray(cols), dtype=torch.int32).to(device).contiguous()
+        n, W, ds = r.shape[0], 0, 0
+    else:
+        H, W, ds = grid
+        r = c = None
+        n = H * W
+    tops = torch.empty(n, 3, device=device, dtype=torch.float32)
+    bots = torch.empty(n, 3, device=device, dtype=torch.float32)
+    good = torch.empty(n, device=device, dtype=torch.uint8) if bounds is not None else None
+    xy64 = torch.empty(n, 4, device=device, dtype=torch.float64) if want_xy64 else None
+    bp = (C.c_double * 4)(*[float(v) for v in np.asarray(bounds, dtype=np.float64).reshape(4)]) if bounds is not None else None
+    check(_lib.load().snb_camera_rays(Pp, _ptr(r), _ptr(c), n, int(W), int(ds), float(z_top), float(z_bot), bp, _ptr(tops),
+                                      _ptr(bots), _ptr(xy64), _ptr(good), _stream()))
+    return tops, bots, (good.bool() if good is not None else None), xy64
+
+
 def solar_tops(pts, sun_vec, f64=True):
     """mg_Img_Eval.py:57-60 (f64) / Eval_Tools_2.py:255-258 (f32).  pts [M,3] -> tops [M,3]."""
     pts = _cuda(pts, torch.float32, "pts").contiguous().reshape(-1, 3)

@@ -130,13 +130,23 @@ def component_render_by_P(the_network, a_P_img, out_img_size: tuple, device, max
         XY = np.stack(np.meshgrid(np.linspace(0, a_P_img.img.shape[0] - 1, out_img_size[0]),
                                   np.linspace(0, a_P_img.img.shape[1] - 1, out_img_size[1]), indexing="ij"), -1)
         XY = np.round(XY).astype(int).reshape([-1, 2])
-        x, y, z = a_P_img.invert_P(XY[:, 0], XY[:, 1], 1.)
-        tops = np.stack([x, y, np.ones_like(x)], -1)
-        x, y, z = a_P_img.invert_P(XY[:, 0], XY[:, 1], -1.)
-        bots = np.stack([x, y, -np.ones_like(x)], -1)
-        good = (tops[:, 0] >= -1) * (tops[:, 1] <= 1) * (bots[:, 0] >= -1) * (bots[:, 1] <= 1) * \
-               (tops[:, 1] >= -1) * (tops[:, 0] <= 1) * (bots[:, 1] >= -1) * (bots[:, 0] <= 1)
-        R = _internal_render(the_network, t.tensor(tops[good]).float(), t.tensor(bots[good]).float(),
+        P = getattr(a_P_img, "P", None)
+        if type(a_P_img).__name__ in ("P_img_Pinhole", "P_img_Parallel") and P is not None and np.asarray(P).shape == (3, 4):
+            # closed-form inversion of the affine-approximated RPC camera on the device (bit-exact with invert_P,
+            # pre_NeRF/P_Img.py:133-147): no per-pixel host arrays, no H2D of the ray endpoints
+            tops_d, bots_d, good_d, _ = ops.camera_rays(P, t.device(device), rows=XY[:, 0], cols=XY[:, 1], bounds=(-1, 1, -1, 1))
+            keep = good_d.nonzero().squeeze(1)
+            tops_t, bots_t = tops_d[keep], bots_d[keep]
+            good = good_d.cpu().numpy()
+        else:
+            x, y, z = a_P_img.invert_P(XY[:, 0], XY[:, 1], 1.)
+            tops = np.stack([x, y, np.ones_like(x)], -1)
+            x, y, z = a_P_img.invert_P(XY[:, 0], XY[:, 1], -1.)
+            bots = np.stack([x, y, -np.ones_like(x)], -1)
+            good = (tops[:, 0] >= -1) * (tops[:, 1] <= 1) * (bots[:, 0] >= -1) * (bots[:, 1] <= 1) * \
+                   (tops[:, 1] >= -1) * (tops[:, 0] <= 1) * (bots[:, 1] >= -1) * (bots[:, 0] <= 1)
+            tops_t, bots_t = t.tensor(tops[good]).float(), t.tensor(bots[good]).float()
+        R = _internal_render(the_network, tops_t, bots_t,
                              a_P_img.sun_el_and_az_vec, a_P_img.get_year_frac(), out_img_size, max_batch_size,
                              include_exact_solar, device)
         R["Image_Points_in_GT_Img"] = XY[good]

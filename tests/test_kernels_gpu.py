@@ -269,3 +269,40 @@ def test_gemm_sine_bwd_epilogue(M, N, K, bn):
     ref = a * (G - k1 - xhat * k2)
     ops.bn_bwd_apply(Gbuf[:, :N], Z, a, mean, invstd, k1, k2, Gbuf[:, :N])
     assert relerr(Gbuf[:, :N], ref) < 6e-3
+
+
+# ---- camera rays on the device ("next" row 1): P_img_Pinhole.invert_P + bounds filter -----------------------------
+def test_camera_rays_bit_exact_vs_reference_golden():
+    from season_nerf_b200 import ops
+    g = load_golden("camera_rays")
+    dev = t.device("cuda")
+    tops, bots, good, xy = ops.camera_rays(g["P"], dev, rows=g["XY"][:, 0], cols=g["XY"][:, 1], bounds=(-1, 1, -1, 1), want_xy64=True)
+    assert np.array_equal(xy.cpu().numpy(), np.concatenate([g["tops64"][:, :2], g["bots64"][:, :2]], 1))     # float64, bit for bit
+    assert np.array_equal(tops.cpu().numpy(), g["tops32"]) and np.array_equal(bots.cpu().numpy(), g["bots32"])
+    assert np.array_equal(good.cpu().numpy(), g["good"])
+    H, W = (g["img_shape"] // g["DS"]).tolist()
+    tg, bg, gg, xyg = ops.camera_rays(g["P"], dev, grid=(H, W, int(g["DS"])), bounds=(-1, 1, -1, 1), want_xy64=True)
+    assert np.array_equal(xyg.cpu().numpy(), g["grid_xy64"]) and np.array_equal(gg.cpu().numpy(), g["grid_good"])
+
+
+def test_camera_rays_full_size_properties():
+    """2048 x 2048 raster (4.2 M rays): re-projecting the generated endpoints through P returns the pixel (apply_P,
+    pre_NeRF/P_Img.py:149-166) and the ray count equals the oracle's on a strided subset."""
+    from oracle import season_oracle as so
+    from season_nerf_b200 import ops
+    P = so.synthetic_camera_P(seed=3)
+    P = P / P[-1, -1]
+    dev = t.device("cuda")
+    H = W = 2048
+    tops, bots, good, xy = ops.camera_rays(P, dev, grid=(H, W, 1), bounds=(-1, 1, -1, 1), want_xy64=True)
+    assert tops.shape == (H * W, 3) and float(tops[:, 2].min()) == 1.0 and float(bots[:, 2].max()) == -1.0
+    Pd = t.tensor(P, device=dev)
+    for k, z in ((0, 1.0), (2, -1.0)):
+        X = t.stack([xy[:, k], xy[:, k + 1], t.full_like(xy[:, 0], z), t.ones_like(xy[:, 0])], 1)
+        uvw = X @ Pd.T
+        rc = uvw[:, :2] / uvw[:, 2:3]
+        idx = t.arange(H * W, device=dev)
+        assert float((rc[:, 0] - (idx // W)).abs().max()) < 1e-6 and float((rc[:, 1] - (idx % W)).abs().max()) < 1e-6
+    sub = np.arange(0, H * W, 997)
+    _, _, gs = so.camera_rays(P, sub // W, sub % W)
+    assert np.array_equal(good.cpu().numpy()[sub], gs)

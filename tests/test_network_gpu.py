@@ -207,3 +207,38 @@ def test_quick_run_and_engine_exact_solar_golden(params0, precision):
         R = _tool().eval_exact_solar(_data(g), net, -1, False)
     assert maxabs(R["Solar_Vis"], g["ex_Solar_Vis"]) < tol["out"]
     assert maxabs(R["Rendered_Col"], g["ex_Rendered_Col"]) < tol["out"]
+
+
+def test_component_render_by_P_device_rays_equal_host_rays(params0):
+    """component_render_by_P (mg_Img_Eval.py:74-94): the on-device camera-ray path (objects of the reference's
+    P_img_Pinhole class) and the host path (any other object with invert_P) give identical rays, masks and components."""
+    import season_nerf_b200 as snb
+    from oracle import season_oracle as so
+
+    class _Cam:
+        def __init__(self):
+            P = so.synthetic_camera_P(seed=7)
+            self.P = P / P[-1, -1]
+            self.img = np.zeros((2048, 2048, 3), dtype=np.uint8)
+            self.sun_el_and_az_vec = so.world_angle_2_local_vec(45, 135, so.OMA_W2C, so.oma_w2l_h())
+
+        def invert_P(self, row, col, h=0):
+            return so.invert_P(self.P, row, col, h)
+
+        def get_year_frac(self):
+            return 0.5
+
+    P_img_Pinhole = type("P_img_Pinhole", (_Cam,), {})
+    net = make_net(params0, "bf16")
+    size = (9, 8, 24)
+    Dd = snb.component_render_by_P(net, P_img_Pinhole(), size, t.device("cuda"), include_exact_solar=False)
+    Dh = snb.component_render_by_P(net, _Cam(), size, t.device("cuda"), include_exact_solar=False)
+    assert np.array_equal(Dd["Image_Points"], Dh["Image_Points"]) and np.array_equal(Dd["Image_Points_in_GT_Img"], Dh["Image_Points_in_GT_Img"])
+    assert Dd["World_Points"].shape[0] < size[0] * size[1]          # some rays fall outside the cube and are dropped
+    for k in ("World_Points", "Deltas", "Rho", "Base_Col", "Adjust_col"):
+        assert np.array_equal(Dd[k], Dh[k]), k
+    pts, tops, bots = snb.ray_table_from_P(P_img_Pinhole().P, (2048, 2048), 64, np.array([[-1., 1.]] * 3), "cuda")
+    r, c = pts[:, 0].cpu().numpy() * 64, pts[:, 1].cpu().numpy() * 64
+    to, bo, go = so.camera_rays(P_img_Pinhole().P, np.repeat(np.arange(32), 32) * 64, np.tile(np.arange(32), 32) * 64)
+    assert pts.shape[0] == int(go.sum()) and np.array_equal(tops.cpu().numpy(), to[go].astype(np.float32))
+    assert np.array_equal(bots.cpu().numpy(), bo[go].astype(np.float32))

@@ -187,3 +187,18 @@ def test_geometry():
     g = load_golden("geometry")
     for a, v in zip(g["ang"], g["vecs"]):
         np.testing.assert_allclose(so.world_angle_2_local_vec(a[0], a[1], g["W2C"], g["W2L_H"]), v, rtol=1e-12)
+
+
+def test_camera_rays_oracle_matches_reference_bit_exact():
+    """invert_P restatement (oracle) == unmodified P_img_Pinhole.invert_P + the bounds filters (float64, bit-exact)."""
+    from oracle import season_oracle as so
+    g = load_golden("camera_rays")
+    tops, bots, good = so.camera_rays(g["P"], g["XY"][:, 0], g["XY"][:, 1])
+    assert np.array_equal(tops, g["tops64"]) and np.array_equal(bots, g["bots64"]) and np.array_equal(good, g["good"])
+    H, W = (g["img_shape"] // g["DS"]).tolist()
+    ds = int(g["DS"])
+    r = np.repeat(np.arange(H), W) * ds
+    c = np.tile(np.arange(W), H) * ds
+    tg, bg, gg = so.camera_rays(g["P"], r, c)
+    assert np.array_equal(np.stack([tg[:, 0], tg[:, 1], bg[:, 0], bg[:, 1]], -1), g["grid_xy64"])
+    assert np.array_equal(gg, g["grid_good"])
