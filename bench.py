@@ -202,7 +202,8 @@ def run_ours(a):
     H[0, 3], H[1, 3], H[2, 3] = -W2C[0] * H[0, 0], -W2C[1] * H[1, 1], -W2C[2] * H[2, 2]
 
     t.manual_seed(0)
-    ts = snb.TrainStep(args, dev, H, W2C, world_size=world, precision=a.precision, use_graph=not a.no_graph)
+    ts = snb.TrainStep(args, dev, H, W2C, world_size=world, precision=a.precision, use_graph=not a.no_graph,
+                       micro_batch=a.micro_batch)
     if world > 1:                                     # identical initial weights on every rank
         for p_ in ts.params + ts.ada_params:
             dist.broadcast(p_.data, 0)
@@ -356,8 +357,8 @@ def run_ours(a):
            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "bf16" if a.precision == "bf16" else "f32", "data": "synthetic",
            "config": {"workload": "train step, %d synthetic OMA_281-shaped rays + %d solar rays per GPU, S=96, Barron + solar "
-                                  "losses, Adam+OneCycle (BASELINE.json configs[1])" % (n, n),
-                      "rays_per_gpu": n, "samples_per_ray": S, "weights": "random-init T_NeRF(512,4)",
+                                  "losses, Adam+OneCycle (BASELINE.json configs[%d])" % (n, n, 3 if n >= 65536 else 1),
+                      "rays_per_gpu": n, "micro_batch": a.micro_batch, "samples_per_ray": S, "weights": "random-init T_NeRF(512,4)",
                       "launch": "eager" if a.no_graph else "whole step captured once in a CUDA graph, replayed per step",
                       "l2": "per-step working set (~10 GB of activations) far exceeds the 126 MB L2; no explicit flush"},
            "clocks": clocks, "gpu_launches": int(launches),
@@ -443,6 +444,9 @@ def main():
     ap.add_argument("--no-render", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the compositing / shadow-march / year-sweep measurements")
+    ap.add_argument("--micro-batch", type=int, default=None, dest="micro_batch",
+                    help="rays per micro-batch (gradient accumulation; each chunk is its own BatchNorm batch) - needed for "
+                         "--rays 65536 (BASELINE.json configs[3]): one 65536-ray BatchNorm batch would need ~225 GB of activations")
     ap.add_argument("--no-graph", action="store_true", help="eager kernel launches instead of the captured CUDA graph")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else max(a.warmup, 1)

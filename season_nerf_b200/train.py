@@ -55,7 +55,7 @@ class TrainStep:
     DSM-guided section (use_prior True, learning_mode 1 with jump_start)."""
 
     def __init__(self, args, device, H, WC, network=None, training_DSM=None, use_prior=False, total_steps=None,
-                 world_size=1, precision="bf16", use_graph=False, graph_warmup=2):
+                 world_size=1, precision="bf16", use_graph=False, graph_warmup=2, micro_batch=None):
         """use_graph: after `graph_warmup` eager steps at a given batch size, the whole step (sampling, network forward,
         losses, backward and - single GPU - both Adam updates) is captured once into a CUDA graph and replayed; inputs live
         in static device buffers refreshed before each replay.  The arithmetic and kernel sequence are those of the eager
@@ -65,6 +65,7 @@ class TrainStep:
         self.world_size = world_size
         self.use_graph = bool(use_graph) and not use_prior and self.device.type == "cuda"
         self.graph_warmup = graph_warmup
+        self.micro_batch = micro_batch
         self._graphs = {}
         self._eager_calls = {}
         self.launches_replayed = 0     # kernels of this library launched through graph replays (not seen by snb_launch_count)
@@ -106,7 +107,7 @@ class TrainStep:
         grads = [p.grad for p in self.params + self.ada_params if p.grad is not None]
         self._flat = flat_allreduce_mean_(grads, self.world_size, self._flat)
 
-    # ---- CUDA-graph step -----------------------------------------------------------------------------------
+    # ---- one step -----------------------------------------------------------------------------------------
     _BATCH_KEYS = ("Top", "Bot", "Sun_Angle", "Time_Encoded", "GT_Color")
 
     def _draw_inputs(self, n, inject):
@@ -120,32 +121,40 @@ class TrainStep:
         ts_sol = sample_ts(S, False, True, inject.get("solar_jitter")) if self.args.Use_Solar else None
         return ts_img, solar, ts_sol
 
-    def _capture(self, data_dict, current_step, n):
+    def _chunks(self, n):
+        """micro-batches of one step: [(lo, hi)] - equal sizes (the captured graph has one shape)"""
+        mb = self.micro_batch if (self.micro_batch and self.micro_batch < n) else n
+        if n % mb:
+            raise ValueError("batch of %d rays is not a multiple of micro_batch=%d" % (n, mb))
+        return [(lo, lo + mb) for lo in range(0, n, mb)]
+
+    def _static(self, data_dict, mb):
         dev = self.device
         f32 = dict(device=dev, dtype=t.float32)
         S = self.args.n_samples
-        st = {"batch": {k: t.empty(tuple(data_dict[k].shape), **f32) for k in self._BATCH_KEYS},
+        st = {"batch": {k: t.empty((mb,) + tuple(data_dict[k].shape[1:]), **f32) for k in self._BATCH_KEYS},
               "ts_img": t.empty(S, **f32), "ts_sol": t.empty(S, **f32),
-              "solar": tuple(t.empty(n, w, **f32) for w in (3, 3, 3, 4)) if self.args.Use_Solar else None}
-        self._graphs[n] = st
+              "solar": tuple(t.empty(mb, w, **f32) for w in (3, 3, 3, 4)) if self.args.Use_Solar else None}
         return st
 
-    def _fill_static(self, st, data_dict, ts_img, solar, ts_sol):
+    def _fill_static(self, st, data_dict, ts_img, solar, ts_sol, lo, hi):
         for k in self._BATCH_KEYS:
-            st["batch"][k].copy_(data_dict[k], non_blocking=True)
+            st["batch"][k].copy_(data_dict[k][lo:hi], non_blocking=True)
         st["ts_img"].copy_(ts_img, non_blocking=True)
         if st["solar"] is not None:
             st["ts_sol"].copy_(ts_sol, non_blocking=True)
             for d, s_ in zip(st["solar"], solar):
-                d.copy_(s_, non_blocking=True)
+                d.copy_(s_[lo:hi], non_blocking=True)
 
-    def _fwd_bwd(self, st, current_step):
-        loss = self.eval_tool.get_loss(st["batch"], self.network, current_step, train_mode=True, solar=st["solar"],
-                                       ts=st["ts_img"], solar_ts=st["ts_sol"])
+    def _fwd_bwd(self, batch, current_step, scale, **kw):
+        """loss of one (micro-)batch and its backward; gradients accumulate into .grad (scale = 1 / number of chunks)"""
+        loss = self.eval_tool.get_loss(batch, self.network, current_step, train_mode=True, **kw)
         total = 0
         for k in loss.keys():
             total = total + loss[k][0] * loss[k][1]
-        total.backward()
+        (total * scale if scale != 1.0 else total).backward()
+        # the step has consumed the autograd graph: hand back plain values (a caller that kept graph-attached losses alive
+        # would also keep this iteration's AccumulateGrad nodes alive, which breaks a later CUDA-graph capture)
         return {k: [v[0].detach() if isinstance(v[0], t.Tensor) else v[0], v[1]] for k, v in loss.items()}, total.detach()
 
     def _optim_step(self):
@@ -153,71 +162,107 @@ class TrainStep:
         if self.optim2 is not None:
             self.optim2.step()
 
+    def _zero_grads(self, to_none):
+        self.optim.zero_grad(set_to_none=to_none)
+        if self.optim2 is not None:
+            self.optim2.zero_grad(set_to_none=to_none)
+
+    @staticmethod
+    def _merge(losses, totals):
+        k = len(losses)
+        if k == 1:
+            return losses[0], totals[0]
+        out = {}
+        for name in losses[0]:
+            v0 = losses[0][name][0]
+            out[name] = [sum(l[name][0] for l in losses) / k if isinstance(v0, t.Tensor) else v0, losses[0][name][1]]
+        return out, sum(totals) / k
+
     def _step_graphed(self, data_dict, current_step, inject):
         n = data_dict["Top"].shape[0]
+        chunks = self._chunks(n)
+        k = len(chunks)
+        mb = chunks[0][1] - chunks[0][0]
         ts_img, solar, ts_sol = self._draw_inputs(n, inject)
-        st = self._graphs.get(n)
+        st = self._graphs.get((n, mb))
         if st is None:
-            st = self._capture(data_dict, current_step, n)
-        self._fill_static(st, data_dict, ts_img, solar, ts_sol)
+            st = self._graphs[(n, mb)] = self._static(data_dict, mb)
+        fused_opt = self.world_size == 1 and k == 1        # the optimiser updates ride in the same graph
+        if k > 1 and self.graph_warmup < 1:
+            raise ValueError("micro-batched graph capture needs graph_warmup >= 1 (the eager step creates the .grad tensors)")
         if "g_fb" not in st:
-            # record: fwd + bwd (+ the optimiser updates when there is no all-reduce in between)
-            self.optim.zero_grad(set_to_none=True)
-            if self.optim2 is not None:
-                self.optim2.zero_grad(set_to_none=True)
+            # record: fwd + bwd of one (micro-)batch.  One chunk: gradients are (re)created by the graph itself.  Several
+            # chunks: the graph accumulates into the existing .grad tensors, zeroed before the first chunk of every step.
+            self._fill_static(st, data_dict, ts_img, solar, ts_sol, *chunks[0])
+            self._zero_grads(to_none=(k == 1))
             t.cuda.synchronize()
             from . import _lib
             l0 = _lib.launch_count()
             g_fb = t.cuda.CUDAGraph()
             with t.cuda.graph(g_fb):
-                st["loss"], st["total"] = self._fwd_bwd(st, current_step)
-                if self.world_size == 1:
+                st["loss"], st["total"] = self._fwd_bwd(st["batch"], current_step, 1.0 / k, solar=st["solar"],
+                                                        ts=st["ts_img"], solar_ts=st["ts_sol"])
+                if fused_opt:
                     self._optim_step()
             st["g_fb"] = g_fb
             st["launches"] = _lib.launch_count() - l0
-            if self.world_size > 1:
+            if not fused_opt:
                 g_opt = t.cuda.CUDAGraph()
                 with t.cuda.graph(g_opt, pool=g_fb.pool()):
                     self._optim_step()
                 st["g_opt"] = g_opt
-        st["g_fb"].replay()
-        self.launches_replayed += st["launches"]
+        if k > 1:
+            self._zero_grads(to_none=False)
+        losses, totals = [], []
+        for lo, hi in chunks:
+            self._fill_static(st, data_dict, ts_img, solar, ts_sol, lo, hi)
+            st["g_fb"].replay()
+            self.launches_replayed += st["launches"]
+            if k > 1:
+                losses.append({kk: [v[0].clone() if isinstance(v[0], t.Tensor) else v[0], v[1]] for kk, v in st["loss"].items()})
+                totals.append(st["total"].clone())
         # a replay rewrites parameters and BatchNorm buffers behind autograd's back: bump their version counters so that
         # every derived cache (packed render program, staged bf16 weights) sees the change
         t.autograd.graph.increment_version(self._versioned)
         if self.world_size > 1:
             self._allreduce_grads()
+        if not fused_opt:
             st["g_opt"].replay()
         self.sched.step()
         if self.sched2 is not None:
             self.sched2.step()
-        self.last_loss = st["total"]
-        return st["loss"]
+        loss, self.last_loss = (st["loss"], st["total"]) if k == 1 else self._merge(losses, totals)
+        return loss
 
     def step(self, data_dict, current_step, **inject):
-        """mg_run_NeRF.py:288-326 without the per-term TensorBoard .item() syncs; returns the loss dict."""
+        """mg_run_NeRF.py:288-326 without the per-term TensorBoard .item() syncs; returns the loss dict.
+        With `micro_batch`, the batch is processed in equal chunks whose gradients accumulate before ONE optimiser step
+        (each chunk is its own BatchNorm batch and its own Albedo_Color minimum; one jitter vector per step)."""
+        n = data_dict["Top"].shape[0]
         if self.use_graph:
-            n = data_dict["Top"].shape[0]
             if self._eager_calls.get(n, 0) >= self.graph_warmup:
                 return self._step_graphed(data_dict, current_step, inject)
             self._eager_calls[n] = self._eager_calls.get(n, 0) + 1
-        self.optim.zero_grad(set_to_none=True)
-        if self.optim2 is not None:
-            self.optim2.zero_grad(set_to_none=True)
-        loss = self.eval_tool.get_loss(data_dict, self.network, current_step, train_mode=True, **inject)
-        total = 0
-        for k in loss.keys():
-            total = total + loss[k][0] * loss[k][1]
-        total.backward()
+        chunks = self._chunks(n)
+        self._zero_grads(to_none=True)
+        if len(chunks) == 1:
+            loss, total = self._fwd_bwd(data_dict, current_step, 1.0, **inject)
+        else:
+            ts_img, solar, ts_sol = self._draw_inputs(n, inject)
+            dev = self.device
+            ts_img, ts_sol = ts_img.to(dev), (ts_sol.to(dev) if ts_sol is not None else None)
+            losses, totals = [], []
+            for lo, hi in chunks:
+                l, tt = self._fwd_bwd({kk: data_dict[kk][lo:hi] for kk in self._BATCH_KEYS}, current_step, 1.0 / len(chunks),
+                                      solar=None if solar is None else tuple(x[lo:hi] for x in solar), ts=ts_img, solar_ts=ts_sol)
+                losses.append(l)
+                totals.append(tt)
+            loss, total = self._merge(losses, totals)
         if self.world_size > 1:
             self._allreduce_grads()
-        self.optim.step()
-        if self.optim2 is not None:
-            self.optim2.step()
+        self._optim_step()
         self.sched.step()
         if self.sched2 is not None:
             self.sched2.step()
-        self.last_loss = total.detach()
-        # the step has consumed the autograd graph: hand back plain values (a caller that kept graph-attached losses alive
-        # would also keep this iteration's AccumulateGrad nodes alive, which breaks a later CUDA-graph capture)
-        return {k: [v[0].detach() if isinstance(v[0], t.Tensor) else v[0], v[1]] for k, v in loss.items()}
+        self.last_loss = total
+        return loss

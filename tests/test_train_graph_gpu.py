@@ -19,12 +19,12 @@ def _args():
                                  lr_alpha_scale=1000.0, max_train_steps=1000)
 
 
-def _run(use_graph, n_steps, n=192):
+def _run(use_graph, n_steps, n=192, micro_batch=None):
     import season_nerf_b200 as snb
     from oracle import season_oracle as so
     dev = t.device("cuda")
     t.manual_seed(0)
-    ts = snb.TrainStep(_args(), dev, so.oma_w2l_h(), so.OMA_W2C, use_graph=use_graph, graph_warmup=1)
+    ts = snb.TrainStep(_args(), dev, so.oma_w2l_h(), so.OMA_W2C, use_graph=use_graph, graph_warmup=1, micro_batch=micro_batch)
     batch = so.synthetic_batch(n, seed=1, n_images=5)
     losses = []
     for i in range(n_steps):
@@ -39,10 +39,13 @@ def _run(use_graph, n_steps, n=192):
     return losses, sd, lr, ts
 
 
-def test_graph_step_matches_eager():
+@pytest.mark.parametrize("micro_batch", [None, 64])
+def test_graph_step_matches_eager(micro_batch):
+    """micro_batch=64: 192 rays as 3 chunks whose gradients accumulate before one optimiser step (eager loop vs the
+    accumulate-in-place graph replayed 3 times)."""
     n_steps = 5
-    le, sde, lre, _ = _run(False, n_steps)
-    lg, sdg, lrg, tsg = _run(True, n_steps)
+    le, sde, lre, _ = _run(False, n_steps, micro_batch=micro_batch)
+    lg, sdg, lrg, tsg = _run(True, n_steps, micro_batch=micro_batch)
     assert tsg._graphs and tsg.launches_replayed > 0, "the graph path did not run"
     assert abs(lre - lrg) < 1e-12 * max(1.0, abs(lre)) + 1e-9
     for a, b in zip(le, lg):
