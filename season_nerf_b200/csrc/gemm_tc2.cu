@@ -276,7 +276,24 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
           for (int r = 0; r < 32; ++r) z[r] = (r < rows_valid && n0 + c + 2 * lane < p.N) ? __ldg(zp + r * ldw) : 0u;
         }
       };
-      if (kEpi == 2) load_z(c_begin, zc);
+      if (kEpi == 2) {
+        load_z(c_begin, zc);
+        // pull the Z lines of this warp's chunks of the NEXT work item into L2 now (one 128-byte line per lane and
+        // chunk): by the time the register loads above are issued for that item they no longer pay the HBM latency,
+        // which one chunk of lookahead cannot hide when the epilogue is the critical path
+        const int tn_ = t + num_pairs;
+        if (tn_ < total_items) {
+          int tm2, tn2, ks2;
+          decode(tn_, tm2, tn2, ks2);
+          const long long r2 = (long long)tm2 * (2 * k2BM) + (long long)rank * k2BM + q * 32 + lane;
+          if (r2 < p.M) {
+            for (int c = c_begin; c < c_end && tn2 * p.block_n + c < p.N; c += 64) {
+              const __nv_bfloat16* zl = p.X + r2 * p.ldx + tn2 * p.block_n + c;
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(zl));
+            }
+          }
+        }
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * k2MaxBN;

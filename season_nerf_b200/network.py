@@ -713,6 +713,10 @@ class _NetFn(t.autograd.Function):
     @staticmethod
     def forward(ctx, run, X, sun, time, S, n_params, *params):
         outs = run.forward(X, sun, time, S, keep=True)
+        # outputs that receive no gradient (e.g. the solar-visibility head of the image pass: vis is detached in the
+        # colour formula, Eval_Tools_2.py:214) must arrive as None, not as materialised zeros - otherwise their whole
+        # branch would be back-propagated with zero gradients
+        ctx.set_materialize_grads(False)
         ctx.run = run
         ctx.params = params
         ctx.x_cols = X.shape[1] if run.x_requires_grad else 0

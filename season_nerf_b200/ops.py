@@ -117,6 +117,7 @@ class _Composite(torch.autograd.Function):
         rho, deltas, col, vis, sky = [_cuda(x, torch.float32).contiguous() for x in (rho, deltas, col, vis, sky)]
         PV, PE, PS, albedo, rendered, vsum = composite_fwd(rho, deltas, col, vis, sky, classic)
         ctx.save_for_backward(rho, deltas, col, vis, sky)
+        ctx.set_materialize_grads(False)       # unused outputs (PV / PE / PS when only the colour is in the loss) stay None
         ctx.classic = classic
         ctx.mark_non_differentiable(vsum)
         return PV, PE, PS, albedo, rendered, vsum
