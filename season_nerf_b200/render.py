@@ -257,11 +257,20 @@ def render_shard(the_network, view_el_az, sun_el_az, time_frac, out_img_size, W2
     exactly as main_run_Season_NeRF.py:90-92 forms the output image; with `class_vecs` [T,C]: rgb is the [T,hi-lo,3] year
     sweep of get_imgs_from_Img_Dict_t_step.  No communication: rays are independent."""
     from .train import shard_range
-    tops, bots = view_rays(view_el_az, out_img_size, W2C, W2L_H)
-    lo, hi = shard_range(tops.shape[0], rank, world_size)
+    H, W = out_img_size[0], out_img_size[1]
+    lo, hi = shard_range(H * W, rank, world_size)
     sun_vec = world_angle_2_local_vec(sun_el_az[0], sun_el_az[1], W2C, W2L_H)
     with t.no_grad():
-        D = _internal_render(the_network, tops[lo:hi], bots[lo:hi], sun_vec, time_frac, out_img_size, 150000,
+        # this rank's rows of the pixel grid of mg_Img_Eval.py:98-106, built on the device in float64 from the two 1-D
+        # numpy linspaces (same additions as the reference's float64 meshgrid + offset, then .float(): bit-identical)
+        view_vec = world_angle_2_local_vec(view_el_az[0], view_el_az[1], W2C, W2L_H)
+        off = t.tensor(view_vec / view_vec[2], dtype=t.float64, device=device)
+        lin_h = t.tensor(np.linspace(1, -1, H), dtype=t.float64, device=device)
+        lin_w = t.tensor(np.linspace(-1, 1, W), dtype=t.float64, device=device)
+        idx = t.arange(lo, hi, device=device)
+        xyz = t.stack([lin_h[idx // W], lin_w[idx % W], t.zeros(hi - lo, dtype=t.float64, device=device)], 1)
+        tops, bots = (xyz + off).float(), (xyz - off).float()
+        D = _internal_render(the_network, tops, bots, sun_vec, time_frac, out_img_size, 150000,
                              include_exact_solar, device)
         keys = ["Rho", "Deltas", "Base_Col", "Est_Solar_Vis", "Adjust_col", "Output_class", "Sky_Col"]
         rho, dl, base, vis, adj, ocl, skyc = [D.dev[k] for k in keys]
