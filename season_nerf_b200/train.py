@@ -102,6 +102,31 @@ class TrainStep:
         self.last_loss = None
         self._versioned = [v for v in self.network.state_dict(keep_vars=True).values()] + list(ada_params)
 
+    # ---- checkpoint / resume (the reference saves only network.state_dict(), mg_run_NeRF.py:225: no resume path) --------
+    def state_dict(self):
+        """everything a resumed run needs: network (the reference's 94 keys), both optimisers, both schedulers and the
+        adaptive-loss parameters"""
+        ada = self.eval_tool.ada_loss
+        ada = [] if ada is None else (list(ada) if isinstance(ada, (list, tuple)) else [ada])
+        return {"network": self.network.state_dict(), "optim": self.optim.state_dict(),
+                "optim2": None if self.optim2 is None else self.optim2.state_dict(),
+                "sched": self.sched.state_dict(), "sched2": None if self.sched2 is None else self.sched2.state_dict(),
+                "ada_loss": [a.state_dict() for a in ada]}
+
+    def load_state_dict(self, sd):
+        self.network.load_state_dict(sd["network"])
+        self.optim.load_state_dict(sd["optim"])
+        self.sched.load_state_dict(sd["sched"])
+        if self.optim2 is not None and sd.get("optim2") is not None:
+            self.optim2.load_state_dict(sd["optim2"])
+            self.sched2.load_state_dict(sd["sched2"])
+        ada = self.eval_tool.ada_loss
+        ada = [] if ada is None else (list(ada) if isinstance(ada, (list, tuple)) else [ada])
+        for a, s_ in zip(ada, sd.get("ada_loss", [])):
+            a.load_state_dict(s_)
+        self._graphs.clear()            # captured graphs baked the old optimiser state tensors
+        self._eager_calls.clear()
+
     def _allreduce_grads(self):
         """one flat fp32 bucket (3.19 M network gradients + the adaptive-loss scalars), NCCL sum -> mean"""
         grads = [p.grad for p in self.params + self.ada_params if p.grad is not None]

@@ -81,3 +81,28 @@ def test_compat_install_redirects_reference_imports():
         if k.startswith(("T_NeRF_Full_2", "T_NeRF_Eval_Utils", "all_NeRF")) or k == "misc":
             if getattr(sys.modules[k], "__season_nerf_b200__", False) or not hasattr(sys.modules[k], "__file__"):
                 del sys.modules[k]
+
+
+def test_ray_table_epochs_cover_every_ray_once():
+    """device-resident replacement of the DataLoader (mg_run_NeRF.py:229-264): shuffled, every ray once per epoch, the
+    reference's column layout (mg_run_NeRF.py:122-133).  Runs on CPU tensors here."""
+    from season_nerf_b200.data import RayTable, data_to_dict
+    n = 1000
+    table = t.arange(n * 22, dtype=t.float32).reshape(n, 22)
+    rt = RayTable(table, 96, "cpu", seed=3)
+    assert len(rt) == 11
+    seen, eofs = [], []
+    for _ in range(2 * len(rt)):
+        d, eof = rt.next_batch()
+        seen.append(d["Img_Pt"][:, 0] / 22)
+        eofs.append(eof)
+        assert d["Top"].shape[1] == 3 and d["Time_Encoded"].shape[1] == 4 and d["GT_Color"].shape[1] == 3
+        assert t.equal(d["Bot"][:, 0], d["Img_Pt"][:, 0] + 5)
+    first, second = t.cat(seen[:11]), t.cat(seen[11:])
+    assert first.numel() == n and t.equal(first.sort().values, t.arange(n, dtype=t.float32))
+    assert t.equal(second.sort().values, t.arange(n, dtype=t.float32)) and not t.equal(first, second)
+    assert eofs.index(True) == 11 and sum(eofs) == 1
+    dd = data_to_dict(table[:4])
+    assert set(dd) == {"Img_Pt", "Top", "Bot", "View_Angle", "Sun_Angle", "Time_Encoded", "Sample_Weight", "GT_Color"}
+    sh = [RayTable.shard(table, r, 3) for r in range(3)]
+    assert sum(len(x) for x in sh) == n and t.equal(t.cat(sh), table)

@@ -78,3 +78,40 @@ def test_graph_step_accepts_host_batches_and_changes_inputs():
         vals.append(float(ts.last_loss))
     assert all(np.isfinite(v) for v in vals)
     assert abs(vals[2] - vals[3]) > 1e-6
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_checkpoint_resume_continues_the_same_trajectory(use_graph):
+    """TrainStep.state_dict(): network + both Adam optimisers + both OneCycle schedulers + adaptive-loss parameters; a run
+    resumed from it produces the losses of the uninterrupted run."""
+    import season_nerf_b200 as snb
+    from oracle import season_oracle as so
+    dev = t.device("cuda")
+    batch = so.synthetic_batch(128, seed=1, n_images=5)
+
+    def draws(i):
+        rs, g = np.random.RandomState(50 + i), t.Generator().manual_seed(50 + i)
+        st, en, vec, tm, _ = so.create_solar_rays_uniform(128, so.OMA_W2C, so.oma_w2l_h(), rs, g)
+        jit = t.rand(S, generator=g)
+        return dict(jitter=jit, solar=(st, en, vec, tm), solar_jitter=jit)
+
+    t.manual_seed(0)
+    a = snb.TrainStep(_args(), dev, so.oma_w2l_h(), so.OMA_W2C, use_graph=use_graph, graph_warmup=1)
+    for i in range(3):
+        a.step(batch, i, **draws(i))
+    ck = {k: (v if not isinstance(v, dict) else v) for k, v in a.state_dict().items()}
+    import copy
+    ck = copy.deepcopy(ck)
+    ref = []
+    for i in range(3, 6):
+        a.step(batch, i, **draws(i))
+        ref.append(float(a.last_loss))
+    t.manual_seed(123)                       # different initial weights: everything must come from the checkpoint
+    b = snb.TrainStep(_args(), dev, so.oma_w2l_h(), so.OMA_W2C, use_graph=use_graph, graph_warmup=1)
+    b.load_state_dict(ck)
+    got = []
+    for i in range(3, 6):
+        b.step(batch, i, **draws(i))
+        got.append(float(b.last_loss))
+    for x, y in zip(ref, got):
+        assert abs(x - y) <= 2e-3 * max(abs(x), 1e-3), (ref, got)
