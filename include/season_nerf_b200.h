@@ -129,10 +129,11 @@ int snb_gemm_sine_bwd(const void* dZn, int lda, const void* W, int ldw, void* G,
                       const float* a, const float* c, const float* mean, const float* invstd, float alpha,
                       long long M, int N, int K, float* stats, void* stream);
 
-/* dZ = a[n]*(G - k1[n] - (Z-mean[n])*invstd[n]*k2[n])   (train-mode BatchNorm backward after snb_gemm_sine_bwd; dZ may alias G) */
+/* dZ = a[n]*(G - scale*k1[n] - (Z-mean[n])*invstd[n]*scale*k2[n])   (train-mode BatchNorm backward after snb_gemm_sine_bwd;
+ * k1, k2 = the column sums it left, scale = 1/M; scale 0 = eval-mode BatchNorm; dZ may alias G) */
 int snb_bn_bwd_apply(const void* G, int ldg, const void* Z, int ldz, const float* a, const float* mean,
-                     const float* invstd, const float* k1, const float* k2, void* dZ, int ldo, long long M, int N,
-                     int dtype, void* stream);
+                     const float* invstd, const float* k1, const float* k2, float scale, void* dZ, int ldo, long long M,
+                     int N, int dtype, void* stream);
 
 /* Train-mode nn.BatchNorm1d(momentum, eps) bookkeeping of one SineLayer in one launch (misc.py:169-170,189): from the
  * column sums (float32 or float64, stats_dtype) of the M = rows pre-activations: batch mean / biased variance, the

@@ -349,7 +349,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_vec_kernel(const T* G, int ldg, const T* __restrict__ Z, int ldz, const float* __restrict__ a,
                         const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ k1,
-                        const float* __restrict__ k2, T* dZ, int ldo, long long M, int N) {
+                        const float* __restrict__ k2, float scale, T* dZ, int ldo, long long M, int N) {
   const int col = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
   if (col >= N) return;
   float av[8], mv[8], iv[8], k1v[8], k2v[8];
@@ -359,7 +359,7 @@ bn_bwd_apply_vec_kernel(const T* G, int ldg, const T* __restrict__ Z, int ldz, c
   load8f(k1 + col, k1v);
   load8f(k2 + col, k2v);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) k2v[i] *= iv[i];
+  for (int i = 0; i < 8; ++i) k1v[i] *= scale, k2v[i] *= iv[i] * scale;
   for (long long r = blockIdx.x * (long long)blockDim.y + threadIdx.y; r < M; r += (long long)gridDim.x * blockDim.y) {
     float z[8], g[8];
     Vec8<T>::load(Z + r * ldz + col, z);
@@ -610,15 +610,15 @@ extern "C" int snb_sine_bwd_apply(const void* dY, int ldd, const void* Z, int ld
 }
 
 extern "C" int snb_bn_bwd_apply(const void* G, int ldg, const void* Z, int ldz, const float* a, const float* mean,
-                                const float* invstd, const float* k1, const float* k2, void* dZ, int ldo, long long M, int N,
-                                int dtype, void* stream) {
+                                const float* invstd, const float* k1, const float* k2, float scale, void* dZ, int ldo,
+                                long long M, int N, int dtype, void* stream) {
   SNB_CHECK_ARG(G && Z && a && mean && invstd && k1 && k2 && dZ && M >= 0 && N > 0);
   if (M == 0) return SNB_OK;
   cudaStream_t st = (cudaStream_t)stream;
   VecLaunch v = vec_launch(M, N, ldg, ldz, ldo, G, Z, dZ, 0, 8);
   if (!v.ok) return SNB_ERR_UNSUPPORTED;
-  if (dtype == SNB_F32) bn_bwd_apply_vec_kernel<float><<<v.grid, v.block, 0, st>>>((const float*)G, ldg, (const float*)Z, ldz, a, mean, invstd, k1, k2, (float*)dZ, ldo, M, N);
-  else if (dtype == SNB_BF16) bn_bwd_apply_vec_kernel<bf16><<<v.grid, v.block, 0, st>>>((const bf16*)G, ldg, (const bf16*)Z, ldz, a, mean, invstd, k1, k2, (bf16*)dZ, ldo, M, N);
+  if (dtype == SNB_F32) bn_bwd_apply_vec_kernel<float><<<v.grid, v.block, 0, st>>>((const float*)G, ldg, (const float*)Z, ldz, a, mean, invstd, k1, k2, scale, (float*)dZ, ldo, M, N);
+  else if (dtype == SNB_BF16) bn_bwd_apply_vec_kernel<bf16><<<v.grid, v.block, 0, st>>>((const bf16*)G, ldg, (const bf16*)Z, ldz, a, mean, invstd, k1, k2, scale, (bf16*)dZ, ldo, M, N);
   else return SNB_ERR_ARG;
   count_launch();
   SNB_LAUNCH_CHECK();

@@ -29,6 +29,19 @@ FUSE_EPILOGUES = _os.environ.get("SNB_FUSE_EPILOGUES", "1") != "0"
 # and the step is HBM-bound - and the whole step gains 0.6 %.  Off by default (SNB_OVERLAP=1 enables).
 OVERLAP = _os.environ.get("SNB_OVERLAP", "0") == "1"
 _side_streams = {}
+_consts = {}
+
+
+def const_vec(n, value, device):
+    """cached read-only float32 [n] vector of `value` (identity affine of layers without BatchNorm, zero offsets): created
+    once per (n, value, device) instead of a fill launch per layer and pass"""
+    key = (int(n), float(value), str(device))
+    v = _consts.get(key)
+    if v is None:
+        v = t.full((int(n),), float(value), device=device, dtype=t.float32)
+        if not t.cuda.is_current_stream_capturing():      # a vector born inside a graph capture is only filled by replays
+            _consts[key] = v
+    return v
 
 
 def side_stream(key):
@@ -440,6 +453,18 @@ class _Pass:
             self.bufs[name] = mk(rows, width, device=self.dev, dtype=dtype or self.dt)
         return self.bufs[name]
 
+    def _stats_slot(self, n):
+        """[2, n] float32 zeros carved from one zero-filled pool per sweep (forward / backward): the fused GEMM epilogues
+        accumulate their column sums into it"""
+        pool = self.__dict__.get("_spool")
+        if pool is None or self._spool_off + 2 * n > pool.numel():
+            total = sum(2 * s_.n_out for s_ in self.specs if s_.kind == "sine")
+            pool = self._spool = t.zeros(max(total, 2 * n), device=self.dev, dtype=t.float32)
+            self._spool_off = 0
+        out = pool[self._spool_off:self._spool_off + 2 * n].view(2, n)
+        self._spool_off += 2 * n
+        return out
+
     def _width(self, name):
         lw = getattr(self.net, "layer_width", None)
         if name == "cat5":
@@ -503,7 +528,7 @@ class _Pass:
             Z = t.empty(rows, n_out, device=dev, dtype=self.dt)
             st = None
             if training and sp.layer.has_bn:          # batch statistics fused into the GEMM epilogue (CTA-pair kernel)
-                st = ops.gemm_stats(Xv, Wc, Z, bias=b, alpha=OMEGA_0)
+                st = ops.gemm_stats(Xv, Wc, Z, bias=b, alpha=OMEGA_0, stats=self._stats_slot(n_out))
             if sp.out in ("cat5", "cats1"):
                 Y = self.bufs[sp.out][:, sp.out_col0:sp.out_col0 + n_out]
             else:
@@ -537,7 +562,7 @@ class _Pass:
         dev = Z.device
         n = Z.shape[1]
         if not layer.has_bn:
-            return t.ones(n, device=dev), t.zeros(n, device=dev), None, None
+            return const_vec(n, 1.0, dev), const_vec(n, 0.0, dev), None, None
         bn = layer.norm
         if training:
             s, ss = stats if stats is not None else ops.col_stats(Z)
@@ -591,6 +616,7 @@ class _Pass:
         wstream = side_stream(("wgrad", cur.cuda_stream)) if (OVERLAP and self.M >= 4096) else None
         if wstream is not None:
             wstream.wait_stream(cur)
+        self._spool = None      # fresh statistics pool for the backward sweep
         fused_bwd = {}      # sine layer name -> (sum g, sum g*xhat) left by the consumer's fused input-gradient GEMM
         producers = {(s_.out, s_.out_col0): s_ for s_ in self.specs if s_.kind == "sine"}
         n_readers = {}
@@ -630,9 +656,7 @@ class _Pass:
                     if sp.layer.has_bn:
                         self._acc(grads, sp.layer.norm.weight, sgx)
                         self._acc(grads, sp.layer.norm.bias, sg)
-                        zero = t.zeros_like(sg)
-                        ops.bn_bwd_apply(dY, Z, a, mean, invstd, (sg / rows) if bn_train else zero,
-                                         (sgx / rows) if bn_train else zero, dZ)
+                        ops.bn_bwd_apply(dY, Z, a, mean, invstd, sg, sgx, dZ, scale=(1.0 / rows) if bn_train else 0.0)
                     else:
                         fused_db = sg
                 elif bn_train:
@@ -690,8 +714,9 @@ class _Pass:
                     # sole consumer of a sine layer's output: its cos / BatchNorm-backward column sums ride in this epilogue
                     _, Zp, ap, cp, meanp, invstdp = self.saved[pr.name]
                     if meanp is None:
-                        meanp, invstdp = t.zeros_like(ap), t.ones_like(ap)
-                    st = ops.gemm_sine_bwd(dZv, Wc[:, :kin], G[:, sp.in_col0:sp.in_col0 + kin], Zp, ap, cp, meanp, invstdp, alpha=alpha)
+                        meanp, invstdp = const_vec(ap.shape[0], 0.0, dev), const_vec(ap.shape[0], 1.0, dev)
+                    st = ops.gemm_sine_bwd(dZv, Wc[:, :kin], G[:, sp.in_col0:sp.in_col0 + kin], Zp, ap, cp, meanp, invstdp, alpha=alpha,
+                                           stats=self._stats_slot(kin))
                     if st is not None:
                         fused_bwd[pr.name] = st
                 if st is None:

@@ -207,7 +207,7 @@ def gemm(A, B, out, bias=None, alpha=1.0, accumulate=0, a_t=False, b_t=False):
     return out
 
 
-def gemm_stats(A, B, out, bias=None, alpha=1.0):
+def gemm_stats(A, B, out, bias=None, alpha=1.0, stats=None):
     """out[M,N] (bf16) = alpha*(A.B^T + bias) with the column sum / sum of squares of the stored values fused into the
     GEMM epilogue.  -> (sum[N], sumsq[N]) float32, or None when the CTA-pair kernel does not take the shape (the
     caller then runs gemm + col_stats)."""
@@ -222,7 +222,7 @@ def gemm_stats(A, B, out, bias=None, alpha=1.0):
         raise ValueError("gemm_stats shape mismatch: A%s B%s out%s" % (tuple(A.shape), tuple(B.shape), tuple(out.shape)))
     if bias is not None:
         _cuda(bias, torch.float32, "bias")
-    s = torch.zeros(2, N, device=out.device, dtype=torch.float32)
+    s = stats if stats is not None else torch.zeros(2, N, device=out.device, dtype=torch.float32)
     rc = _lib.load().snb_gemm_stats(_ptr(A), lda, _ptr(B), ldb, _ptr(out), ldc, _ptr(bias), float(alpha), M, N, K, _ptr(s), _stream())
     if rc == -2:
         return None
@@ -253,7 +253,7 @@ def gemm_sine_fwd(A, B, Z, Y, bias=None, alpha=1.0):
     return True
 
 
-def gemm_sine_bwd(dZn, W, G, Z, a, c, mean, invstd, alpha=1.0):
+def gemm_sine_bwd(dZn, W, G, Z, a, c, mean, invstd, alpha=1.0, stats=None):
     """G = alpha*(dZn . W) * cos(a*Z + c) with the column sums (sum G, sum G*xhat) fused into the epilogue of the
     input-gradient GEMM.  dZn [M,K]; W [K,N] (the next layer's weight, rows = its outputs); G, Z [M,N] bf16.
     -> (sum_g [N], sum_g_xhat [N]) float32, or None when the CTA-pair kernel does not take the shape."""
@@ -269,7 +269,7 @@ def gemm_sine_bwd(dZn, W, G, Z, a, c, mean, invstd, alpha=1.0):
         raise ValueError("gemm_sine_bwd shape mismatch: dZn%s W%s G%s Z%s" % (tuple(dZn.shape), tuple(W.shape), tuple(G.shape), tuple(Z.shape)))
     for v in (a, c, mean, invstd):
         _cuda(v, torch.float32, "column vector")
-    s = torch.zeros(2, N, device=G.device, dtype=torch.float32)
+    s = stats if stats is not None else torch.zeros(2, N, device=G.device, dtype=torch.float32)
     rc = _lib.load().snb_gemm_sine_bwd(_ptr(dZn), lda, _ptr(W), ldw, _ptr(G), ldg, _ptr(Z), ldz, _ptr(a), _ptr(c), _ptr(mean),
                                        _ptr(invstd), float(alpha), M, N, K, _ptr(s), _stream())
     if rc == -2:
@@ -278,13 +278,13 @@ def gemm_sine_bwd(dZn, W, G, Z, a, c, mean, invstd, alpha=1.0):
     return s[0], s[1]
 
 
-def bn_bwd_apply(G, Z, a, mean, invstd, k1, k2, dZ):
-    """dZ = a*(G - k1 - xhat*k2) (may alias G)."""
+def bn_bwd_apply(G, Z, a, mean, invstd, k1, k2, dZ, scale=1.0):
+    """dZ = a*(G - scale*k1 - xhat*scale*k2) (may alias G); scale = 1/rows when k1, k2 are the raw column sums."""
     G, ldg = _mat(G, "G")
     Z, ldz = _mat(Z, "Z")
     dZ, ldo = _mat(dZ, "dZ")
     check(_lib.load().snb_bn_bwd_apply(_ptr(G), ldg, _ptr(Z), ldz, _ptr(a), _ptr(mean), _ptr(invstd), _ptr(k1), _ptr(k2),
-                                       _ptr(dZ), ldo, Z.shape[0], Z.shape[1], _DT[Z.dtype], _stream()))
+                                       float(scale), _ptr(dZ), ldo, Z.shape[0], Z.shape[1], _DT[Z.dtype], _stream()))
     return dZ
 
 

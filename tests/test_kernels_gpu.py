@@ -267,7 +267,7 @@ def test_gemm_sine_bwd_epilogue(M, N, K, bn):
     # second half of the train-mode BatchNorm backward, in place
     k1, k2 = (st[0] / M).contiguous(), (st[1] / M).contiguous()
     ref = a * (G - k1 - xhat * k2)
-    ops.bn_bwd_apply(Gbuf[:, :N], Z, a, mean, invstd, k1, k2, Gbuf[:, :N])
+    ops.bn_bwd_apply(Gbuf[:, :N], Z, a, mean, invstd, st[0], st[1], Gbuf[:, :N], scale=1.0 / M)
     assert relerr(Gbuf[:, :N], ref) < 6e-3
 
 
