@@ -633,6 +633,31 @@ def get_imgs_from_img_dict_t_step(D, size, class_vecs):
 OMA_W2C = np.array([41.2905, -95.8967, 315.0])
 
 
+def gen_results(p, img_shape, n_samples):
+    """T_NeRF_Eval_Utils/Eval_funcs.py:268-296 (dense sigma / colour volume and its vertical compositing, float64 numpy)."""
+    H, W, S = img_shape[0], img_shape[1], n_samples
+    XYZ = np.stack(np.meshgrid(np.arange(0, H), np.arange(0, W), np.arange(S), indexing="ij"), -1).reshape([-1, 3])
+    s = np.array([1 / H, 1 / W, 1 / S])
+    xyz = XYZ * s * 2 - 1
+    xyz[:, 2] *= -1
+    X = t.tensor(xyz).float()
+    with t.no_grad():
+        Rho = forward_sigma_only(p, X, training=False)
+        Col = forward_color_only(p, X, training=False)
+    all_Rhos = Rho.double().numpy().reshape(H, W, S, 1)
+    all_Cols = Col.double().numpy().reshape(H, W, S, 3)
+    delta = 2 / S
+    P_E = 1 - np.exp(-all_Rhos * delta)[:, :, :, 0]
+    P_Vis = np.exp(-np.cumsum(np.concatenate([np.zeros([H, W, 1, 1]), all_Rhos * delta], 2), 2)[:, :, 0:-1])[:, :, :, 0]
+    return all_Rhos, P_E, P_Vis, P_E * P_Vis, all_Cols
+
+
+def height_map(p, shape, n_samples):
+    """Eval_funcs.py:298-313: expected surface height in the normalised cube."""
+    _, _, _, P_Surf, _ = gen_results(p, shape, n_samples)
+    return np.sum(P_Surf * np.linspace(1, -1, n_samples).reshape([1, 1, -1]), 2) / np.sum(P_Surf, 2)
+
+
 def synthetic_camera_P(seed=7):
     """A 3x4 projection shaped like the reference's affine-approximated RPC camera after scale_P (pre_NeRF/P_Img.py:168-201):
     pixel (row, col) of a 2048 x 2048 image from normalised scene coordinates in [-1,1]^3, off-nadir by a few degrees,

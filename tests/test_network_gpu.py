@@ -242,3 +242,22 @@ def test_component_render_by_P_device_rays_equal_host_rays(params0):
     to, bo, go = so.camera_rays(P_img_Pinhole().P, np.repeat(np.arange(32), 32) * 64, np.tile(np.arange(32), 32) * 64)
     assert pts.shape[0] == int(go.sum()) and np.array_equal(tops.cpu().numpy(), to[go].astype(np.float32))
     assert np.array_equal(bots.cpu().numpy(), bo[go].astype(np.float32))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_gen_results_and_height_map(params0, precision):
+    """"next" row 4: dense volume consumers (Eval_funcs.py:268-313) against the unmodified reference's arrays."""
+    import season_nerf_b200 as snb
+    g = load_golden("gen_results")
+    shape, S = tuple(int(v) for v in g["shape"]), int(g["S"])
+    net = make_net(params0, precision)
+    rho, pe, pv, ps, col = snb.gen_results(net, shape, S, t.device("cuda"), 1000)
+    tol = TOL[precision]
+    assert rho.dtype == np.float64 and rho.shape == g["rho"].shape and col.shape == g["col"].shape
+    assert maxabs(rho, g["rho"]) < tol["rho"] and maxabs(col, g["col"]) < tol["out"]
+    for a, k in ((pe, "P_E"), (pv, "P_Vis"), (ps, "P_Surf")):
+        assert maxabs(a, g[k]) < tol["out"], k
+    hm = snb.height_map(net, shape, S, t.device("cuda"))
+    assert maxabs(hm, g["height"]) < (5e-2 if precision == "bf16" else 1e-3)
+    hm_m = snb.height_map(net, shape, S, t.device("cuda"), h_range=(280.0, 350.0))
+    assert maxabs(hm_m, (hm + 1) / 2 * 70.0 + 280.0) < 1e-9

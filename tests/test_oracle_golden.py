@@ -202,3 +202,14 @@ def test_camera_rays_oracle_matches_reference_bit_exact():
     tg, bg, gg = so.camera_rays(g["P"], r, c)
     assert np.array_equal(np.stack([tg[:, 0], tg[:, 1], bg[:, 0], bg[:, 1]], -1), g["grid_xy64"])
     assert np.array_equal(gg, g["grid_good"])
+
+
+def test_gen_results_oracle_matches_reference(params0):
+    """dense sigma / colour volume (Eval_funcs.py:268-296): oracle restatement vs the unmodified reference."""
+    from oracle import season_oracle as so
+    g = load_golden("gen_results")
+    shape, S = tuple(int(v) for v in g["shape"]), int(g["S"])
+    rho, pe, pv, ps, col = so.gen_results(params0, shape, S)
+    for a, k in ((rho, "rho"), (pe, "P_E"), (pv, "P_Vis"), (ps, "P_Surf"), (col, "col")):
+        assert a.shape == g[k].shape and np.abs(a - g[k]).max() <= 2e-5 * max(1.0, np.abs(g[k]).max()), k
+    assert np.abs(so.height_map(params0, shape, S) - g["height"]).max() < 1e-4
