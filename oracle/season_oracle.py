@@ -633,6 +633,33 @@ def get_imgs_from_img_dict_t_step(D, size, class_vecs):
 OMA_W2C = np.array([41.2905, -95.8967, 315.0])
 
 
+def seasonal_align_v3(p, D, target_img, t0):
+    """T_NeRF_Eval_Utils/mg_Img_Eval.py:354-414 (_grad_descent_v3): 367 candidate times, closed-form sky colour, MSE."""
+    ts = t.tensor([t0] + list(np.linspace(0, 1, 366))).float()
+    ts_scaled = t.stack([t.cos(ts * 2 * np.pi), t.sin(ts * 2 * np.pi), t.cos(ts * 2 * np.pi), t.sin(ts * 2 * np.pi)], 1)
+    with t.no_grad():
+        tv = time_classes(p, ts_scaled)
+        ip = np.asarray(D["Image_Points_in_GT_Img"])
+        GT = t.tensor(np.asarray(target_img)[ip[:, 0], ip[:, 1]]).float()
+        rho, dl = np.asarray(D["Rho"], dtype=np.float64), np.asarray(D["Deltas"], dtype=np.float64)
+        PS = get_PV(t.tensor(rho), t.tensor(dl)).numpy() * (1 - np.exp(-rho * dl))
+        PS = t.tensor(PS).float()
+        Base, Adj = t.tensor(np.asarray(D["Base_Col"])).float(), t.tensor(np.asarray(D["Adjust_col"])).float()
+        SV = t.sigmoid((t.sum(PS * t.tensor(np.asarray(D["Est_Solar_Vis"])).float(), 1) - .2) * 30)
+        good = (SV < .99)[:, 0]
+        scores, skies = np.ones(ts.shape[0]), np.zeros([ts.shape[0], 3])
+        for i in range(ts.shape[0]):
+            A = t.sum(PS * t.sigmoid(Base + t.sum(Adj * tv[i].reshape([1, 1, -1, 1]), 2)), 1)
+            Y = GT[good] - A[good] * SV[good]
+            X = (1 - SV[good]) * A[good]
+            sky = t.clamp((1 / t.sum(X * X, 0)) * t.sum(X * Y, 0), 0, 1)
+            R = A * (SV + (1 - SV) * sky)
+            scores[i] = float(t.mean((R - GT) ** 2))
+            skies[i] = sky.numpy()
+        best = int(np.argmin(scores))
+    return tv[best], t.tensor(skies[best]).reshape([1, 1, 3]).float(), ts[best].item(), scores
+
+
 def gen_results(p, img_shape, n_samples):
     """T_NeRF_Eval_Utils/Eval_funcs.py:268-296 (dense sigma / colour volume and its vertical compositing, float64 numpy)."""
     H, W, S = img_shape[0], img_shape[1], n_samples

@@ -11,6 +11,7 @@ Public surface mirrors the reference's Python API for this path (SURVEY.md secti
 `season_nerf_b200.compat.install()` registers these under the reference's module names.
 """
 from .adaptive_loss import AdaptiveLossFunction
+from .align import Grad_Descent_Seasonal_Align_v3
 from .data import RayTable, data_to_dict
 from .engine import (All_in_One_Eval, create_solor_rays_uniform, get_PV, sample_pt_coarse, sample_ts,
                      zero_invalid_pts)

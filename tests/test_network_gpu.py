@@ -261,3 +261,17 @@ def test_gen_results_and_height_map(params0, precision):
     assert maxabs(hm, g["height"]) < (5e-2 if precision == "bf16" else 1e-3)
     hm_m = snb.height_map(net, shape, S, t.device("cuda"), h_range=(280.0, 350.0))
     assert maxabs(hm_m, (hm + 1) / 2 * 70.0 + 280.0) < 1e-9
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_seasonal_alignment_search(params0, precision):
+    """"next" row 3: Grad_Descent_Seasonal_Align_v3 (mg_Img_Eval.py:349-414) on the reference's cached components - one
+    fused sweep over the 367 candidate times - returns the reference's time of year, class vector and sky colour."""
+    import season_nerf_b200 as snb
+    from test_oracle_golden import _align_inputs
+    g, P, D = _align_inputs(params0)
+    net = make_net(P, precision)
+    adj, sky, best_t = snb.Grad_Descent_Seasonal_Align_v3(D, g["target"], float(g["t0"]), net, t.device("cuda"))
+    assert abs(best_t - float(g["best_t"])) < (1e-7 if precision == "fp32" else 2.5 / 365)      # bf16 class vectors: +-2 days
+    tol = 1e-4 if precision == "fp32" else 3e-2
+    assert tuple(sky.shape) == (1, 1, 3) and maxabs(sky, g["sky"]) < tol and maxabs(adj, g["adj_vec"]) < tol

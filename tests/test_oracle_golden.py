@@ -213,3 +213,21 @@ def test_gen_results_oracle_matches_reference(params0):
     for a, k in ((rho, "rho"), (pe, "P_E"), (pv, "P_Vis"), (ps, "P_Surf"), (col, "col")):
         assert a.shape == g[k].shape and np.abs(a - g[k]).max() <= 2e-5 * max(1.0, np.abs(g[k]).max()), k
     assert np.abs(so.height_map(params0, shape, S) - g["height"]).max() < 1e-4
+
+
+def _align_inputs(params0):
+    g = load_golden("season_align")
+    P = {k: v.clone() for k, v in params0.items()}
+    P["get_class_layer.weight"] = P["get_class_layer.weight"] * float(g["class_scale"])
+    D = {k[2:]: g[k] for k in g if k.startswith("D_")}
+    return g, P, D
+
+
+def test_seasonal_align_oracle_matches_reference(params0):
+    """_grad_descent_v3 (mg_Img_Eval.py:354-414): the restatement finds the reference's time, class vector and sky colour."""
+    from oracle import season_oracle as so
+    g, P, D = _align_inputs(params0)
+    adj, sky, best_t, scores = so.seasonal_align_v3(P, D, g["target"], float(g["t0"]))
+    assert abs(best_t - float(g["best_t"])) < 1e-7 and abs(best_t - float(g["t_star"])) < 1e-6
+    assert np.abs(adj.numpy() - g["adj_vec"]).max() < 1e-5 and np.abs(sky.numpy() - g["sky"]).max() < 1e-4
+    assert scores.min() < 1e-3 * np.median(scores)                  # the target's own time is a sharp minimum
