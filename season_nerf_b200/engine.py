@@ -143,7 +143,7 @@ class All_in_One_Eval():
              "Adjust": Adj, "Rho": Rho, "Col": Col, "Col_Adj": -1, "deltas": deltas, "sample_pts": Xs,
              "Albedo_Color": Albedo}
         if self.use_prior:
-            trust = current_step / self.n_steps
+            trust = self._trust(current_step)
             with t.no_grad():
                 Rho_S = Network.Supervised_Sample(Xs.reshape(-1, 3), deltas.reshape(-1, 1)).reshape(N, S, 1)
             PV_S, PE_S, PS_S, _, Rend_S = self._shade(Rho_S, deltas, Col, Vis, Sky_ray)
@@ -184,17 +184,25 @@ class All_in_One_Eval():
         Vis = Network.Sigmoid(vis_raw).reshape(N, S, 1)
         Sky = sky_raw.repeat_interleave(S, 0).reshape(N, S, -1)     # RAW sky (T_NeRF_net_v2.py:157)
         if self.use_prior:
-            trust = current_step / self.n_steps
+            trust = self._trust(current_step)
             with t.no_grad():
+                # Eval_Tools_2.py:319-334: the prior-DSM density replaces rho only at points inside the cube.  Shape-static
+                # form of the reference's boolean indexing (CUDA-graph capturable): look every point up with clamped
+                # coordinates, keep the look-up where the point is inside
                 Xs2, d2 = Xs.reshape(-1, 3), deltas.reshape(-1, 1)
-                good = t.all((Xs2 <= 1.) * (Xs2 >= -1.), 1)
-                Rho_S = Rho.reshape(-1, 1).detach().clone()
-                Rho_S[good] = Network.Supervised_Sample(Xs2[good], d2[good])
-                Rho_S = Rho_S.reshape(N, S, 1)
+                good = t.all((Xs2 <= 1.) * (Xs2 >= -1.), 1, keepdim=True)
+                sup = Network.Supervised_Sample(t.clamp(Xs2, -1., 1.), d2)
+                Rho_S = t.where(good, sup, Rho.reshape(-1, 1).detach()).reshape(N, S, 1)
             Rho = Rho * trust + Rho_S * (1 - trust)
         PE = 1 - t.exp(-Rho * deltas)
         PV = get_PV(Rho.detach(), deltas) if not Rho.requires_grad else self._pv_autograd(Rho, deltas)
         return {"PE": PE, "PV_Exact": PV, "Solar_Vis": Vis, "Sky_Col": Sky}
+
+    def _trust(self, current_step):
+        """trust = step / n_steps (Eval_Tools_2.py:218); a device scalar `trust_tensor` (set by the CUDA-graph training
+        step, refreshed before each replay) takes precedence over the Python number"""
+        tt = getattr(self, "trust_tensor", None)
+        return tt if tt is not None else current_step / self.n_steps
 
     def _pv_autograd(self, Rho, deltas):
         N, S = Rho.shape[0], Rho.shape[1]

@@ -59,11 +59,12 @@ class TrainStep:
         """use_graph: after `graph_warmup` eager steps at a given batch size, the whole step (sampling, network forward,
         losses, backward and - single GPU - both Adam updates) is captured once into a CUDA graph and replayed; inputs live
         in static device buffers refreshed before each replay.  The arithmetic and kernel sequence are those of the eager
-        step; only the ~1300 per-step launches stop costing host time.  Not used for the DSM-guided section (use_prior:
-        the trust factor changes every step)."""
+        step; only the per-step launches stop costing host time.  The DSM-guided section (use_prior) is captured too: its
+        trust factor step / n_steps lives in a device scalar refreshed before each replay."""
         self.args, self.device = args, t.device(device)
         self.world_size = world_size
-        self.use_graph = bool(use_graph) and not use_prior and self.device.type == "cuda"
+        self.use_graph = bool(use_graph) and self.device.type == "cuda"
+        self.use_prior = use_prior
         self.graph_warmup = graph_warmup
         self.micro_batch = micro_batch
         self._graphs = {}
@@ -212,6 +213,10 @@ class TrainStep:
         st = self._graphs.get((n, mb))
         if st is None:
             st = self._graphs[(n, mb)] = self._static(data_dict, mb)
+        if self.use_prior:
+            if getattr(self.eval_tool, "trust_tensor", None) is None:
+                self.eval_tool.trust_tensor = t.zeros((), device=self.device, dtype=t.float32)
+            self.eval_tool.trust_tensor.fill_(current_step / self.eval_tool.n_steps)
         fused_opt = self.world_size == 1 and k == 1        # the optimiser updates ride in the same graph
         if k > 1 and self.graph_warmup < 1:
             raise ValueError("micro-batched graph capture needs graph_warmup >= 1 (the eager step creates the .grad tensors)")
@@ -270,6 +275,8 @@ class TrainStep:
             self._eager_calls[n] = self._eager_calls.get(n, 0) + 1
         chunks = self._chunks(n)
         self._zero_grads(to_none=True)
+        if self.use_prior and getattr(self.eval_tool, "trust_tensor", None) is not None:
+            self.eval_tool.trust_tensor.fill_(current_step / self.eval_tool.n_steps)
         if len(chunks) == 1:
             loss, total = self._fwd_bwd(data_dict, current_step, 1.0, **inject)
         else:
