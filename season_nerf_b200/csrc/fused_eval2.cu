@@ -9,15 +9,20 @@
 //
 // Table-driven interpreter of the static program built by season_nerf_b200/packing2.py (schedule, slot plan and
 // hazard rules are documented there).  Roles (320 threads per CTA): warp 0 weight producer (both CTAs), warp 1 MMA
-// issuer (leader CTA only; TMEM allocation in both), warps 2-9 epilogue (two warps per TMEM lane quarter; warp half h
-// drains columns [128h, 128h+128) of a 256-column region = two 64-column activation chunks).
+// issuer (ONE thread of the leader CTA runs the whole issue loop; TMEM allocation in both), warps 2-9 epilogue: two
+// warps per TMEM lane quarter, warp half h drains columns [128h, 128h+128) of a 256-column region = two 64-column
+// activation chunks.  A warp hands its part of the TMEM region back to the MMA issuer as soon as the accumulators of its
+// last chunk are in registers - before the sin / store work - so the next layer's first MMAs overlap the drain.
+// SNB_FUSED_EPI_WARPS=16 selects four warps per lane quarter (one chunk each): measured slower on B200 (1.08 vs 1.14
+// PFLOP/s algorithmic sustained; the drain is bound by MUFU.SIN + TMEM reads, not by latency hiding).
 // Barriers (same offsets in both CTAs):
 //   w_full[5]       leader; expect_tx by the leader's producer, TMA bytes of both CTAs
 //   w_empty[5]      each CTA; tcgen05.commit multicast
 //   acc_full[2]     each CTA; tcgen05.commit multicast (region complete)
-//   acc_empty[2]    leader; 16 arrivals (8 epilogue warps x 2 CTAs, remote arrive from the peer)
+//   acc_empty[2]    leader; 2 x kEpiWarps arrivals (epilogue warps of both CTAs, remote arrive from the peer)
 //   chunk_ready[9]  leader; 8 arrivals (4 lane-quarter warps x 2 CTAs)
 //   reference semantics: T_NeRF_net_v2.py:75-105,131-151,169-170; G_NeRF.py:74-133; misc.py:105-139,188-189.
+#include <cstdlib>
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "api.h"
@@ -33,10 +38,9 @@ constexpr int kSlots = 9;
 constexpr int kWStages = 5;
 constexpr uint32_t kSlotBytes = 128 * 64 * 2;      // 16 KB: 128 rows x 64 bf16, 128B-swizzled
 constexpr uint32_t kWStageBytes = 128 * 64 * 2;    // 16 KB: this CTA's half (<= 128 rows) of a weight tile
-constexpr int kThreads = 320;
+
 constexpr uint32_t kBarBytes = 512;
 constexpr uint32_t kSmem = 1024 + kSlots * kSlotBytes + kWStages * kWStageBytes + kBarBytes;
-constexpr int kRegionCols = 256;
 
 enum { F_ACC = 1, F_WAIT_CHUNK = 2, F_WAIT_EMPTY = 4, F_COMMIT = 8 };
 enum { K_ENC_POS = 0, K_ENC_SUN = 1, K_SINE = 2, K_HEAD = 3 };
@@ -62,6 +66,21 @@ __device__ __forceinline__ uint4 ld_step(const uint4* p) { return __ldg(p); }
 __device__ __forceinline__ void store_row_unit(uint32_t slot_addr, int row, int unit, uint4 v) {
   const uint32_t a = slot_addr + (uint32_t)row * 128u + (uint32_t)((unit ^ (row & 7)) << 4);
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// bias + sin -> bf16 of 32 accumulator columns (four 16-byte units of a 128-byte swizzled activation row)
+__device__ __forceinline__ void sine_units(const uint32_t (&r)[32], const float4* __restrict__ bp4, uint32_t slot_addr, int row,
+                                           int unit0) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const float4 b0 = __ldg(bp4 + 2 * u), b1 = __ldg(bp4 + 2 * u + 1);
+    const float v0 = __sinf(__uint_as_float(r[8 * u + 0]) + b0.x), v1 = __sinf(__uint_as_float(r[8 * u + 1]) + b0.y);
+    const float v2 = __sinf(__uint_as_float(r[8 * u + 2]) + b0.z), v3 = __sinf(__uint_as_float(r[8 * u + 3]) + b0.w);
+    const float v4 = __sinf(__uint_as_float(r[8 * u + 4]) + b1.x), v5 = __sinf(__uint_as_float(r[8 * u + 5]) + b1.y);
+    const float v6 = __sinf(__uint_as_float(r[8 * u + 6]) + b1.z), v7 = __sinf(__uint_as_float(r[8 * u + 7]) + b1.w);
+    store_row_unit(slot_addr, row, unit0 + u,
+                   make_uint4(pack_bf16x2(v0, v1), pack_bf16x2(v2, v3), pack_bf16x2(v4, v5), pack_bf16x2(v6, v7)));
+  }
 }
 
 // PE_Encode (misc.py:105-139), extended: [x (D) | per dim: cos(k_j x) j<n, sin(k_j x) j<n], k_j = 2^j fl32(pi/2).
@@ -94,7 +113,9 @@ __device__ __forceinline__ void encode_row(float x0, float x1, float x2, uint32_
   }
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+// kEpiWarps: 8 (default: two warps per lane quarter, two chunks each) or 16 (one chunk each, SNB_FUSED_EPI_WARPS=16)
+template <int kEpiWarps>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (2 + kEpiWarps), 1)
 fused_eval2_kernel(const __grid_constant__ CUtensorMap tmapW128, const __grid_constant__ CUtensorMap tmapW8, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -125,7 +146,7 @@ fused_eval2_kernel(const __grid_constant__ CUtensorMap tmapW128, const __grid_co
     }
     for (int r = 0; r < 2; ++r) {
       mbar_init(acc_full(r), 1);
-      mbar_init(acc_empty(r), 16);
+      mbar_init(acc_empty(r), 2 * kEpiWarps);
     }
     for (int s = 0; s < kSlots; ++s) mbar_init(chunk_ready(s), 8);
     fence_barrier_init();
@@ -162,8 +183,10 @@ fused_eval2_kernel(const __grid_constant__ CUtensorMap tmapW128, const __grid_co
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA) =====================
-    if (rank == 0) {
+    // ===================== MMA issuer (one thread of the leader CTA) =====================
+    // The whole loop runs in ONE elected thread (no per-step elect / warp re-convergence): the time between two steps'
+    // issue has to stay well below the 512 tensor clocks one step keeps the pipe busy.
+    if (rank == 0 && elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       uint32_t chunk_par = 0;        // parity to wait for, per slot
@@ -185,7 +208,7 @@ fused_eval2_kernel(const __grid_constant__ CUtensorMap tmapW128, const __grid_co
           }
           mbar_wait(w_full(stage), phase);
           tc_fence_after();
-          if (elect_one()) {
+          {
             const uint32_t idesc = make_idesc_bf16(256, (int)n, 0, 0);
             const uint32_t sa = slots_base + a_slot * kSlotBytes;
             const uint32_t sb = wst_base + stage * kWStageBytes;
@@ -196,7 +219,6 @@ fused_eval2_kernel(const __grid_constant__ CUtensorMap tmapW128, const __grid_co
             umma_commit_cg2_mc(w_empty(stage), 3);
             if (flags & F_COMMIT) umma_commit_cg2_mc(acc_full(regions >> 4), 3);
           }
-          __syncwarp();
           if (++stage == kWStages) { stage = 0; phase ^= 1; }
           raw = nxt;
         }
@@ -205,7 +227,8 @@ fused_eval2_kernel(const __grid_constant__ CUtensorMap tmapW128, const __grid_co
   } else {
     // ===================== epilogue / activation warps (both CTAs) =====================
     const int wq = warp & 3;                 // TMEM lane quarter
-    const int h = (warp - 2) >> 2;           // which 128-column half of a region this warp drains
+    constexpr int kChunksPerWarp = 16 / kEpiWarps;
+    const int h = (warp - 2) >> 2;           // which 64-column chunk(s) of a region this warp drains
     const int row = wq * 32 + lane;
     const uint32_t l_acc_empty = leader_bar_base + 8u * (2 * kWStages + 2);
     const uint32_t l_chunk_ready = leader_bar_base + 8u * (2 * kWStages + 4);
@@ -251,39 +274,28 @@ fused_eval2_kernel(const __grid_constant__ CUtensorMap tmapW128, const __grid_co
           const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + d_col;
           if (kind == K_SINE) {
 #pragma unroll 1
-            for (int cc = 0; cc < 2; ++cc) {
-              const int chunk = 2 * h + cc;                      // 64-column chunk of the region
+            for (int cc = 0; cc < kChunksPerWarp; ++cc) {
+              const int chunk = kChunksPerWarp * h + cc;           // 64-column chunk of the region
               const uint32_t dst = (dstw >> (8 * chunk)) & 0xFF;
               const uint32_t slot_addr = slots_base + dst * kSlotBytes;
+              const float4* bp4 = reinterpret_cast<const float4*>(p.bias + bias_off + 64 * chunk);
               uint32_t r0[32], r1[32];
               tmem_ld_32x32(t_row + 64 * chunk, r0);
               tmem_ld_32x32(t_row + 64 * chunk + 32, r1);
-              float bv[64];
-              const float4* bp4 = reinterpret_cast<const float4*>(p.bias + bias_off + 64 * chunk);
-#pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                const float4 q = __ldg(bp4 + e);
-                bv[4 * e] = q.x, bv[4 * e + 1] = q.y, bv[4 * e + 2] = q.z, bv[4 * e + 3] = q.w;
-              }
               tmem_ld_wait();
-#pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                float v[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const uint32_t a = u < 4 ? r0[8 * u + e] : r1[8 * (u - 4) + e];
-                  v[e] = __sinf(__uint_as_float(a) + bv[8 * u + e]);
-                }
-                store_row_unit(slot_addr, row, u,
-                               make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
+              if (cc == kChunksPerWarp - 1) {
+                // the accumulators of this warp's part of the region are in registers: hand the TMEM region back to the
+                // MMA issuer BEFORE the sin / store work, so that the next layer's first MMAs overlap this drain
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(l_acc_empty + 8u * region);
               }
+              sine_units(r0, bp4, slot_addr, row, 0);
+              sine_units(r1, bp4 + 8, slot_addr, row, 4);
               fence_proxy_async_smem();
               __syncwarp();
               if (lane == 0) mbar_arrive_cluster(l_chunk_ready + 8u * dst);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(l_acc_empty + 8u * region);
           } else {  // K_HEAD: 16 accumulator columns -> raw outputs in global memory
             if (h == 0) {
               uint32_t r[16];
@@ -351,15 +363,24 @@ extern "C" int snb_fused_eval2(const void* program, unsigned n_mma, unsigned n_e
   if (rc) return rc;
   rc = make_tmap_bf16(&t8, base + w_off, w_rows, 64, 64, 64, 8);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(f2::fused_eval2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, f2::kSmem);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+  static int epi_warps = 0;
+  if (!epi_warps) {
+    const char* ev = getenv("SNB_FUSED_EPI_WARPS");
+    epi_warps = (ev && atoi(ev) == 16) ? 16 : 8;
+    cudaError_t e = cudaFuncSetAttribute(f2::fused_eval2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, f2::kSmem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(f2::fused_eval2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, f2::kSmem);
+    if (e != cudaSuccess) {
+      epi_warps = 0;
+      return (int)e;
+    }
   }
   const int num_pairs = kNumSMs / 2;
   const int grid = 2 * (p.num_tiles < num_pairs ? p.num_tiles : num_pairs);
-  f2::fused_eval2_kernel<<<grid, f2::kThreads, f2::kSmem, st>>>(t128, t8, p);
+  if (epi_warps == 8)
+    f2::fused_eval2_kernel<8><<<grid, 32 * 10, f2::kSmem, st>>>(t128, t8, p);
+  else
+    f2::fused_eval2_kernel<16><<<grid, 32 * 18, f2::kSmem, st>>>(t128, t8, p);
   count_launch();
   SNB_LAUNCH_CHECK();
   return SNB_OK;
