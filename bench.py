@@ -10,7 +10,8 @@ Headline workload (BASELINE.json configs[1]): one training step on 4096 syntheti
 metric = training rays/s (image rays; every image ray is paired with one solar ray).
   value : inputs (rays, solar rays, jitter) resident in HBM before the timed region.
   e2e   : the public API call `TrainStep.step(batch)` with HOST tensors like the reference's DataLoader rows: H2D of the
-          batch, host-side solar-ray generation + H2D, and a D2H read of the loss every step.
+          batch, solar rays drawn and built on the device (TrainStep(solar_rng="device"), the default), and a D2H read of
+          the loss every step.
 A secondary `render` object reports the fused render kernel on a 512x512x96 view (BASELINE.json configs[2] without
 the exact shadow march) with its own tensor roofline.
 """
@@ -265,7 +266,7 @@ def run_ours(a):
     value = world * n * a.steps / (ms * 1e-3)
 
     # ---- e2e: public API with host tensors, loss read back every step ----------------------------------
-    h2d = sum(v.numel() * 4 for v in host_batch.values()) + n * (3 + 3 + 3 + 4) * 4
+    h2d = sum(v.numel() * 4 for v in host_batch.values()) + 2 * S * 4      # batch rows + the two jitter vectors
     sink = []
 
     def step_host(i):

@@ -68,12 +68,18 @@ int snb_march_transmittance(const float* rho, const float* deltas, long long M, 
 int snb_cli_composite(const void* rho, const void* deltas, const void* base, const void* vis, const void* adj,
                       const double* cls, const void* exact_vis, int in_dtype, int N, int S, int C, double* base_img,
                       double* season_img, double* extreme, double* raw_shadow, double* raw_shadow_exact, void* stream);
+/* classic shadows of get_imgs_from_Img_Dict (mg_Img_Eval.py:166-181): out[n,:] = sum_s PS * sigmoid(base + cls . adj) *
+ * (vis + (1 - vis) * sky) with the per-sample sky colour sky [N,S,3]; `vis` is Est_Solar_Vis or Exact_Solar.  float64 sums. */
+int snb_cli_classic_shadow(const void* rho, const void* deltas, const void* base, const void* vis, const void* adj,
+                           const void* sky, const double* cls, int in_dtype, int N, int S, int C, double* out, void* stream);
 /* year sweep: mg_Img_Eval.py:192-228 get_imgs_from_Img_Dict_t_step, fused over T class vectors.
  * cls [T,C] -> out [T,N,3] (float64) = season colour * shade[N,3] (the per-ray Shadow_Adjust factor of :214-226;
  * null = 1).  float32 components are recombined in float32 and reduced in float64 (|error| < 3e-7); float64
- * components keep float64 arithmetic throughout.  T*C <= 5120. */
+ * components keep float64 arithmetic throughout.  T*C <= 5120.  ps_weight [N,S] (element type in_dtype, optional)
+ * multiplies PS per sample: the classic-shadow alignment sums PS * vis (mg_Img_Eval.py:448-449). */
 int snb_year_sweep(const void* rho, const void* deltas, const void* base, const void* adj, const double* cls,
-                   const double* shade, int in_dtype, int N, int S, int C, int T, double* out, void* stream);
+                   const double* shade, const void* ps_weight, int in_dtype, int N, int S, int C, int T, double* out,
+                   void* stream);
 
 /* ---- camera rays ("next" row of the scope table): P_img_Pinhole.invert_P, pre_NeRF/P_Img.py:133-147 -------------
  * For n pixels - explicit (rows[i], cols[i]) int32 device arrays, or the raster grid (i / W * ds, i % W * ds) when both
@@ -85,6 +91,17 @@ int snb_year_sweep(const void* rho, const void* deltas, const void* base, const 
 int snb_camera_rays(const double* P, const int* rows, const int* cols, long long n, int W, int ds, double z_top,
                     double z_bot, const double* bounds, float* tops, float* bots, double* xy64, unsigned char* good,
                     void* stream);
+
+/* ---- solar-ray generator: create_solor_rays_uniform.__call__, T_NeRF_Full_2/Eval_Tools_2.py:72-108 ----------------
+ * n random solar rays from already drawn random numbers (device arrays): az_el [n,2] float64 = (azimuth in
+ * [-180,180), elevation in [1,90)) degrees, u_xy [n,2] float32 uniforms, u_time [n,2] float32 uniforms (null with
+ * times == null).  world_center (3 doubles) and W2L_H (4x4 row-major doubles) are HOST pointers.  Per ray, in float64
+ * in numpy's evaluation order: v = world_angle_2_local_vec(el, az) (all_NeRF/mg_unit_converter.py:5-9,29-34,59-68),
+ * delta = 2 v / v_z;  starts = (2 u_x - 1, 2 u_y - 1, 1) float32;  ends = float32(starts - delta);  vec = float32(v);
+ * times = (cos f0, sin f0, cos f1, sin f1) with f = (u_time * 2) * fl32(pi) in float32.  Replaces the reference's
+ * per-ray Python loop (89 us / ray) and the host->device copy of the four arrays. */
+int snb_solar_rays(const double* world_center, const double* W2L_H, const double* az_el, const float* u_xy,
+                   const float* u_time, int n, float* starts, float* ends, float* vec, float* times, void* stream);
 
 /* ---- positional encoding: misc.py:105-139 PE_Encode (extended) ------------------------------
  * out[m, col0 + ...] = [x (D), per dim: cos(k_j x) j<n, sin(k_j x) j<n], k_j = 2^j * fl32(pi/2);

@@ -588,8 +588,8 @@ def _scatter(D, size, vals):
 
 
 def get_imgs_from_img_dict(D, size, use_classic_shadows=False):
-    """get_imgs_from_Img_Dict, mg_Img_Eval.py:123-190 (float64 numpy;
-    use_classic_shadows=False branch, the one the CLI takes)."""
+    """get_imgs_from_Img_Dict, mg_Img_Eval.py:123-190 (float64 numpy), both shadow conventions (the CLI takes
+    use_classic_shadows=False; True = :166-181)."""
     sky = D["Sky_Col"][0, 0]
     cls = D["Output_class"][0, 0]
     PS = _ps_f64(D)
@@ -609,6 +609,15 @@ def get_imgs_from_img_dict(D, size, use_classic_shadows=False):
         R["Shadow_Adjust_Exact"] = np.expand_dims(mask_e, -1) + np.expand_dims(1 - mask_e, -1) * sky.reshape(1, 1, 3)
         R["Shadow_Mask_Exact"] = mask_e
         R["Raw_Shadow_Mask_Exact"] = raw_e
+    if use_classic_shadows:                                                    # mg_Img_Eval.py:166-181
+        ip = D["Image_Points"]
+        cols_season = np.sum(PS * _sig(D["Base_Col"] + mixed), 1)
+        for key, name in (("Est_Solar_Vis", "Shadow_Adjust"), ("Exact_Solar", "Shadow_Adjust_Exact")):
+            if key not in D:
+                continue
+            shadow_term = D[key] + (1 - D[key]) * D["Sky_Col"]
+            classic = np.sum(PS * (_sig(D["Base_Col"] + mixed) * shadow_term), 1)
+            R[name][ip[:, 0], ip[:, 1]] = classic / (cols_season + 1e-8)
     return R
 
 
@@ -625,6 +634,32 @@ def get_imgs_from_img_dict_t_step(D, size, class_vecs):
         mixed = (class_vecs[i].reshape(1, 1, -1) @ D["Adjust_col"])[:, :, 0, :]
         imgs.append(_scatter(D, size, np.sum(PS * _sig(D["Base_Col"] + mixed), 1)) * adj)
     return np.array(imgs)
+
+
+def seasonal_align_v3_classic(p, D, target_img, t0):
+    """T_NeRF_Eval_Utils/mg_Img_Eval.py:416-475 (_grad_descent_v3_classic_shadows): per-sample shading inside the sum."""
+    ts = t.tensor([t0] + list(np.linspace(0, 1, 366))).float()
+    ts_scaled = t.stack([t.cos(ts * 2 * np.pi), t.sin(ts * 2 * np.pi), t.cos(ts * 2 * np.pi), t.sin(ts * 2 * np.pi)], 1)
+    with t.no_grad():
+        tv = time_classes(p, ts_scaled)
+        ip = np.asarray(D["Image_Points_in_GT_Img"])
+        GT = t.tensor(np.asarray(target_img)[ip[:, 0], ip[:, 1]]).float()
+        rho, dl = np.asarray(D["Rho"], dtype=np.float64), np.asarray(D["Deltas"], dtype=np.float64)
+        PS = t.tensor(get_PV(t.tensor(rho), t.tensor(dl)).numpy() * (1 - np.exp(-rho * dl))).float()
+        Base, Adj = t.tensor(np.asarray(D["Base_Col"])).float(), t.tensor(np.asarray(D["Adjust_col"])).float()
+        SV = t.tensor(np.asarray(D["Est_Solar_Vis"])).float()
+        scores, skies = np.ones(ts.shape[0]), np.zeros([ts.shape[0], 3])
+        for i in range(ts.shape[0]):
+            col = t.sigmoid(Base + t.sum(Adj * tv[i].reshape([1, 1, -1, 1]), 2))
+            Y = GT - t.sum(PS * col * SV, 1)
+            X = t.sum(PS * col * (1 - SV), 1)
+            good = t.sum(X * X, 0) > 0
+            sky = t.clamp((1 / t.sum(X * X, 0)[good]) * t.sum(X * Y, 0)[good], 0, 1)
+            R = t.sum(PS * col * (SV + (1 - SV) * sky), 1)
+            scores[i] = float(t.mean((R - GT) ** 2))
+            skies[i] = sky.numpy()
+        best = int(np.argmin(scores))
+    return tv[best], t.tensor(skies[best]).reshape([1, 1, 3]).float(), ts[best].item(), scores
 
 
 # --------------------------------------------------------------------------

@@ -21,12 +21,14 @@ SIGNATURES = {
     "snb_sample_rays": [_p, _p, _p, _i, _i, _i, _p, _p, _p],
     "snb_camera_rays": [C.POINTER(C.c_double), _p, _p, _ll, _i, _i, C.c_double, C.c_double, C.POINTER(C.c_double), _p, _p, _p,
                         _p, _p],
+    "snb_solar_rays": [C.POINTER(C.c_double), C.POINTER(C.c_double), _p, _p, _p, _i, _p, _p, _p, _p, _p],
     "snb_solar_tops": [_p, _ll, C.POINTER(C.c_double), _i, _p, _p],
     "snb_composite_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
     "snb_composite_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "snb_march_transmittance": [_p, _p, _ll, _i, _p, _p],
     "snb_cli_composite": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p],
-    "snb_year_sweep": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p],
+    "snb_cli_classic_shadow": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p],
+    "snb_year_sweep": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p],
     "snb_pe_encode": [_p, _i, _ll, _i, _i, _p, _i, _i, _i, _i, _p],
     "snb_gemm": [_p, _i, _i, _p, _i, _i, _p, _i, _p, _f, _i, _ll, _i, _i, _i, _i, _p],
     "snb_gemm_stats": [_p, _i, _p, _i, _p, _i, _p, _f, _ll, _i, _i, _p, _p],

@@ -355,6 +355,40 @@ cli_composite_kernel(const T* __restrict__ rho, const T* __restrict__ deltas, co
   }
 }
 
+// mg_Img_Eval.py:166-181 (use_classic_shadows): classic[n,:] = sum_s PS * sigmoid(base + class . adjust) * (vis + (1 - vis) * sky)
+// with the per-sample sky colour of the component dict, float64 sums like the reference's numpy.
+template <typename T>
+__global__ void __launch_bounds__(128)
+cli_classic_shadow_kernel(const T* __restrict__ rho, const T* __restrict__ deltas, const T* __restrict__ base,
+                          const T* __restrict__ vis, const T* __restrict__ adj, const T* __restrict__ sky,
+                          const double* __restrict__ cls, int N, int S, int C, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int n = blockIdx.x * wpb + (threadIdx.x >> 5); n < N; n += gridDim.x * wpb) {
+    double carry = 0.0, acc[3] = {0, 0, 0};
+    for (int s0 = 0; s0 < S; s0 += 32) {
+      const int s = s0 + lane;
+      const bool ok = s < S;
+      const long long o = (long long)n * S + s;
+      const double ps = ps_chunk_d(ok ? (double)rho[o] * (double)deltas[o] : 0.0, lane, carry);
+      if (ok) {
+        const double v = (double)vis[o];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          double mix = 0;
+          for (int c = 0; c < C; ++c) mix += cls[c] * (double)adj[(o * C + c) * 3 + d];
+          const double col = sigd((double)base[3 * o + d] + mix) * (v + (1.0 - v) * (double)sky[3 * o + d]);
+          acc[d] += ps * col;
+        }
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) acc[d] = warp_sum_d(acc[d]);
+    if (lane == 0)
+      for (int d = 0; d < 3; ++d) out[3 * (long long)n + d] = acc[d];
+  }
+}
+
 // mg_Img_Eval.py:192-228 fused over the T class vectors: PS, base and adjust are read ONCE per ray and kept
 // in registers (3 samples per lane at S=96); the T recombinations run out of registers.
 //   out[t, n, :] = shade[n, :] * sum_s PS[n,s] * sigmoid(base[n,s,:] + sum_c cls[t,c] * adj[n,s,c,:])
@@ -369,8 +403,8 @@ template <> __device__ __forceinline__ float sig_ct<float>(float x) { return __f
 template <typename TI, int kChunks>
 __global__ void __launch_bounds__(128)
 year_sweep_kernel(const TI* __restrict__ rho, const TI* __restrict__ deltas, const TI* __restrict__ base,
-                  const TI* __restrict__ adj, const double* __restrict__ cls, const double* __restrict__ shade, int N,
-                  int S, int C, int T, double* __restrict__ out) {
+                  const TI* __restrict__ adj, const double* __restrict__ cls, const double* __restrict__ shade,
+                  const TI* __restrict__ ps_weight, int N, int S, int C, int T, double* __restrict__ out) {
   typedef TI CT;
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
@@ -386,7 +420,8 @@ year_sweep_kernel(const TI* __restrict__ rho, const TI* __restrict__ deltas, con
       const int s = c * 32 + lane;
       const bool ok = s < S;
       const long long o = (long long)n * S + s;
-      const double psd = ps_chunk_d(ok ? (double)rho[o] * (double)deltas[o] : 0.0, lane, carry);
+      double psd = ps_chunk_d(ok ? (double)rho[o] * (double)deltas[o] : 0.0, lane, carry);
+      if (ps_weight && ok) psd *= (double)ps_weight[o];     // classic-shadow alignment: PS * vis (mg_Img_Eval.py:448-449)
       ps[c] = ok ? (CT)psd : (CT)0;
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
@@ -516,28 +551,48 @@ extern "C" int snb_cli_composite(const void* rho, const void* deltas, const void
   return SNB_OK;
 }
 
+extern "C" int snb_cli_classic_shadow(const void* rho, const void* deltas, const void* base, const void* vis, const void* adj,
+                                      const void* sky, const double* cls, int in_dtype, int N, int S, int C, double* out,
+                                      void* stream) {
+  SNB_CHECK_ARG(rho && deltas && base && vis && adj && sky && cls && out);
+  SNB_CHECK_ARG(N >= 0 && S > 0 && C >= 1 && C <= 8 && (in_dtype == SNB_F32 || in_dtype == SNB_F64));
+  if (N == 0) return SNB_OK;
+  const int grid = grid_for(N, 4, 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (in_dtype == SNB_F64)
+    cli_classic_shadow_kernel<double><<<grid, 128, 0, st>>>((const double*)rho, (const double*)deltas, (const double*)base,
+        (const double*)vis, (const double*)adj, (const double*)sky, cls, N, S, C, out);
+  else
+    cli_classic_shadow_kernel<float><<<grid, 128, 0, st>>>((const float*)rho, (const float*)deltas, (const float*)base,
+        (const float*)vis, (const float*)adj, (const float*)sky, cls, N, S, C, out);
+  count_launch();
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
 template <typename TI>
 static void launch_sweep(int chunks, int grid, cudaStream_t st, const void* rho, const void* deltas, const void* base,
-                         const void* adj, const double* cls, const double* shade, int N, int S, int C, int T, double* out) {
-  const TI *r = (const TI*)rho, *d = (const TI*)deltas, *b = (const TI*)base, *a = (const TI*)adj;
+                         const void* adj, const double* cls, const double* shade, const void* ps_weight, int N, int S, int C,
+                         int T, double* out) {
+  const TI *r = (const TI*)rho, *d = (const TI*)deltas, *b = (const TI*)base, *a = (const TI*)adj, *w = (const TI*)ps_weight;
   const size_t sm = (size_t)T * C * sizeof(double);
-  if (chunks <= 1) year_sweep_kernel<TI, 1><<<grid, 128, sm, st>>>(r, d, b, a, cls, shade, N, S, C, T, out);
-  else if (chunks == 2) year_sweep_kernel<TI, 2><<<grid, 128, sm, st>>>(r, d, b, a, cls, shade, N, S, C, T, out);
-  else if (chunks == 3) year_sweep_kernel<TI, 3><<<grid, 128, sm, st>>>(r, d, b, a, cls, shade, N, S, C, T, out);
-  else year_sweep_kernel<TI, 4><<<grid, 128, sm, st>>>(r, d, b, a, cls, shade, N, S, C, T, out);
+  if (chunks <= 1) year_sweep_kernel<TI, 1><<<grid, 128, sm, st>>>(r, d, b, a, cls, shade, w, N, S, C, T, out);
+  else if (chunks == 2) year_sweep_kernel<TI, 2><<<grid, 128, sm, st>>>(r, d, b, a, cls, shade, w, N, S, C, T, out);
+  else if (chunks == 3) year_sweep_kernel<TI, 3><<<grid, 128, sm, st>>>(r, d, b, a, cls, shade, w, N, S, C, T, out);
+  else year_sweep_kernel<TI, 4><<<grid, 128, sm, st>>>(r, d, b, a, cls, shade, w, N, S, C, T, out);
 }
 
 extern "C" int snb_year_sweep(const void* rho, const void* deltas, const void* base, const void* adj,
-                              const double* cls, const double* shade, int in_dtype, int N, int S, int C, int T, double* out,
-                              void* stream) {
+                              const double* cls, const double* shade, const void* ps_weight, int in_dtype, int N, int S,
+                              int C, int T, double* out, void* stream) {
   SNB_CHECK_ARG(rho && deltas && base && adj && cls && out && N >= 0 && S > 0 && T >= 0);
   SNB_CHECK_ARG(in_dtype == SNB_F32 || in_dtype == SNB_F64);
   if (C < 1 || C > 4 || S > 128 || (long long)T * C * 8 > 40 * 1024) return SNB_ERR_UNSUPPORTED;
   if (N == 0 || T == 0) return SNB_OK;
   const int grid = grid_for(N, 4, 16);
   const int chunks = (S + 31) / 32;
-  if (in_dtype == SNB_F64) launch_sweep<double>(chunks, grid, (cudaStream_t)stream, rho, deltas, base, adj, cls, shade, N, S, C, T, out);
-  else launch_sweep<float>(chunks, grid, (cudaStream_t)stream, rho, deltas, base, adj, cls, shade, N, S, C, T, out);
+  if (in_dtype == SNB_F64) launch_sweep<double>(chunks, grid, (cudaStream_t)stream, rho, deltas, base, adj, cls, shade, ps_weight, N, S, C, T, out);
+  else launch_sweep<float>(chunks, grid, (cudaStream_t)stream, rho, deltas, base, adj, cls, shade, ps_weight, N, S, C, T, out);
   count_launch();
   SNB_LAUNCH_CHECK();
   return SNB_OK;

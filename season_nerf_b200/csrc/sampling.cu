@@ -120,6 +120,51 @@ __global__ void __launch_bounds__(256) camera_rays_kernel(CamP cam, const int* _
   }
 }
 
+// create_solor_rays_uniform (Eval_Tools_2.py:72-108) for n rays at once: the reference's per-ray Python loop over
+// world_angle_2_local_vec (all_NeRF/mg_unit_converter.py:5-9,29-34,59-68) in float64, like numpy, then
+//   delta = 2 v / v_z (float64),  start = (2 u_x - 1, 2 u_y - 1, 1) (float32),  end = float(start - delta),
+//   time  = (cos f0, sin f0, cos f1, sin f1),  f = (u * 2) * fl32(pi)   (float32, like `t.rand([n,2]) * 2 * np.pi`).
+struct SolarGeo {
+  double wc[3];
+  double h[12];   // first three rows of World2Local_H
+};
+
+__global__ void __launch_bounds__(128) solar_rays_kernel(SolarGeo g, const double* __restrict__ az_el, const float* __restrict__ u_xy,
+                                                         const float* __restrict__ u_time, int n, float* __restrict__ starts,
+                                                         float* __restrict__ ends, float* __restrict__ vec,
+                                                         float* __restrict__ times) {
+  const double kDeg = 0.017453292519943295;      // pi / 180
+  const double kRadDeg = 57.29577951308232;      // 180 / pi
+  const double kR = 1000. * 6378.137;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double az = az_el[2 * i], el = az_el[2 * i + 1];
+    // LLA_get_vec(center, theta = az, rho = el)
+    const double Y = cos(az * kDeg), X = sin(az * kDeg);
+    const double Z = tan(el * kDeg) * sqrt(X * X + Y * Y);
+    const double norm = sqrt(X * X + Y * Y + Z * Z) / 1000.;
+    const double xn = X / norm, yn = Y / norm, zn = Z / norm;
+    const double lat = g.wc[0] + (yn / kR) * kRadDeg;
+    const double lon = g.wc[1] + (xn / (kR * cos(g.wc[0] * kDeg))) * kRadDeg;
+    const double alt = g.wc[2] + zn;
+    // homogeneous transform, first three rows; then unit length
+    const double t0 = lat * g.h[0] + lon * g.h[1] + alt * g.h[2] + g.h[3];
+    const double t1 = lat * g.h[4] + lon * g.h[5] + alt * g.h[6] + g.h[7];
+    const double t2 = lat * g.h[8] + lon * g.h[9] + alt * g.h[10] + g.h[11];
+    const double len = sqrt(t0 * t0 + t1 * t1 + t2 * t2);
+    const double v0 = t0 / len, v1 = t1 / len, v2 = t2 / len;
+    const double d0 = 2. * (v0 / v2), d1 = 2. * (v1 / v2), d2 = 2. * (v2 / v2);
+    const float sx = __fadd_rn(__fmul_rn(2.0f, u_xy[2 * i]), -1.0f), sy = __fadd_rn(__fmul_rn(2.0f, u_xy[2 * i + 1]), -1.0f);
+    starts[3 * i] = sx, starts[3 * i + 1] = sy, starts[3 * i + 2] = 1.0f;
+    ends[3 * i] = (float)((double)sx - d0), ends[3 * i + 1] = (float)((double)sy - d1), ends[3 * i + 2] = (float)(1.0 - d2);
+    vec[3 * i] = (float)v0, vec[3 * i + 1] = (float)v1, vec[3 * i + 2] = (float)v2;
+    if (times) {
+      const float f0 = __fmul_rn(__fmul_rn(u_time[2 * i], 2.0f), 3.14159274101257324f);
+      const float f1 = __fmul_rn(__fmul_rn(u_time[2 * i + 1], 2.0f), 3.14159274101257324f);
+      times[4 * i] = cosf(f0), times[4 * i + 1] = sinf(f0), times[4 * i + 2] = cosf(f1), times[4 * i + 3] = sinf(f1);
+    }
+  }
+}
+
 }  // namespace snb
 
 extern "C" int snb_sample_rays(const float* top, const float* bot, const float* ts, int N, int S, int zero_oob,
@@ -157,6 +202,20 @@ extern "C" int snb_camera_rays(const double* P, const int* rows, const int* cols
   for (int i = 0; i < 4; ++i) cam.bounds[i] = bounds ? bounds[i] : 0.0;
   snb::camera_rays_kernel<<<snb::grid_for(n, 256, 16), 256, 0, (cudaStream_t)stream>>>(cam, rows, cols, n, W, ds, z_top, z_bot, tops,
                                                                                       bots, xy64, good);
+  snb::count_launch();
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_solar_rays(const double* world_center, const double* W2L_H, const double* az_el, const float* u_xy,
+                              const float* u_time, int n, float* starts, float* ends, float* vec, float* times,
+                              void* stream) {
+  SNB_CHECK_ARG(world_center && W2L_H && az_el && u_xy && starts && ends && vec && n >= 0 && ((times == nullptr) == (u_time == nullptr)));
+  if (n == 0) return SNB_OK;
+  snb::SolarGeo g;
+  for (int i = 0; i < 3; ++i) g.wc[i] = world_center[i];    // host pointers: travel as a kernel argument
+  for (int i = 0; i < 12; ++i) g.h[i] = W2L_H[i];
+  snb::solar_rays_kernel<<<snb::grid_for(n, 128, 8), 128, 0, (cudaStream_t)stream>>>(g, az_el, u_xy, u_time, n, starts, ends, vec, times);
   snb::count_launch();
   SNB_LAUNCH_CHECK();
   return SNB_OK;

@@ -86,6 +86,22 @@ class create_solor_rays_uniform():
         times = t.stack([t.cos(f[:, 0]), t.sin(f[:, 0]), t.cos(f[:, 1]), t.sin(f[:, 1])], 1)
         return starts, ends, vec, times, az_el
 
+    def on_device(self, n, device, include_times=False, generator=None, out=None):
+        """Same distribution as __call__, drawn and built ON THE DEVICE: azimuth / elevation (float64), the start
+        positions and the year / day fractions come from torch's CUDA generator (NOT the reference's numpy / CPU-torch
+        streams: a run is reproducible under torch.cuda.manual_seed, not draw-identical to the reference), the geometry
+        of :75-87 runs in one kernel (ops.solar_rays).  Nothing is computed on the host and nothing is copied.
+        -> starts, ends, vec (, times) float32 device tensors; `out` = preallocated tensors to fill."""
+        device = t.device(device)
+        sc = self.__dict__.get("_dev_scale")
+        if sc is None or sc[0] != device:
+            sc = self._dev_scale = (device, t.tensor([[360., 89.]], dtype=t.float64, device=device),
+                                    t.tensor([[-180., 1.]], dtype=t.float64, device=device))
+        az_el = t.rand(n, 2, dtype=t.float64, device=device, generator=generator).mul_(sc[1]).add_(sc[2])
+        u_xy = t.rand(n, 2, device=device, generator=generator)
+        u_t = t.rand(n, 2, device=device, generator=generator) if include_times else None
+        return ops.solar_rays(self.WC, self.W2L, az_el, u_xy, u_t, out=out)
+
     def create_given_vec(self, n, solar_angle_vec, include_times=False):
         delta = 2 * (solar_angle_vec / solar_angle_vec[2::])
         starts = t.ones([n, 3])
@@ -115,6 +131,9 @@ class All_in_One_Eval():
         self.use_MSE_loss = args.Use_MSE_loss
         self.ada_loss = ada_loss
         self.solar_creation_tool = create_solor_rays_uniform(H, WC, base_solar_vecs)
+        # False (default): solar rays are drawn on the host from the reference's RNG streams, in the reference's order.
+        # True: drawn and built on the device (create_solor_rays_uniform.on_device) - no host work, no H2D copy.
+        self.solar_on_device = False
         self.Sigmoid = t.nn.Sigmoid()
         self.BCE_loss = t.nn.BCELoss()
 
@@ -272,7 +291,9 @@ class All_in_One_Eval():
         try:
             out = self.eval(data_dict, Network, current_step, train_mode, jitter=jitter, ts=ts)
             if args.Use_Solar:
-                if solar is None:
+                if solar is None and self.solar_on_device:
+                    starts, ends, svec, stime = self.solar_creation_tool.on_device(n_rays, device, include_times=True)
+                elif solar is None:
                     starts, ends, svec, stime, _ = self.solar_creation_tool(n_rays, include_times=True)
                 else:
                     starts, ends, svec, stime = solar

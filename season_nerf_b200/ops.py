@@ -75,6 +75,30 @@ def camera_rays(P, device, rows=None, cols=None, grid=None, z_top=1.0, z_bot=-1.
     return tops, bots, (good.bool() if good is not None else None), xy64
 
 
+def solar_rays(world_center, W2L_H, az_el, u_xy, u_time=None, out=None):
+    """create_solor_rays_uniform.__call__ (Eval_Tools_2.py:72-108) from drawn random numbers, on the device:
+    az_el [n,2] f64 degrees, u_xy [n,2] f32 uniforms, u_time [n,2] f32 uniforms (optional)
+    -> starts, ends, vec [n,3] f32 (, times [n,4] f32).  `out`: preallocated (starts, ends, vec, times) to write into."""
+    import numpy as np
+    az_el = _cuda(az_el, torch.float64, "az_el").contiguous()
+    u_xy = _cuda(u_xy, torch.float32, "u_xy").contiguous()
+    n, dev = az_el.shape[0], az_el.device
+    if u_time is not None:
+        u_time = _cuda(u_time, torch.float32, "u_time").contiguous()
+    if out is None:
+        mk = lambda w: torch.empty(n, w, device=dev, dtype=torch.float32)
+        out = (mk(3), mk(3), mk(3), mk(4) if u_time is not None else None)
+    starts, ends, vec, times = out[0], out[1], out[2], (out[3] if u_time is not None else None)
+    for x in (starts, ends, vec, times):
+        if x is not None and not (x.is_cuda and x.is_contiguous() and x.dtype == torch.float32 and x.shape[0] == n):
+            raise ValueError("solar_rays: out tensors must be contiguous float32 CUDA tensors with n rows")
+    wc = (C.c_double * 3)(*[float(v) for v in np.asarray(world_center, dtype=np.float64).reshape(3)])
+    Hm = (C.c_double * 16)(*np.asarray(W2L_H, dtype=np.float64).reshape(16).tolist())
+    check(_lib.load().snb_solar_rays(wc, Hm, _ptr(az_el), _ptr(u_xy), _ptr(u_time), n, _ptr(starts), _ptr(ends), _ptr(vec),
+                                     _ptr(times), _stream()))
+    return (starts, ends, vec, times) if u_time is not None else (starts, ends, vec)
+
+
 def solar_tops(pts, sun_vec, f64=True):
     """mg_Img_Eval.py:57-60 (f64) / Eval_Tools_2.py:255-258 (f32).  pts [M,3] -> tops [M,3]."""
     pts = _cuda(pts, torch.float32, "pts").contiguous().reshape(-1, 3)
@@ -160,8 +184,23 @@ def cli_composite(rho, deltas, base, vis, adj, cls, exact_vis=None):
     return base_img, season, extreme, raw, raw_e
 
 
-def year_sweep(rho, deltas, base, adj, cls, shade=None, out=None):
-    """mg_Img_Eval.py:192-228 recombination for T class vectors at once -> [T,N,3] f64 (times shade [N,3] f64 if given)."""
+def cli_classic_shadow(rho, deltas, base, vis, adj, sky, cls):
+    """mg_Img_Eval.py:166-181: sum_s PS * sigmoid(base + cls . adj) * (vis + (1 - vis) * sky) -> [N,3] f64.
+    rho, deltas, vis [N,S]; base, sky [N,S,3]; adj [N,S,C,3] (all f32 or all f64 device tensors); cls [C] f64."""
+    N, S = rho.shape[0], rho.shape[1]
+    Cn = adj.shape[2]
+    out = torch.empty(N, 3, device=rho.device, dtype=torch.float64)
+    ins = [x.contiguous() for x in (rho, deltas, base, vis, adj, sky)]
+    if any(x.dtype != rho.dtype for x in ins):
+        raise TypeError("cli_classic_shadow: all components must share one dtype")
+    cls = _cuda(cls, torch.float64).contiguous()
+    check(_lib.load().snb_cli_classic_shadow(*[_ptr(x) for x in ins], _ptr(cls), _DT[rho.dtype], N, S, Cn, _ptr(out), _stream()))
+    return out
+
+
+def year_sweep(rho, deltas, base, adj, cls, shade=None, out=None, ps_weight=None):
+    """mg_Img_Eval.py:192-228 recombination for T class vectors at once -> [T,N,3] f64 (times shade [N,3] f64 if given).
+    ps_weight [N,S] (same dtype as rho) multiplies PS per sample (classic-shadow alignment, mg_Img_Eval.py:448-449)."""
     N, S = rho.shape[0], rho.shape[1]
     Cn, T = adj.shape[2], cls.shape[0]
     if out is None:
@@ -170,8 +209,10 @@ def year_sweep(rho, deltas, base, adj, cls, shade=None, out=None):
     cls = _cuda(cls, torch.float64).contiguous()
     if shade is not None:
         shade = _cuda(shade, torch.float64, "shade").contiguous()
-    check(_lib.load().snb_year_sweep(*[_ptr(x) for x in ins], _ptr(cls), _ptr(shade), _DT[rho.dtype], N, S, Cn, T, _ptr(out),
-                                     _stream()))
+    if ps_weight is not None:
+        ps_weight = _cuda(ps_weight, rho.dtype, "ps_weight").contiguous()
+    check(_lib.load().snb_year_sweep(*[_ptr(x) for x in ins], _ptr(cls), _ptr(shade), _ptr(ps_weight), _DT[rho.dtype], N, S, Cn, T,
+                                     _ptr(out), _stream()))
     return out
 
 

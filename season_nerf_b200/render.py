@@ -181,8 +181,6 @@ def _scatter(D, size, vals):
 
 def get_imgs_from_Img_Dict(Img_Dict, out_img_size: tuple, use_classic_shadows: bool):
     """mg_Img_Eval.py:123-190: float64 compositing of the cached components into images."""
-    if use_classic_shadows:
-        raise NotImplementedError("use_classic_shadows=True (mg_Img_Eval.py:166-181) is not on the render CLI path")
     has_exact = "Exact_Solar" in Img_Dict.keys()
     keys = ["Rho", "Deltas", "Base_Col", "Est_Solar_Vis", "Adjust_col", "Output_class", "Sky_Col"]
     rho, dl, base, vis, adj, ocl, skyc = _device_components(Img_Dict, keys)
@@ -207,6 +205,17 @@ def get_imgs_from_Img_Dict(Img_Dict, out_img_size: tuple, use_classic_shadows: b
         R["Shadow_Adjust_Exact"] = np.expand_dims(Mask_e, -1) + np.expand_dims(1 - Mask_e, -1) * Sky_Col.reshape([1, 1, 3])
         R["Shadow_Mask_Exact"] = Mask_e
         R["Raw_Shadow_Mask_Exact"] = Raw_e
+    if use_classic_shadows:                                                       # :166-181
+        # per-sample shading vis + (1 - vis) * sky inside the colour sum; the image keeps its name but becomes the ratio
+        # classic / seasonal colour at every rendered pixel
+        (sky_s,) = _device_components(Img_Dict, ["Sky_Col"])
+        ip = Img_Dict["Image_Points"]
+        args = (rho.reshape(N, S), dl.reshape(N, S), base)
+        classic = ops.cli_classic_shadow(*args, vis.reshape(N, S), adj, sky_s, cls.contiguous())
+        R["Shadow_Adjust"][ip[:, 0], ip[:, 1]] = (classic / (season + 1e-8)).cpu().numpy()
+        if has_exact:
+            classic_e = ops.cli_classic_shadow(*args, ev.reshape(N, S), adj, sky_s, cls.contiguous())
+            R["Shadow_Adjust_Exact"][ip[:, 0], ip[:, 1]] = (classic_e / (season + 1e-8)).cpu().numpy()
     return R
 
 

@@ -55,12 +55,18 @@ class TrainStep:
     DSM-guided section (use_prior True, learning_mode 1 with jump_start)."""
 
     def __init__(self, args, device, H, WC, network=None, training_DSM=None, use_prior=False, total_steps=None,
-                 world_size=1, precision="bf16", use_graph=False, graph_warmup=2, micro_batch=None):
+                 world_size=1, precision="bf16", use_graph=False, graph_warmup=2, micro_batch=None, solar_rng="device"):
         """use_graph: after `graph_warmup` eager steps at a given batch size, the whole step (sampling, network forward,
         losses, backward and - single GPU - both Adam updates) is captured once into a CUDA graph and replayed; inputs live
         in static device buffers refreshed before each replay.  The arithmetic and kernel sequence are those of the eager
         step; only the per-step launches stop costing host time.  The DSM-guided section (use_prior) is captured too: its
-        trust factor step / n_steps lives in a device scalar refreshed before each replay."""
+        trust factor step / n_steps lives in a device scalar refreshed before each replay.
+        solar_rng: "device" (default) draws the random solar rays of a step with torch's CUDA generator and builds them in
+        one kernel (Eval_Tools_2.py:72-108 without its 89 us / ray host loop and without the H2D copy); "host" draws them
+        from the reference's numpy / CPU-torch streams in the reference's order.  Injected rays (`solar=`) bypass both."""
+        if solar_rng not in ("device", "host"):
+            raise ValueError("solar_rng must be 'device' or 'host'")
+        self.solar_rng = solar_rng
         self.args, self.device = args, t.device(device)
         self.world_size = world_size
         self.use_graph = bool(use_graph) and self.device.type == "cuda"
@@ -86,6 +92,7 @@ class TrainStep:
             ada = mk(3, .03, 0.01)
             ada_params = list(ada.parameters())
         self.eval_tool = All_in_One_Eval(args, self.device, total_steps, use_prior, ada, H, WC)
+        self.eval_tool.solar_on_device = solar_rng == "device"
         self.params = [p for p in self.network.parameters()]
         self.ada_params = ada_params
         gk = {}
@@ -143,7 +150,10 @@ class TrainStep:
         ts_img = sample_ts(S, False, False, inject.get("jitter"))
         solar = inject.get("solar")
         if solar is None and self.args.Use_Solar:
-            solar = self.eval_tool.solar_creation_tool(n, include_times=True)[:4]
+            if self.solar_rng == "device":
+                solar = self.eval_tool.solar_creation_tool.on_device(n, self.device, include_times=True)
+            else:
+                solar = self.eval_tool.solar_creation_tool(n, include_times=True)[:4]
         ts_sol = sample_ts(S, False, True, inject.get("solar_jitter")) if self.args.Use_Solar else None
         return ts_img, solar, ts_sol
 

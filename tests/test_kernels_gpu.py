@@ -306,3 +306,61 @@ def test_camera_rays_full_size_properties():
     sub = np.arange(0, H * W, 997)
     _, _, gs = so.camera_rays(P, sub // W, sub % W)
     assert np.array_equal(good.cpu().numpy()[sub], gs)
+
+
+def _ulp_diff(a, b):
+    """distance in float32 units in the last place between two float32 arrays"""
+    a = np.ascontiguousarray(a, dtype=np.float32).view(np.int32).astype(np.int64)
+    b = np.ascontiguousarray(b, dtype=np.float32).view(np.int32).astype(np.int64)
+    a = np.where(a < 0, -(a & 0x7FFFFFFF), a)
+    b = np.where(b < 0, -(b & 0x7FFFFFFF), b)
+    return np.abs(a - b)
+
+
+@pytest.mark.parametrize("n", [1, 8, 4097])
+def test_solar_rays_kernel_vs_oracle_same_draws(n):
+    """Eval_Tools_2.py:72-108: the device generator fed with the oracle's own random draws (same numpy / torch generators,
+    same order) returns the oracle's rays: start positions bit-exact, float64 geometry rounded to float32 within 1 ulp."""
+    from oracle import season_oracle as so
+    from season_nerf_b200 import ops
+    WC, H = so.OMA_W2C, so.oma_w2l_h()
+    st, en, vec, tm, az_el = so.create_solar_rays_uniform(n, WC, H, np.random.RandomState(7), t.Generator().manual_seed(7))
+    gen = t.Generator().manual_seed(7)
+    u_xy = t.stack([t.rand(n, generator=gen), t.rand(n, generator=gen)], 1)
+    u_t = t.rand(n, 2, generator=gen)
+    s2, e2, v2, t2 = ops.solar_rays(WC, H, T(az_el), u_xy.cuda(), u_t.cuda())
+    assert np.array_equal(s2.cpu().numpy(), st.numpy())
+    assert _ulp_diff(v2.cpu().numpy(), vec.numpy()).max() <= 1
+    # end points: |xy| reaches ~27 for low suns; 1 ulp of the float32 result
+    assert _ulp_diff(e2.cpu().numpy(), en.numpy()).max() <= 1
+    assert np.array_equal(e2.cpu().numpy()[:, 2], np.full(n, -1.0, dtype=np.float32))
+    assert maxabs(t2, tm) <= 2.4e-7                      # accurate sinf / cosf vs torch CPU on the same float32 argument
+    # without times
+    s3, e3, v3 = ops.solar_rays(WC, H, T(az_el), u_xy.cuda())
+    assert t.equal(s3, s2) and t.equal(e3, e2) and t.equal(v3, v2)
+
+
+def test_solar_rays_kernel_vs_reference_golden_and_device_draws():
+    """sun vectors of the rays the UNMODIFIED reference drew (fixture loss_barron: az_el -> s_sun), then the statistics of
+    create_solor_rays_uniform.on_device (torch CUDA generator): ranges of Eval_Tools_2.py:80,94-95 and reproducibility."""
+    from oracle import season_oracle as so
+    from season_nerf_b200 import ops
+    import season_nerf_b200 as snb
+    g = load_golden("loss_barron")
+    n = g["az_el"].shape[0]
+    u = t.zeros(n, 2, device="cuda")
+    # the fixture keeps the drawn angles as float32 (1e-5 degrees of rounding): compare at that resolution
+    _, _, vec = ops.solar_rays(so.OMA_W2C, so.oma_w2l_h(), T(g["az_el"].astype(np.float64)), u)
+    assert maxabs(vec, g["s_sun"]) < 1e-6
+    tool = snb.create_solor_rays_uniform(so.oma_w2l_h(), so.OMA_W2C)
+    gen = t.Generator(device="cuda").manual_seed(5)
+    s, e, v, tm = tool.on_device(100000, "cuda", include_times=True, generator=gen)
+    assert s.shape == (100000, 3) and e.shape == (100000, 3) and v.shape == (100000, 3) and tm.shape == (100000, 4)
+    assert float(s[:, :2].min()) >= -1 and float(s[:, :2].max()) <= 1 and bool((s[:, 2] == 1).all()) and bool((e[:, 2] == -1).all())
+    assert abs(float(s[:, 0].mean())) < 0.01 and abs(float(s[:, :2].var()) - 1 / 3) < 0.01
+    assert maxabs(v.norm(dim=1), t.ones(100000)) < 1e-6 and float(v[:, 2].min()) > 0          # elevation in [1, 90) degrees
+    assert maxabs(tm[:, 0] ** 2 + tm[:, 1] ** 2, t.ones(100000)) < 1e-6
+    s_b, e_b, v_b, tm_b = tool.on_device(100000, "cuda", include_times=True, generator=t.Generator(device="cuda").manual_seed(5))
+    assert t.equal(s, s_b) and t.equal(e, e_b) and t.equal(v, v_b) and t.equal(tm, tm_b)
+    out0 = tool.on_device(0, "cuda", include_times=True)
+    assert out0[0].shape == (0, 3)

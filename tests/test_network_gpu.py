@@ -275,3 +275,36 @@ def test_seasonal_alignment_search(params0, precision):
     assert abs(best_t - float(g["best_t"])) < (1e-7 if precision == "fp32" else 2.5 / 365)      # bf16 class vectors: +-2 days
     tol = 1e-4 if precision == "fp32" else 3e-2
     assert tuple(sky.shape) == (1, 1, 3) and maxabs(sky, g["sky"]) < tol and maxabs(adj, g["adj_vec"]) < tol
+
+
+def test_classic_shadow_images_and_alignment_golden(params0):
+    """use_classic_shadows=True: get_imgs_from_Img_Dict (mg_Img_Eval.py:166-181) on the REFERENCE's component arrays
+    (float64 arithmetic parity with the unmodified reference), on device-resident components of our own render, and the
+    classic-shadow alignment search (:416-475) - two weighted year-sweep launches - against the reference's result."""
+    import season_nerf_b200 as snb
+    from oracle import season_oracle as so
+    from test_oracle_golden import _align_inputs
+    gc = load_golden("cli_classic")
+    for fx, size, keys in (("cli_render", (5, 6, S), (("Shadow_Adjust", "sa_classic"),)),
+                           ("cli_render_exact", (2, 3, S), (("Shadow_Adjust", "sa_classic_x"), ("Shadow_Adjust_Exact", "sae_classic_x")))):
+        g = load_golden(fx)
+        Dref = {k[2:]: (g[k].astype(np.float64) if g[k].dtype == np.float32 else g[k]) for k in g if k.startswith("d_")}
+        imgs = snb.get_imgs_from_Img_Dict(Dref, size, True)
+        for k, gk in keys:
+            assert maxabs(imgs[k], gc[gk]) < 2e-6, (fx, k, maxabs(imgs[k], gc[gk]))
+        plain = snb.get_imgs_from_Img_Dict(Dref, size, False)
+        assert maxabs(plain["Shadow_Adjust"], imgs["Shadow_Adjust"]) > 1e-3
+        assert maxabs(plain["Season_Adj_Img"], imgs["Season_Adj_Img"]) == 0
+    # device-resident float32 components of our own fp32 render (DeviceImgDict path)
+    net = make_net(params0, "fp32")
+    D = snb.component_render_by_dir(net, [80, 0], [45, 135], 184 / 365, (5, 6, S), so.OMA_W2C, so.oma_w2l_h(),
+                                    t.device("cuda"), include_exact_solar=False)
+    imgs = snb.get_imgs_from_Img_Dict(D, (5, 6, S), True)
+    assert maxabs(imgs["Shadow_Adjust"], gc["sa_classic"]) < 1e-3
+    # alignment
+    g, P, Da = _align_inputs(params0)
+    net = make_net(P, "fp32")
+    adj, sky, best_t = snb.Grad_Descent_Seasonal_Align_v3(Da, g["target"], float(g["t0"]), net, t.device("cuda"),
+                                                          use_classic_shadows=True)
+    assert abs(best_t - float(gc["best_t"])) < 1e-7
+    assert tuple(sky.shape) == (1, 1, 3) and maxabs(sky, gc["sky"]) < 1e-4 and maxabs(adj, gc["adj_vec"]) < 1e-4

@@ -231,3 +231,23 @@ def test_seasonal_align_oracle_matches_reference(params0):
     assert abs(best_t - float(g["best_t"])) < 1e-7 and abs(best_t - float(g["t_star"])) < 1e-6
     assert np.abs(adj.numpy() - g["adj_vec"]).max() < 1e-5 and np.abs(sky.numpy() - g["sky"]).max() < 1e-4
     assert scores.min() < 1e-3 * np.median(scores)                  # the target's own time is a sharp minimum
+
+
+def test_classic_shadow_conventions_oracle_matches_reference(params0):
+    """use_classic_shadows=True of get_imgs_from_Img_Dict (mg_Img_Eval.py:166-181) and _grad_descent_v3_classic_shadows
+    (:416-475): restatements vs the unmodified reference run on the reference's own component arrays."""
+    from oracle import season_oracle as so
+    gc = load_golden("cli_classic")
+    for fx, size, keys in (("cli_render", (5, 6, S), (("Shadow_Adjust", "sa_classic"),)),
+                           ("cli_render_exact", (2, 3, S), (("Shadow_Adjust", "sa_classic_x"), ("Shadow_Adjust_Exact", "sae_classic_x")))):
+        g = load_golden(fx)
+        D = {k[2:]: (g[k].astype(np.float64) if g[k].dtype == np.float32 else g[k]) for k in g if k.startswith("d_")}
+        imgs = so.get_imgs_from_img_dict(D, size, use_classic_shadows=True)
+        for k, gk in keys:
+            np.testing.assert_allclose(imgs[k], gc[gk], rtol=1e-12, atol=1e-14, err_msg=fx + ":" + k)
+        plain = so.get_imgs_from_img_dict(D, size)
+        assert np.abs(plain["Shadow_Adjust"] - imgs["Shadow_Adjust"]).max() > 1e-3       # it is a different image
+    g, P, D = _align_inputs(params0)
+    adj, sky, best_t, _ = so.seasonal_align_v3_classic(P, D, g["target"], float(g["t0"]))
+    assert abs(best_t - float(gc["best_t"])) < 1e-7
+    assert np.abs(adj.numpy() - gc["adj_vec"]).max() < 1e-5 and np.abs(sky.numpy() - gc["sky"]).max() < 1e-4

@@ -145,3 +145,47 @@ def test_graph_step_with_prior_dsm_matches_eager():
     assert len(set(round(x, 6) for x in le)) > 1                # the loss really changes with the trust factor / weights
     for a, b in zip(le, lg):
         assert abs(a - b) <= 2e-3 * max(abs(a), 1e-3), (le, lg)
+
+
+@pytest.mark.parametrize("use_graph,micro_batch", [(False, None), (True, None), (True, 64)])
+def test_device_solar_rng_steps_are_reproducible(use_graph, micro_batch):
+    """TrainStep(solar_rng='device') (the default): the random solar rays of every step are drawn with torch's CUDA
+    generator and built by the solar_rays kernel - nothing on the host.  Same seeds -> same loss trajectory; a different
+    CUDA seed -> different solar rays -> a different solar loss; the batch may still arrive from the host."""
+    import season_nerf_b200 as snb
+    from oracle import season_oracle as so
+
+    def run(cuda_seed):
+        t.manual_seed(0)
+        t.cuda.manual_seed(cuda_seed)
+        ts = snb.TrainStep(_args(), t.device("cuda"), so.oma_w2l_h(), so.OMA_W2C, use_graph=use_graph, graph_warmup=1,
+                           micro_batch=micro_batch)
+        assert ts.solar_rng == "device" and ts.eval_tool.solar_on_device
+        batch = so.synthetic_batch(192, seed=1, n_images=5)                    # host tensors
+        out = []
+        for i in range(4):
+            jit = t.rand(S, generator=t.Generator().manual_seed(20 + i))
+            L = ts.step(batch, i, jitter=jit, solar_jitter=jit)
+            out.append((float(L["Solar_Correction"][0]), float(ts.last_loss)))
+        return out
+
+    a, b, c = run(11), run(11), run(12)
+    assert all(np.isfinite(v) for pair in a for v in pair)
+    for (sa, ta), (sb, tb) in zip(a, b):
+        assert abs(sa - sb) <= 2e-3 * abs(sa) + 1e-6 and abs(ta - tb) <= 2e-3 * abs(ta) + 1e-6
+    assert any(abs(x[0] - y[0]) > 1e-4 * abs(x[0]) for x, y in zip(a, c))
+
+
+def test_host_solar_rng_still_follows_the_reference_streams():
+    """solar_rng='host': numpy / CPU-torch global streams in the reference's order (Eval_Tools_2.py:72-108) - the same
+    seeds give the rays the oracle draws"""
+    import season_nerf_b200 as snb
+    from oracle import season_oracle as so
+    ts = snb.TrainStep(_args(), t.device("cuda"), so.oma_w2l_h(), so.OMA_W2C, solar_rng="host")
+    assert not ts.eval_tool.solar_on_device
+    np.random.seed(4)
+    t.manual_seed(4)
+    _, solar, _ = ts._draw_inputs(16, {"jitter": t.zeros(S), "solar_jitter": t.zeros(S)})
+    ref = so.create_solar_rays_uniform(16, so.OMA_W2C, so.oma_w2l_h(), np.random.RandomState(4), t.Generator().manual_seed(4))
+    for x, y in zip(solar, ref[:4]):
+        assert maxabs(x, y) < 1e-6
