@@ -62,6 +62,14 @@ def get_PV(Rhos, Deltas):
     return PV.reshape(N, S, 1).to(Rhos.dtype)
 
 
+def owns_global_min(local_min):
+    """1.0 where this rank's per-channel batch minimum is the minimum over all data-parallel ranks, else 0.0 (no gradient)"""
+    import torch.distributed as dist
+    g_min = local_min.detach().clone()
+    dist.all_reduce(g_min, op=dist.ReduceOp.MIN)
+    return (local_min.detach() == g_min).float()
+
+
 class create_solor_rays_uniform():
     """Eval_Tools_2.py:42-108 with the per-ray Python loop vectorised (same RNG draws in the same order)."""
 
@@ -134,6 +142,9 @@ class All_in_One_Eval():
         # False (default): solar rays are drawn on the host from the reference's RNG streams, in the reference's order.
         # True: drawn and built on the device (create_solor_rays_uniform.on_device) - no host work, no H2D copy.
         self.solar_on_device = False
+        # > 1: the batch of a step is spread over this many data-parallel ranks (train.TrainStep(sync_bn=True)); the one loss
+        # term that is not a mean over rays - the per-channel minimum of Albedo_Color (:374-377) - is then taken over all ranks
+        self.sync_world = 1
         self.Sigmoid = t.nn.Sigmoid()
         self.BCE_loss = t.nn.BCELoss()
 
@@ -321,6 +332,10 @@ class All_in_One_Eval():
                 alb = out["Albedo_Color"]
                 sk_alb, _ = t.min(alb, 0)
                 m = (sk_alb < .2).float()           # branch-free: no host sync (.item() stalls)
+                if self.sync_world > 1 and train_mode:
+                    # global minimum: only the rank that owns it contributes (the mean over ranks of the gradient
+                    # all-reduce then equals the single-batch term  sum_c (1 - min_c/.2)^2 / N_total)
+                    m = m * owns_global_min(sk_alb)
                 alb_loss = t.sum(m * (1. - sk_alb / .2) ** 2) / alb.shape[0]
                 sk = (out["Sky_Col"] - .5) / .5
                 sk_loss = t.sum(t.relu(sk) ** 2) / float(np.prod(sk.shape))

@@ -44,6 +44,20 @@ def const_vec(n, value, device):
     return v
 
 
+def _sync_world(net):
+    """world size of a BatchNorm-synchronised data-parallel run (train.TrainStep(sync_bn=True)), else 1"""
+    w = getattr(net, "_sync_bn", None)
+    return int(w) if w else 1
+
+
+def _allreduce_pair(a, b):
+    """column statistics of all ranks: one small all-reduce (sum) of the stacked pair -> (a_all, b_all)"""
+    import torch.distributed as dist
+    pair = t.stack([a, b])
+    dist.all_reduce(pair, op=dist.ReduceOp.SUM)
+    return pair[0], pair[1]
+
+
 def side_stream(key):
     """one lazily created side stream per (purpose, parent stream)"""
     st = _side_streams.get(key)
@@ -571,6 +585,12 @@ class _Pass:
         bn = layer.norm
         if training:
             s, ss = stats if stats is not None else ops.col_stats(Z)
+            world = _sync_world(self.net)
+            if world > 1:
+                # SyncBN: the batch of a data-parallel step is the union of the ranks' rays (equal shards): sums of z and
+                # z^2 over all ranks, so that every rank normalises with - and stores - the same statistics
+                s, ss = _allreduce_pair(s, ss)
+                rows = rows * world
             with t.no_grad():
                 # two passes of one step may run on parallel streams: the running statistics of a module are updated in
                 # program order (image pass, then solar pass - misc.py:169-170 is not commutative in the momentum update)
@@ -659,9 +679,12 @@ class _Pass:
                     sg, sgx = fused
                     dZ = dY
                     if sp.layer.has_bn:
-                        self._acc(grads, sp.layer.norm.weight, sgx)
+                        self._acc(grads, sp.layer.norm.weight, sgx)      # local sums: the gradient all-reduce adds the ranks
                         self._acc(grads, sp.layer.norm.bias, sg)
-                        ops.bn_bwd_apply(dY, Z, a, mean, invstd, sg, sgx, dZ, scale=(1.0 / rows) if bn_train else 0.0)
+                        world = _sync_world(net) if bn_train else 1
+                        if world > 1:
+                            sg, sgx = _allreduce_pair(sg, sgx)           # SyncBN backward: batch means over all ranks
+                        ops.bn_bwd_apply(dY, Z, a, mean, invstd, sg, sgx, dZ, scale=(1.0 / (rows * world)) if bn_train else 0.0)
                     else:
                         fused_db = sg
                 elif bn_train:
@@ -670,8 +693,11 @@ class _Pass:
                     bn = sp.layer.norm
                     self._acc(grads, bn.weight, sgx.float())
                     self._acc(grads, bn.bias, sg.float())
-                    ops.sine_bwd_apply(dY, Z, a, c, dZ, mean, invstd, (sg / rows).float().contiguous(),
-                                       (sgx / rows).float().contiguous())
+                    world = _sync_world(net)
+                    if world > 1:
+                        sg, sgx = _allreduce_pair(sg, sgx)
+                    ops.sine_bwd_apply(dY, Z, a, c, dZ, mean, invstd, (sg / (rows * world)).float().contiguous(),
+                                       (sgx / (rows * world)).float().contiguous())
                 else:
                     dZ = t.empty(rows, n_out, device=dev, dtype=dt)
                     if sp.layer.has_bn:  # eval-mode BN: plain affine, parameters still get gradients

@@ -55,7 +55,8 @@ class TrainStep:
     DSM-guided section (use_prior True, learning_mode 1 with jump_start)."""
 
     def __init__(self, args, device, H, WC, network=None, training_DSM=None, use_prior=False, total_steps=None,
-                 world_size=1, precision="bf16", use_graph=False, graph_warmup=2, micro_batch=None, solar_rng="device"):
+                 world_size=1, precision="bf16", use_graph=False, graph_warmup=2, micro_batch=None, solar_rng="device",
+                 sync_bn=False):
         """use_graph: after `graph_warmup` eager steps at a given batch size, the whole step (sampling, network forward,
         losses, backward and - single GPU - both Adam updates) is captured once into a CUDA graph and replayed; inputs live
         in static device buffers refreshed before each replay.  The arithmetic and kernel sequence are those of the eager
@@ -63,7 +64,11 @@ class TrainStep:
         trust factor step / n_steps lives in a device scalar refreshed before each replay.
         solar_rng: "device" (default) draws the random solar rays of a step with torch's CUDA generator and builds them in
         one kernel (Eval_Tools_2.py:72-108 without its 89 us / ray host loop and without the H2D copy); "host" draws them
-        from the reference's numpy / CPU-torch streams in the reference's order.  Injected rays (`solar=`) bypass both."""
+        from the reference's numpy / CPU-torch streams in the reference's order.  Injected rays (`solar=`) bypass both.
+        sync_bn (world_size > 1): BatchNorm batch statistics - forward sums and the two backward sums of every layer - and
+        the batch minimum of the Albedo_Color term are all-reduced over the ranks, so that N ranks with B/N rays each take
+        the step the reference takes on one device with B rays (SURVEY 8e caveats 1-2); without it each rank normalises
+        with its own shard (DistributedDataParallel semantics).  Ranks must hold equal numbers of rays."""
         if solar_rng not in ("device", "host"):
             raise ValueError("solar_rng must be 'device' or 'host'")
         self.solar_rng = solar_rng
@@ -93,6 +98,12 @@ class TrainStep:
             ada_params = list(ada.parameters())
         self.eval_tool = All_in_One_Eval(args, self.device, total_steps, use_prior, ada, H, WC)
         self.eval_tool.solar_on_device = solar_rng == "device"
+        self.sync_bn = bool(sync_bn) and world_size > 1
+        if self.sync_bn:
+            if micro_batch:
+                raise ValueError("sync_bn and micro_batch do not combine: a micro-batch is its own BatchNorm batch")
+            self.network._sync_bn = world_size
+            self.eval_tool.sync_world = world_size
         self.params = [p for p in self.network.parameters()]
         self.ada_params = ada_params
         gk = {}

@@ -39,6 +39,15 @@ def _worker(rank, world, port, q):
     full = t.arange(n * 3, dtype=t.float32).reshape(n, 3)
     out = gather_rows(full[lo:hi].clone(), n, rank, world)
     ok = ok and t.equal(out, full)
+    # SyncBN plumbing: column statistics summed over the ranks; the Albedo_Color minimum is owned by exactly one rank
+    from season_nerf_b200.network import _allreduce_pair
+    from season_nerf_b200.engine import owns_global_min
+    a, b = t.full((5,), float(rank + 1)), t.arange(5.) * (rank + 1)
+    sa, sb = _allreduce_pair(a, b)
+    ok = ok and t.equal(sa, t.full((5,), 3.0)) and t.equal(sb, t.arange(5.) * 3) and t.equal(a, t.full((5,), float(rank + 1)))
+    local_min = t.tensor([[0.10, 0.30, 0.05], [0.12, 0.25, 0.07]][rank])
+    own = owns_global_min(local_min)
+    ok = ok and t.equal(own, t.tensor([[1., 0., 1.], [0., 1., 0.]][rank]))
     q.put((rank, bool(ok), (lo, hi)))
     dist.destroy_process_group()
 
