@@ -148,7 +148,7 @@ def run_reference(a):
                       "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
-def cpu_baseline(n_rays=256):
+def cpu_baseline(n_rays=512):
     """oracle train step timed on the host cores (rank 0, N=1): ~10-30 s of CPU work."""
     import numpy as np
     import torch as t
@@ -164,7 +164,7 @@ def cpu_baseline(n_rays=256):
     st, en, vec, tm, _ = so.create_solar_rays_uniform(n_rays, so.OMA_W2C, so.oma_w2l_h(), np.random.RandomState(3),
                                                       t.Generator().manual_seed(3))
     best = None
-    for i in range(3):
+    for i in range(4):
         t0 = time.perf_counter()
         L, _ = so.get_loss(args, batch, P, 30, True, ada, solar=(st, en, vec, tm))
         for v in leaves:
@@ -174,7 +174,7 @@ def cpu_baseline(n_rays=256):
         if i > 0:
             best = dt if best is None else min(best, dt)
     return {"value": n_rays / best, "unit": "rays/s", "cores": cores, "kind": "port",
-            "sample": "%d image + %d solar rays, one train step (fwd+bwd), best of 2 after 1 warm-up, torch CPU fp32 oracle" % (n_rays, n_rays)}
+            "sample": "%d image + %d solar rays, one train step (fwd+bwd), best of 3 after 1 warm-up, torch CPU fp32 oracle" % (n_rays, n_rays)}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -204,7 +204,7 @@ def run_ours(a):
 
     t.manual_seed(0)
     ts = snb.TrainStep(args, dev, H, W2C, world_size=world, precision=a.precision, use_graph=not a.no_graph,
-                       micro_batch=a.micro_batch)
+                       micro_batch=a.micro_batch, sync_bn=a.sync_bn)
     if world > 1:                                     # identical initial weights on every rank
         for p_ in ts.params + ts.ada_params:
             dist.broadcast(p_.data, 0)
@@ -370,7 +370,10 @@ def run_ours(a):
                                   "losses, Adam+OneCycle (BASELINE.json configs[%d])" % (n, n, 3 if n >= 65536 else 1),
                       "rays_per_gpu": n, "micro_batch": a.micro_batch, "samples_per_ray": S, "weights": "random-init T_NeRF(512,4)",
                       "launch": "eager" if a.no_graph else "whole step captured once in a CUDA graph, replayed per step",
-                      "l2": "per-step working set (~10 GB of activations) far exceeds the 126 MB L2; no explicit flush"},
+                      "l2": "per-step working set (~10 GB of activations) far exceeds the 126 MB L2; no explicit flush",
+                      "solar_rays": "drawn and built on the device every step (TrainStep solar_rng='device')",
+                      "batchnorm": ("SyncBN: statistics over the rays of all ranks" if (a.sync_bn and world > 1) else
+                                    "per-rank batch statistics (DDP semantics)" if world > 1 else "one batch")},
            "clocks": clocks, "gpu_launches": int(launches),
            "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                    "ms_per_step": ms_e / a.steps},
@@ -479,10 +482,16 @@ def bench_render(snb, net, dev, H, W2C, peaks, size=512, reps=3):
     peak = peaks["bf16_tflops"]
     return {"workload": "%dx%dx%d view render, estimated shadows (BASELINE.json configs[2] without the exact march)" % (size, size, S),
             "kernel_rays_per_s": pts_total / S / (k_ms * 1e-3), "e2e_rays_per_s": N / e2e_s,
-            "roofline": {"bound": "tensor", "kernel": "fused_eval_kernel (tcgen05)", "achieved": achieved, "peak": peak,
-                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "tensor", "kernel": "fused_eval2_kernel (tcgen05 cta_group::2)", "achieved": achieved, "peak": peak,
+                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": 461.2e6,
                          "peak_source": peaks["source"] + " burst cuBLAS bf16", "launches": len(times),
-                         "ms_per_launch": k_ms / len(times)}}
+                         "ms_per_launch": k_ms / len(times),
+                         "frac_of_sustained_peak": achieved / peaks["bf16_tflops_sustained"],
+                         "note": "%d back-to-back launches of ~35 ms run into the board power cap (first launch after idle: "
+                                 "~1.2 PFLOP/s); frac is quoted against the BURST cuBLAS peak, frac_of_sustained_peak against "
+                                 "cuBLAS running back to back for seconds.  traffic: dram bytes of one 6.29 M-point launch "
+                                 "(ncu, profiles/r01_ncu_fused_eval2_v3.txt): 85 MB read + 376 MB written vs 503 MB "
+                                 "algorithmic (12 B in + 68 B out per point)" % len(times)}}
 
 
 def main():
@@ -501,6 +510,8 @@ def main():
     ap.add_argument("--micro-batch", type=int, default=None, dest="micro_batch",
                     help="rays per micro-batch (gradient accumulation; each chunk is its own BatchNorm batch) - needed for "
                          "--rays 65536 (BASELINE.json configs[3]): one 65536-ray BatchNorm batch would need ~225 GB of activations")
+    ap.add_argument("--sync-bn", action="store_true", dest="sync_bn",
+                    help="N > 1: BatchNorm statistics over the rays of all ranks (the reference's single-batch semantics)")
     ap.add_argument("--no-graph", action="store_true", help="eager kernel launches instead of the captured CUDA graph")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else max(a.warmup, 1)

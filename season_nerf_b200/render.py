@@ -48,6 +48,57 @@ class DeviceImgDict(dict):
         dict.__setitem__(self, k, v)
 
 
+_STAGE = {}
+
+
+def device_to_numpy(x, chunk_bytes=128 << 20, threads=4):
+    """Large device tensor -> numpy array of the same dtype / shape.  `x.cpu()` of a multi-GB result (the [T,H,W,3] float64
+    year sweep is 9.2 GB at 365 x 1024^2) runs at ~2 GB/s: it copies through an internal staging buffer into freshly
+    mapped pageable memory, page fault by page fault, on one thread.  Here the device->host copy goes through two cached
+    PINNED staging buffers (asynchronous, PCIe rate) and a few host threads move each landed chunk into the destination
+    (first touch in parallel) while the next chunk is in flight."""
+    x = x.detach().contiguous()
+    nbytes = x.numel() * x.element_size()
+    if nbytes < (64 << 20) or not x.is_cuda:
+        return x.cpu().numpy()
+    from concurrent.futures import ThreadPoolExecutor
+    key = (x.device.index, chunk_bytes)
+    if key not in _STAGE:
+        _STAGE[key] = ([t.empty(chunk_bytes, dtype=t.uint8).pin_memory() for _ in range(2)], ThreadPoolExecutor(max_workers=threads))
+    stage, pool = _STAGE[key]
+    out = np.empty(tuple(x.shape), dtype=t.empty(0, dtype=x.dtype).numpy().dtype)
+    dst = out.reshape(-1).view(np.uint8)
+    src = x.reshape(-1).view(t.uint8)
+    stage_np = [b.numpy() for b in stage]
+    stream = t.cuda.current_stream(x.device)
+    pending = [[], []]                 # host copies still reading staging buffer 0 / 1
+    events = [None, None]
+    spans = [(a, min(a + chunk_bytes, nbytes)) for a in range(0, nbytes, chunk_bytes)]
+
+    def drain(j, a, b):
+        events[j].synchronize()
+        n = b - a
+        step = (n + threads - 1) // threads
+        step = (step + 4095) // 4096 * 4096
+        pending[j] = [pool.submit(np.copyto, dst[a + o:a + min(o + step, n)], stage_np[j][o:min(o + step, n)])
+                      for o in range(0, n, step)]
+
+    for i, (a, b) in enumerate(spans):
+        j = i & 1
+        for f in pending[j]:
+            f.result()                 # the buffer's previous contents have left
+        stage[j][:b - a].copy_(src[a:b], non_blocking=True)
+        events[j] = t.cuda.Event()
+        events[j].record(stream)
+        if i > 0:
+            drain(j ^ 1, *spans[i - 1])
+    drain((len(spans) - 1) & 1, *spans[-1])
+    for j in (0, 1):
+        for f in pending[j]:
+            f.result()
+    return out
+
+
 def _points_per_call(the_network):
     return 1 << 22 if getattr(the_network, "_fused_ready", lambda: False)() else 1 << 19
 
@@ -241,10 +292,10 @@ def get_imgs_from_Img_Dict_t_step(Img_Dict, out_img_size: tuple, class_vecs_arra
     cols = ops.year_sweep(rho.reshape(N, S), dl.reshape(N, S), base, adj, cls, shade=shade)        # [T,N,3]
     ip = np.asarray(Img_Dict["Image_Points"])
     if _is_raster_grid(ip, H, W):
-        return cols.cpu().numpy().reshape(T, H, W, 3)
+        return device_to_numpy(cols).reshape(T, H, W, 3)
     imgs = t.full((T, H * W, 3), float("nan"), device=cols.device, dtype=t.float64)
     imgs[:, t.as_tensor(ip[:, 0] * W + ip[:, 1], device=cols.device)] = cols
-    return imgs.cpu().numpy().reshape(T, H, W, 3)
+    return device_to_numpy(imgs).reshape(T, H, W, 3)
 
 
 # ---- ray-sharded rendering over the GPUs of one box (the reference is single-device) ---------------------------

@@ -364,3 +364,17 @@ def test_solar_rays_kernel_vs_reference_golden_and_device_draws():
     assert t.equal(s, s_b) and t.equal(e, e_b) and t.equal(v, v_b) and t.equal(tm, tm_b)
     out0 = tool.on_device(0, "cuda", include_times=True)
     assert out0[0].shape == (0, 3)
+
+
+def test_device_to_numpy_large_results_are_bit_identical():
+    """render.device_to_numpy (pinned staging + parallel host copies, used for the multi-GB year-sweep result)"""
+    from season_nerf_b200.render import device_to_numpy
+    g = t.Generator(device="cuda").manual_seed(0)
+    x = t.rand(7, 1200007, 1, device="cuda", dtype=t.float64, generator=g)          # 67 MB, ragged chunk tail
+    for chunk in (16 << 20, 5000000, 128 << 20):
+        y = device_to_numpy(x, chunk_bytes=chunk, threads=3)
+        assert y.dtype == np.float64 and y.shape == (7, 1200007, 1) and np.array_equal(y, x.cpu().numpy())
+    small = t.arange(10, device="cuda", dtype=t.float32)
+    assert np.array_equal(device_to_numpy(small), np.arange(10, dtype=np.float32))
+    xf = t.rand(3, 6000000, device="cuda", generator=g)                             # float32, 72 MB
+    assert np.array_equal(device_to_numpy(xf, chunk_bytes=32 << 20), xf.cpu().numpy())
