@@ -20,6 +20,7 @@
 //   empty[s]  each CTA; released by tcgen05.commit multicast from the leader's MMA thread
 //   tfull[a]  each CTA; accumulator stage complete (commit multicast)
 //   tempty[a] leader only; 8 arrivals = 4 epilogue warps x 2 CTAs (remote mbarrier.arrive from the peer)
+#include <cstdlib>
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "api.h"
@@ -34,7 +35,11 @@ constexpr int k2BK = 64;
 // warps: 0 = TMA producer, 1 = MMA issuer, 2.. = epilogue (4 warps; 8 for the input-gradient epilogue kEpi 2, whose
 // per-element work (cos, BatchNorm-backward sums) would otherwise outlast the main loop: two warps per TMEM lane quarter,
 // each taking half of the tile's 64-column chunks)
-__host__ __device__ constexpr int k2_epi_warps(int epi) { return epi == 2 ? 8 : 4; }
+// kEpi 3 = kEpi 0 with 8 epilogue warps: the forward GEMM with fused BatchNorm statistics (measured on the trunk shape:
+// 205 -> 197 us inside a training step; the same change for the sin epilogue, kEpi 1, measured 248 -> 253 us and was
+// dropped.  For reference, cuBLAS and the plain-store kernel both take 179 us on this shape, scripts/gemm_probe.py.)
+__host__ __device__ constexpr int k2_epi_warps(int epi) { return epi >= 2 ? 8 : 4; }
+__host__ __device__ constexpr int k2_base_epi(int epi) { return epi == 3 ? 0 : epi; }
 __host__ __device__ constexpr int k2_threads(int epi) { return 64 + 32 * k2_epi_warps(epi); }
 constexpr int k2MaxBN = 256;
 constexpr uint32_t k2ABytes = k2BM * k2BK * 2;                 // 16 KB
@@ -78,16 +83,18 @@ struct Gemm2Params {
   const float* einvstd;
 };
 
-template <bool kAT, bool kBT, int kEpi>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2_threads(kEpi), 1)
+template <bool kAT, bool kBT, int kEpiT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2_threads(kEpiT), 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                   const __grid_constant__ CUtensorMap tmapC, const __grid_constant__ CUtensorMap tmapX,
                   const Gemm2Params p) {
-  constexpr int k2Stages = k2_stages(kEpi);
-  constexpr int kEpiWarps = k2_epi_warps(kEpi);
-  constexpr int k2Threads = k2_threads(kEpi);
-  constexpr uint32_t kCBytes = k2_cbytes(kEpi);
-  constexpr uint32_t kXBytes = k2_xbytes(kEpi);
+  constexpr int kEpi = k2_base_epi(kEpiT);          // epilogue arithmetic; kEpiT also selects the warp count / staging
+  constexpr int k2Stages = k2_stages(kEpiT);
+  constexpr int kEpiWarps = k2_epi_warps(kEpiT);
+  constexpr int k2Threads = k2_threads(kEpiT);
+  constexpr uint32_t kCBytes = k2_cbytes(kEpiT);
+  constexpr uint32_t kXBytes = k2_xbytes(kEpiT);
+
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -442,7 +449,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
             for (int tnn = 0; tnn < 2; ++tnn)
 #pragma unroll
               for (int cc = 0; cc < 4; ++cc)
-                if (tn == tnn && c == 64 * cc) {
+                if (tn == tnn && c == c_begin + 64 * cc) {
                   st_acc[tnn][cc][0] += s0, st_acc[tnn][cc][1] += s1;
                   st_acc[tnn][cc][2] += q0, st_acc[tnn][cc][3] += q1;
                 }
@@ -648,6 +655,7 @@ int snb_gemm_bf16_tc2(const void* A, int lda, int a_t, const void* B, int ldb, i
   } while (0)
   if (epi == 1) SNB_LAUNCH_GEMM2(false, false, 1);
   else if (epi == 2) SNB_LAUNCH_GEMM2(false, true, 2);
+  else if (!a_t && !b_t && stats) SNB_LAUNCH_GEMM2(false, false, 3);      // forward + BatchNorm statistics: 8 epilogue warps
   else if (!a_t && !b_t) SNB_LAUNCH_GEMM2(false, false, 0);
   else if (!a_t && b_t) SNB_LAUNCH_GEMM2(false, true, 0);
   else if (a_t && !b_t) SNB_LAUNCH_GEMM2(true, false, 0);
