@@ -92,6 +92,8 @@ def solar_rays(world_center, W2L_H, az_el, u_xy, u_time=None, out=None):
     for x in (starts, ends, vec, times):
         if x is not None and not (x.is_cuda and x.is_contiguous() and x.dtype == torch.float32 and x.shape[0] == n):
             raise ValueError("solar_rays: out tensors must be contiguous float32 CUDA tensors with n rows")
+    if n == 0:                                   # empty tensors have no data pointer to hand over
+        return (starts, ends, vec, times) if u_time is not None else (starts, ends, vec)
     wc = (C.c_double * 3)(*[float(v) for v in np.asarray(world_center, dtype=np.float64).reshape(3)])
     Hm = (C.c_double * 16)(*np.asarray(W2L_H, dtype=np.float64).reshape(16).tolist())
     check(_lib.load().snb_solar_rays(wc, Hm, _ptr(az_el), _ptr(u_xy), _ptr(u_time), n, _ptr(starts), _ptr(ends), _ptr(vec),
