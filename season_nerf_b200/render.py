@@ -327,25 +327,42 @@ def render_shard(the_network, view_el_az, sun_el_az, time_frac, out_img_size, W2
         off = t.tensor(view_vec / view_vec[2], dtype=t.float64, device=device)
         lin_h = t.tensor(np.linspace(1, -1, H), dtype=t.float64, device=device)
         lin_w = t.tensor(np.linspace(-1, 1, W), dtype=t.float64, device=device)
-        idx = t.arange(lo, hi, device=device)
-        xyz = t.stack([lin_h[idx // W], lin_w[idx % W], t.zeros(hi - lo, dtype=t.float64, device=device)], 1)
-        tops, bots = (xyz + off).float(), (xyz - off).float()
-        D = _internal_render(the_network, tops, bots, sun_vec, time_frac, out_img_size, 150000,
-                             include_exact_solar, device)
-        keys = ["Rho", "Deltas", "Base_Col", "Est_Solar_Vis", "Adjust_col", "Output_class", "Sky_Col"]
-        rho, dl, base, vis, adj, ocl, skyc = [D.dev[k] for k in keys]
-        n, S = rho.shape[0], rho.shape[1]
-        ev = D.dev["Exact_Solar"].reshape(n, S) if include_exact_solar else None
-        sky0 = skyc[0, 0].double()
-        cls0 = ocl[0, 0].double().contiguous() if class_vecs is None else \
-            t.as_tensor(np.asarray(class_vecs), dtype=t.float64).to(rho.device)[0].contiguous()
-        _, season, _, raw, raw_e = ops.cli_composite(rho.reshape(n, S), dl.reshape(n, S), base, vis.reshape(n, S), adj, cls0, ev)
-        mask = t.sigmoid(((raw_e if include_exact_solar else raw) - .2) * 30)
-        shade = (mask.unsqueeze(1) + (1 - mask.unsqueeze(1)) * sky0.reshape(1, 3)).contiguous()
-        if class_vecs is None:
-            return lo, hi, season * shade, mask
-        cls = t.as_tensor(np.asarray(class_vecs), dtype=t.float64).to(rho.device).contiguous()
-        return lo, hi, ops.year_sweep(rho.reshape(n, S), dl.reshape(n, S), base, adj, cls, shade=shade), mask
+        # the shard is rendered and composited in blocks of rays: the per-sample component arrays of a block (28 floats per
+        # sample point, 11 GB for a whole 1024^2 view) are consumed by the compositing kernels right away and never kept
+        block = max(1, _points_per_call(the_network) // out_img_size[2])
+        if include_exact_solar:
+            block = max(1, min(block, 16384))
+        cls_all = None if class_vecs is None else t.as_tensor(np.asarray(class_vecs), dtype=t.float64).to(device).contiguous()
+        rgb_parts, mask_parts = [], []
+        for b0 in range(lo, max(hi, lo + 1), block):
+            b1 = min(b0 + block, hi)
+            idx = t.arange(b0, b1, device=device)
+            xyz = t.stack([lin_h[idx // W], lin_w[idx % W], t.zeros(b1 - b0, dtype=t.float64, device=device)], 1)
+            tops, bots = (xyz + off).float(), (xyz - off).float()
+            D = _internal_render(the_network, tops, bots, sun_vec, time_frac, out_img_size, 150000, include_exact_solar, device)
+            keys = ["Rho", "Deltas", "Base_Col", "Est_Solar_Vis", "Adjust_col", "Output_class", "Sky_Col"]
+            rho, dl, base, vis, adj, ocl, skyc = [D.dev[k] for k in keys]
+            n, S = rho.shape[0], rho.shape[1]
+            if n == 0:
+                rgb_parts.append(t.zeros((0, 3) if cls_all is None else (cls_all.shape[0], 0, 3), dtype=t.float64, device=device))
+                mask_parts.append(t.zeros(0, dtype=t.float64, device=device))
+                break
+            ev = D.dev["Exact_Solar"].reshape(n, S) if include_exact_solar else None
+            sky0 = skyc[0, 0].double()                  # sun direction and time are those of the whole image: every ray's
+            cls0 = ocl[0, 0].double().contiguous() if cls_all is None else cls_all[0].contiguous()      # value = ray 0's
+            _, season, _, raw, raw_e = ops.cli_composite(rho.reshape(n, S), dl.reshape(n, S), base, vis.reshape(n, S), adj, cls0, ev)
+            mask = t.sigmoid(((raw_e if include_exact_solar else raw) - .2) * 30)
+            shade = (mask.unsqueeze(1) + (1 - mask.unsqueeze(1)) * sky0.reshape(1, 3)).contiguous()
+            mask_parts.append(mask)
+            if cls_all is None:
+                rgb_parts.append(season * shade)
+            else:
+                rgb_parts.append(ops.year_sweep(rho.reshape(n, S), dl.reshape(n, S), base, adj, cls_all, shade=shade))
+            del D
+        cat_dim = 0 if cls_all is None else 1
+        rgb = rgb_parts[0] if len(rgb_parts) == 1 else t.cat(rgb_parts, cat_dim)
+        mask = mask_parts[0] if len(mask_parts) == 1 else t.cat(mask_parts, 0)
+        return lo, hi, rgb, mask
 
 
 def render_image_sharded(the_network, view_el_az, sun_el_az, time_frac, out_img_size, W2C, W2L_H, device, rank=0,
