@@ -356,10 +356,10 @@ def run_ours(a):
 
     # per-variant view of the same kernel on the trunk shape of this workload (M = rays*96 rows, 512 x 512), timed live;
     # `traffic` = dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of that variant at M = 393216 from the
-    # ncu --set full capture committed as profiles/r01_ncu_gemm2_variants_v3.txt (scripts/profile_gpu.sh step 2)
+    # ncu --set full capture committed as profiles/r01_ncu_gemm2_variants_v4.txt (scripts/profile_gpu.sh step 2)
     if not a.no_trunk:
-        roofline["trunk_launches"] = bench_trunk_gemms(min(n, a.micro_batch or n) * S, peak, {"fwd_bn_stats": 762.7e6, "fwd_sin": 1152.3e6,
-                                                                      "dgrad_cos_bnsums": 1178.6e6, "wgrad_splitk": 823.3e6})
+        roofline["trunk_launches"] = bench_trunk_gemms(min(n, a.micro_batch or n) * S, peak, {"fwd_bn_stats": 760.9e6, "fwd_sin": 1153.3e6,
+                                                                      "dgrad_cos_bnsums": 1182.5e6, "wgrad_splitk": 823.7e6})
     roofline["traffic_note"] = "achieved aggregates the 92 GEMM launches of a step; per-launch dram traffic of the four variants " \
                                "(ncu) is under trunk_launches, next to their algorithmic bytes"
 
@@ -483,14 +483,14 @@ def bench_render(snb, net, dev, H, W2C, peaks, size=512, reps=3):
     return {"workload": "%dx%dx%d view render, estimated shadows (BASELINE.json configs[2] without the exact march)" % (size, size, S),
             "kernel_rays_per_s": pts_total / S / (k_ms * 1e-3), "e2e_rays_per_s": N / e2e_s,
             "roofline": {"bound": "tensor", "kernel": "fused_eval2_kernel (tcgen05 cta_group::2)", "achieved": achieved, "peak": peak,
-                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": 461.2e6,
+                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": 460.3e6,
                          "peak_source": peaks["source"] + " burst cuBLAS bf16", "launches": len(times),
                          "ms_per_launch": k_ms / len(times),
                          "frac_of_sustained_peak": achieved / peaks["bf16_tflops_sustained"],
                          "note": "%d back-to-back launches of ~35 ms run into the board power cap (first launch after idle: "
                                  "~1.2 PFLOP/s); frac is quoted against the BURST cuBLAS peak, frac_of_sustained_peak against "
                                  "cuBLAS running back to back for seconds.  traffic: dram bytes of one 6.29 M-point launch "
-                                 "(ncu, profiles/r01_ncu_fused_eval2_v3.txt): 85 MB read + 376 MB written vs 503 MB "
+                                 "(ncu, profiles/r01_ncu_fused_eval2_v4.txt): 85 MB read + 376 MB written vs 503 MB "
                                  "algorithmic (12 B in + 68 B out per point)" % len(times)}}
 
 
