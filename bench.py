@@ -349,7 +349,7 @@ def run_ours(a):
     achieved = flops_step / (gemm_ms * 1e-3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
     roofline = {"bound": "tensor", "kernel": "gemm2_bf16_kernel (tcgen05 cta_group::2, fused SIREN epilogues)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peaks["source"] + " sustained cuBLAS bf16",
+                "frac": achieved / peak, "traffic": 978.0e6, "peak_source": peaks["source"] + " sustained cuBLAS bf16",
                 "launches_per_step": n_gemm, "kernel_ms_per_step": gemm_ms, "step_ms": ms / a.steps,
                 "kernel_share_of_step": gemm_ms / (ms / a.steps),
                 "note": "achieved = algorithmic 2.086 GFLOP/ray-pair x rays per step / summed CUDA-event time of the GEMM launches of one step"}
@@ -360,8 +360,9 @@ def run_ours(a):
     if not a.no_trunk:
         roofline["trunk_launches"] = bench_trunk_gemms(min(n, a.micro_batch or n) * S, peak, {"fwd_bn_stats": 760.9e6, "fwd_sin": 1153.3e6,
                                                                       "dgrad_cos_bnsums": 1182.5e6, "wgrad_splitk": 823.7e6})
-    roofline["traffic_note"] = "achieved aggregates the 92 GEMM launches of a step; per-launch dram traffic of the four variants " \
-                               "(ncu) is under trunk_launches, next to their algorithmic bytes"
+    roofline["traffic_note"] = "achieved aggregates all tcgen05 GEMM launches of a step; traffic = dram bytes per launch averaged over " \
+                               "the 63 trunk-shaped launches of a step (16 fwd+stats, 15 fwd+sin, 17 dgrad, 15 wgrad; ncu --set full, " \
+                               "profiles/r01_ncu_gemm2_variants_v4.txt); per-variant figures next to their algorithmic bytes under trunk_launches"
 
     out = {"metric": "training rays/s (4096-ray step, fwd+bwd)", "value": value, "unit": "rays/s", "n_gpus": world,
            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",

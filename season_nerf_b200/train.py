@@ -283,7 +283,31 @@ class TrainStep:
         if self.sched2 is not None:
             self.sched2.step()
         loss, self.last_loss = (st["loss"], st["total"]) if k == 1 else self._merge(losses, totals)
+        self._last_loss_dict = loss
         return loss
+
+    def scalars(self, loss=None):
+        """{name: float} of a step's loss terms + total + learning rate from ONE device->host copy (the reference pays one
+        `.item()` synchronisation per term and step, mg_run_NeRF.py:299-308)."""
+        loss = loss if loss is not None else self._last_loss_dict
+        names = [k for k in loss if isinstance(loss[k][0], t.Tensor)]
+        vals = t.stack([loss[k][0].detach().float().reshape(()) for k in names] + [self.last_loss.detach().float().reshape(())])
+        host = vals.cpu().tolist()
+        out = dict(zip(names, host[:-1]))
+        out.update({k: float(loss[k][0]) for k in loss if k not in out})
+        out["total"] = host[-1]
+        out["Learning_Rate"] = float(self.sched.get_last_lr()[0])
+        return out
+
+    def log_scalars(self, writer, current_step, loss=None):
+        """TensorBoard tags of mg_run_NeRF.py:301-308,325 ('Training/<term>', 'LR/Learning_Rate') for any object with
+        `add_scalar(tag, value, step)`."""
+        sc = self.scalars(loss)
+        for k, v in sc.items():
+            if k not in ("total", "Learning_Rate"):
+                writer.add_scalar("Training/" + k, v, current_step)
+        writer.add_scalar("LR/Learning_Rate", sc["Learning_Rate"], current_step)
+        return sc
 
     def step(self, data_dict, current_step, **inject):
         """mg_run_NeRF.py:288-326 without the per-term TensorBoard .item() syncs; returns the loss dict.
@@ -318,4 +342,5 @@ class TrainStep:
         if self.sched2 is not None:
             self.sched2.step()
         self.last_loss = total
+        self._last_loss_dict = loss
         return loss

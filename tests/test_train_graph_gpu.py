@@ -189,3 +189,30 @@ def test_host_solar_rng_still_follows_the_reference_streams():
     ref = so.create_solar_rays_uniform(16, so.OMA_W2C, so.oma_w2l_h(), np.random.RandomState(4), t.Generator().manual_seed(4))
     for x, y in zip(solar, ref[:4]):
         assert maxabs(x, y) < 1e-6
+
+
+def test_step_scalars_one_copy_and_tensorboard_tags():
+    """TrainStep.log_scalars: the reference's TensorBoard tags (mg_run_NeRF.py:301-308,325) from one device->host copy"""
+    import season_nerf_b200 as snb
+    from oracle import season_oracle as so
+
+    class Writer:
+        def __init__(self):
+            self.rows = []
+
+        def add_scalar(self, tag, value, step):
+            self.rows.append((tag, float(value), step))
+
+    t.manual_seed(0)
+    ts = snb.TrainStep(_args(), t.device("cuda"), so.oma_w2l_h(), so.OMA_W2C, use_graph=True, graph_warmup=1)
+    batch = so.synthetic_batch(128, seed=1, n_images=5)
+    w = Writer()
+    for i in range(3):
+        L = ts.step(batch, i)
+        sc = ts.log_scalars(w, i)
+        assert abs(sc["total"] - float(ts.last_loss)) < 1e-6 * max(1.0, abs(sc["total"]))
+        for k in L:
+            assert abs(sc[k] - float(L[k][0])) <= 1e-6 * max(1.0, abs(sc[k])), k
+    tags = {r[0] for r in w.rows}
+    assert {"Training/Color_ada", "Training/Solar_Correction", "Training/Albedo_Color", "LR/Learning_Rate"} <= tags
+    assert all(np.isfinite(r[1]) for r in w.rows) and {r[2] for r in w.rows} == {0, 1, 2}
