@@ -139,13 +139,14 @@ def run_reference(a):
     dt = time.perf_counter() - t0
     val = n * a.steps / dt
     sample = "%d image + %d solar rays per step, S=%d, Barron+solar loss, fwd+bwd, torch CPU fp32" % (n, n, S)
-    print(json.dumps({"impl": "reference", "metric": "training rays/s (4096-ray step, fwd+bwd)", "value": val, "unit": "rays/s",
+    line = ({"impl": "reference", "metric": "training rays/s (4096-ray step, fwd+bwd)", "value": val, "unit": "rays/s",
                       "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps,
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                       "config": {"workload": "train step, 4096 synthetic OMA_281-shaped rays + 4096 solar rays per GPU, S=96, "
                                              "Barron + solar losses (BASELINE.json configs[1]); reference arm: bounded sample"},
                       "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
-                      "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                      "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(line), file=a.out, flush=True)
 
 
 def cpu_baseline(n_rays=512):
@@ -388,7 +389,7 @@ def run_ours(a):
     if rank == 0:
         if world == 1 and not a.no_cpu:
             out["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(out))
+        print(json.dumps(out), file=a.out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -495,6 +496,15 @@ def bench_render(snb, net, dev, H, W2C, peaks, size=512, reps=3):
                                  "algorithmic (12 B in + 68 B out per point)" % len(times)}}
 
 
+def _only_json_on_stdout():
+    """Libraries chat on stdout (NCCL prints its version at the first communicator): route fd 1 to stderr for the whole
+    run and hand back the real stdout for the ONE JSON line of the contract."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -516,6 +526,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="eager kernel launches instead of the captured CUDA graph")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else max(a.warmup, 1)
+    a.out = _only_json_on_stdout()
     if a.impl == "reference":
         return run_reference(a)
     run_ours(a)

@@ -11,24 +11,16 @@ from .network import T_NeRF
 
 
 def flat_allreduce_mean_(tensors, world_size, flat=None):
-    """One flat fp32 bucket: pack -> all_reduce(SUM) -> /world_size -> unpack (in place).  Works for NCCL (CUDA) and
-    gloo (CPU, used by the host-logic tests).  Returns the bucket for reuse."""
-    n = sum(x.numel() for x in tensors)
-    if n == 0:
+    """One flat fp32 bucket: pack (one concatenation kernel) -> all_reduce(SUM) -> /world_size -> unpack (one multi-tensor
+    copy), in place.  Works for NCCL (CUDA, capturable in a CUDA graph) and gloo (CPU, used by the host-logic tests).
+    Returns the bucket."""
+    if not tensors:
         return flat
-    dev = tensors[0].device
-    if flat is None or flat.numel() != n or flat.device != dev:
-        flat = t.empty(n, device=dev, dtype=t.float32)
-    o = 0
-    for x in tensors:
-        flat[o:o + x.numel()].copy_(x.reshape(-1))
-        o += x.numel()
+    flat = t.cat([x.reshape(-1).float() for x in tensors])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM)
     flat.div_(world_size)
-    o = 0
-    for x in tensors:
-        x.copy_(flat[o:o + x.numel()].reshape(x.shape))
-        o += x.numel()
+    parts = flat.split([x.numel() for x in tensors])
+    t._foreach_copy_(list(tensors), [v.view_as(x) for v, x in zip(parts, tensors)])
     return flat
 
 
@@ -238,7 +230,8 @@ class TrainStep:
             if getattr(self.eval_tool, "trust_tensor", None) is None:
                 self.eval_tool.trust_tensor = t.zeros((), device=self.device, dtype=t.float32)
             self.eval_tool.trust_tensor.fill_(current_step / self.eval_tool.n_steps)
-        fused_opt = self.world_size == 1 and k == 1        # the optimiser updates ride in the same graph
+        # one chunk: the gradient all-reduce (NCCL, capturable) and the optimiser updates ride in the same graph
+        fused_opt = k == 1
         if k > 1 and self.graph_warmup < 1:
             raise ValueError("micro-batched graph capture needs graph_warmup >= 1 (the eager step creates the .grad tensors)")
         if "g_fb" not in st:
@@ -254,6 +247,8 @@ class TrainStep:
                 st["loss"], st["total"] = self._fwd_bwd(st["batch"], current_step, 1.0 / k, solar=st["solar"],
                                                         ts=st["ts_img"], solar_ts=st["ts_sol"])
                 if fused_opt:
+                    if self.world_size > 1:
+                        self._allreduce_grads()
                     self._optim_step()
             st["g_fb"] = g_fb
             st["launches"] = _lib.launch_count() - l0
@@ -275,9 +270,9 @@ class TrainStep:
         # a replay rewrites parameters and BatchNorm buffers behind autograd's back: bump their version counters so that
         # every derived cache (packed render program, staged bf16 weights) sees the change
         t.autograd.graph.increment_version(self._versioned)
-        if self.world_size > 1:
-            self._allreduce_grads()
         if not fused_opt:
+            if self.world_size > 1:
+                self._allreduce_grads()
             st["g_opt"].replay()
         self.sched.step()
         if self.sched2 is not None:
