@@ -391,6 +391,14 @@ def run_ours(a):
             out["cpu_baseline"] = cpu_baseline()
         print(json.dumps(out), file=a.out, flush=True)
     if world > 1:
+        # the captured step graphs hold NCCL kernels: release them before the communicator goes away (tearing the process
+        # group down underneath live graphs can block the exit)
+        ts._graphs.clear()
+        del ts
+        import gc
+        gc.collect()
+        t.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
 
 
