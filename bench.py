@@ -305,6 +305,30 @@ def run_ours(a):
                    "rays": size_s[0] * size_s[1], "ms": ms_r, "rays_per_s": size_s[0] * size_s[1] / (ms_r * 1e-3),
                    "scaling": "strong", "finite": bool((img == img).all()),
                    "mlp_tflops_algorithmic": size_s[0] * size_s[1] * RENDER_FLOP_PER_RAY / (ms_r * 1e-3) / 1e12}
+        # ---- BASELINE.json configs[4] at N GPUs: 365 time-of-year renders of the same view, ray-sharded; every rank keeps its
+        # [T, rays/N, 3] float64 slab on the device (no gather: SURVEY 8e), time = max over ranks
+        T_year = 365
+        times = np.stack([snb.encode_time(k / T_year) for k in range(T_year)], 0)
+        with t.no_grad():
+            cls_year = ts.network.get_class_only(t.tensor(times, dtype=t.float32, device=dev)).double().cpu().numpy()
+        barrier()
+        e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+        e0.record()
+        lo_, hi_, slab, _ = snb.render_shard(ts.network, [80, 0], [45, 135], 0.0, size_s, W2C, H, dev, rank, world, class_vecs=cls_year)
+        e1.record()
+        barrier()
+        ms_y = e0.elapsed_time(e1)
+        fin = t.tensor([float(bool(t.isfinite(slab).all()))], device=dev)
+        if world > 1:
+            tt = t.tensor([ms_y], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms_y = float(tt)
+            dist.all_reduce(fin, op=dist.ReduceOp.MIN)
+        sharded["year_sweep"] = {"workload": "%d time-of-year renders of the 1024x1024 view (BASELINE.json configs[4]), rays sharded over "
+                                             "%d GPU(s), each rank keeps its [T, rays/N, 3] float64 slab on the device" % (T_year, world),
+                                 "times": T_year, "ms": ms_y, "ray_renders_per_s": T_year * size_s[0] * size_s[1] / (ms_y * 1e-3),
+                                 "slab_shape": list(slab.shape), "finite": bool(fin.item() > 0), "scaling": "strong"}
+        del slab
         ts.network.train()
 
     extras = None
