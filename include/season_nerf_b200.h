@@ -103,6 +103,14 @@ int snb_camera_rays(const double* P, const int* rows, const int* cols, long long
 int snb_solar_rays(const double* world_center, const double* W2L_H, const double* az_el, const float* u_xy,
                    const float* u_time, int n, float* starts, float* ends, float* vec, float* times, void* stream);
 
+/* ---- prior-DSM density: T_NeRF.Supervised_Sample, T_NeRF_Full_2/T_NeRF_net_v2.py:175-181 -----------------------------
+ * pts [M,3], delta [M] float32; hm [H,W] float64 (the module keeps the map as a float64 tensor); out [M] float32 =
+ * -log(1 - P) / delta with P = 0.99 where hm[long(((x,y)+1)/2*(shape-1))] >= z, else 0.  k_hit = -log(1 - fl32(0.99)) is
+ * passed by the caller (evaluated once with the host's float32 log, so that the result is bit-identical to the reference's
+ * CPU path). */
+int snb_supervised_sample(const float* pts, const float* delta, const double* hm, int H, int W, float k_hit, long long M,
+                          float* out, void* stream);
+
 /* ---- positional encoding: misc.py:105-139 PE_Encode (extended) ------------------------------
  * out[m, col0 + ...] = [x (D), per dim: cos(k_j x) j<n, sin(k_j x) j<n], k_j = 2^j * fl32(pi/2);
  * width D*(2n+1), zero padded up to pad_to columns.  x: [M,D] float32, ldx elements. out dtype f32/bf16. */

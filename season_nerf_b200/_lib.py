@@ -22,6 +22,7 @@ SIGNATURES = {
     "snb_camera_rays": [C.POINTER(C.c_double), _p, _p, _ll, _i, _i, C.c_double, C.c_double, C.POINTER(C.c_double), _p, _p, _p,
                         _p, _p],
     "snb_solar_rays": [C.POINTER(C.c_double), C.POINTER(C.c_double), _p, _p, _p, _i, _p, _p, _p, _p, _p],
+    "snb_supervised_sample": [_p, _p, _p, _i, _i, _f, _ll, _p, _p],
     "snb_solar_tops": [_p, _ll, C.POINTER(C.c_double), _i, _p, _p],
     "snb_composite_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
     "snb_composite_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],

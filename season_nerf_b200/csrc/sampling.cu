@@ -165,6 +165,27 @@ __global__ void __launch_bounds__(128) solar_rays_kernel(SolarGeo g, const doubl
   }
 }
 
+// T_NeRF.Supervised_Sample (T_NeRF_net_v2.py:175-181): density implied by the prior height map at every sample point.
+//   idx = long(((xy + 1) / 2) * (shape - 1))   float32 arithmetic, truncation;   P = min(0.99, hm[idx] >= z)  (hm float64)
+//   rho = -log(1 - P) / delta  = k_hit / delta  or  -0 / delta     (k_hit = -log(1 - fl32(0.99)) evaluated by the caller)
+// Negative indices wrap like torch's; anything still outside the map is clamped (torch would raise).
+__global__ void __launch_bounds__(256) supervised_sample_kernel(const float* __restrict__ pts, const float* __restrict__ delta,
+                                                                const double* __restrict__ hm, int H, int W, float k_hit,
+                                                                long long M, float* __restrict__ out) {
+  const float ch = (float)(H - 1), cw = (float)(W - 1);
+  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
+    const float x = pts[3 * m], y = pts[3 * m + 1], z = pts[3 * m + 2];
+    long long ix = (long long)__fmul_rn(__fdiv_rn(__fadd_rn(x, 1.0f), 2.0f), ch);
+    long long iy = (long long)__fmul_rn(__fdiv_rn(__fadd_rn(y, 1.0f), 2.0f), cw);
+    if (ix < 0) ix += H;
+    if (iy < 0) iy += W;
+    ix = ix < 0 ? 0 : (ix >= H ? H - 1 : ix);
+    iy = iy < 0 ? 0 : (iy >= W ? W - 1 : iy);
+    const bool hit = hm[ix * W + iy] >= (double)z;
+    out[m] = __fdiv_rn(hit ? k_hit : -0.0f, delta[m]);
+  }
+}
+
 }  // namespace snb
 
 extern "C" int snb_sample_rays(const float* top, const float* bot, const float* ts, int N, int S, int zero_oob,
@@ -216,6 +237,16 @@ extern "C" int snb_solar_rays(const double* world_center, const double* W2L_H, c
   for (int i = 0; i < 3; ++i) g.wc[i] = world_center[i];    // host pointers: travel as a kernel argument
   for (int i = 0; i < 12; ++i) g.h[i] = W2L_H[i];
   snb::solar_rays_kernel<<<snb::grid_for(n, 128, 8), 128, 0, (cudaStream_t)stream>>>(g, az_el, u_xy, u_time, n, starts, ends, vec, times);
+  snb::count_launch();
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_supervised_sample(const float* pts, const float* delta, const double* hm, int H, int W, float k_hit,
+                                     long long M, float* out, void* stream) {
+  SNB_CHECK_ARG(pts && delta && hm && out && H >= 1 && W >= 1 && M >= 0);
+  if (M == 0) return SNB_OK;
+  snb::supervised_sample_kernel<<<snb::grid_for(M, 256, 16), 256, 0, (cudaStream_t)stream>>>(pts, delta, hm, H, W, k_hit, M, out);
   snb::count_launch();
   SNB_LAUNCH_CHECK();
   return SNB_OK;

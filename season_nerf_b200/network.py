@@ -332,17 +332,15 @@ class T_NeRF(nn.Module):
         return Rho[0:n], Rho[n::], Col, cls, Adjust_col
 
     def Supervised_Sample(self, world_pts, delta):
-        """T_NeRF_net_v2.py:175-181 (the reference runs this on the CPU; any device works here)."""
+        """T_NeRF_net_v2.py:175-181 (the reference runs this on the CPU with a D2H + H2D round trip per step): one kernel on
+        the device; the height map (a plain float64 CPU attribute, :28-29) is uploaded once per version."""
         dev = world_pts.device
+        if dev.type != "cuda":
+            raise ops._lib.SeasonNerfCudaError("season_nerf_b200.T_NeRF.Supervised_Sample runs on CUDA only (no CPU fallback)")
         cached = self.__dict__.get("_hm_dev")
         if cached is None or cached[0] != dev or cached[1] is not self.hm or cached[2] != self.hm._version:
-            cached = self.__dict__["_hm_dev"] = (dev, self.hm, self.hm._version, self.hm.to(dev),
-                                                 (t.tensor(self.hm.shape).reshape([1, 2]) - 1).to(dev))
-        hm, hm_const = cached[3], cached[4]           # device copies, made once (`hm` is a plain CPU attribute, :28-29)
-        xy = ((world_pts[:, 0:2] + 1) / 2 * hm_const).long()
-        P = (hm[xy[:, 0], xy[:, 1]] >= world_pts[:, 2]).float()
-        P = t.clamp(P, max=0.99)                      # P[P > .99] = 0.99 without a data-dependent index (graph capturable)
-        return -t.log(1 - P.unsqueeze(1)) / delta
+            cached = self.__dict__["_hm_dev"] = (dev, self.hm, self.hm._version, self.hm.to(device=dev, dtype=t.float64).contiguous())
+        return ops.supervised_sample(world_pts.float(), delta.float().reshape(-1), cached[3])
 
 
 # =========================================================================================================

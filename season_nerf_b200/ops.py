@@ -101,6 +101,25 @@ def solar_rays(world_center, W2L_H, az_el, u_xy, u_time=None, out=None):
     return (starts, ends, vec, times) if u_time is not None else (starts, ends, vec)
 
 
+_K_HIT = None
+
+
+def supervised_sample(pts, delta, hm):
+    """T_NeRF.Supervised_Sample (T_NeRF_net_v2.py:175-181): pts [M,3] f32, delta [M,1] f32, hm [H,W] f64 (device) -> [M,1] f32"""
+    global _K_HIT
+    if _K_HIT is None:
+        _K_HIT = float(-torch.log(1 - torch.tensor(0.99, dtype=torch.float32)))      # the reference's CPU float32 log
+    pts = _cuda(pts, torch.float32, "pts").contiguous()
+    delta = _cuda(delta, torch.float32, "delta").contiguous()
+    hm = _cuda(hm, torch.float64, "hm").contiguous()
+    M = pts.shape[0]
+    out = torch.empty(M, 1, device=pts.device, dtype=torch.float32)
+    if M:
+        check(_lib.load().snb_supervised_sample(_ptr(pts), _ptr(delta), _ptr(hm), int(hm.shape[0]), int(hm.shape[1]), _K_HIT, M,
+                                                _ptr(out), _stream()))
+    return out
+
+
 def solar_tops(pts, sun_vec, f64=True):
     """mg_Img_Eval.py:57-60 (f64) / Eval_Tools_2.py:255-258 (f32).  pts [M,3] -> tops [M,3]."""
     pts = _cuda(pts, torch.float32, "pts").contiguous().reshape(-1, 3)

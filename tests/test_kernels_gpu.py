@@ -378,3 +378,26 @@ def test_device_to_numpy_large_results_are_bit_identical():
     assert np.array_equal(device_to_numpy(small), np.arange(10, dtype=np.float32))
     xf = t.rand(3, 6000000, device="cuda", generator=g)                             # float32, 72 MB
     assert np.array_equal(device_to_numpy(xf, chunk_bytes=32 << 20), xf.cpu().numpy())
+
+
+def test_supervised_sample_bit_exact_vs_oracle():
+    """T_NeRF.Supervised_Sample (T_NeRF_net_v2.py:175-181): prior-DSM density, bit-identical to the torch-CPU restatement
+    (same float32 index arithmetic and truncation, float64 height comparison, the host's float32 log constant)."""
+    import season_nerf_b200 as snb
+    from oracle import season_oracle as so
+    g = t.Generator().manual_seed(3)
+    hm = (t.rand(37, 53, generator=g, dtype=t.float64) * 2 - 1).numpy()
+    M = 20011
+    pts = t.rand(M, 3, generator=g) * 2 - 1
+    pts[:7] = t.tensor([[1., 1., 0.], [-1., -1., 0.], [1., -1., .5], [-1., 1., -.5], [0., 0., 1.], [0.999999, -0.999999, -1.], [0.5, 0.25, 0.]])
+    delta = t.rand(M, 1, generator=g) * 0.05 + 1e-3
+    ref = so.supervised_sample(hm, pts, delta)
+    net = snb.T_NeRF(64, 4, HM=hm).cuda()
+    out = net.Supervised_Sample(pts.cuda(), delta.cuda())
+    assert out.shape == (M, 1) and out.dtype == t.float32
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), ref.numpy().view(np.uint32))      # incl. the sign of -0
+    assert 0.2 < float((out > 0).float().mean()) < 0.8
+    # a modified height map is picked up (plain attribute, versioned)
+    net.hm[:] = 2.0
+    assert bool((net.Supervised_Sample(pts.cuda(), delta.cuda()) > 0).all())
+    assert net.Supervised_Sample(pts[:0].cuda(), delta[:0].cuda()).shape == (0, 1)
