@@ -135,6 +135,8 @@ def march_transmittance(rho, deltas):
     S = rho.shape[-1]
     Mrows = rho.numel() // S
     out = torch.empty(Mrows, device=rho.device, dtype=torch.float32)
+    if Mrows == 0:
+        return out
     check(_lib.load().snb_march_transmittance(_ptr(rho), _ptr(deltas), Mrows, S, _ptr(out), _stream()))
     return out
 
@@ -148,6 +150,8 @@ def composite_fwd(rho, deltas, col, vis, sky, classic=False, want_pv=True):
     mk = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
     PV, PE, PS = (mk(N, S), mk(N, S), mk(N, S)) if want_pv else (None, None, None)
     albedo, rendered, vsum = mk(N, 3), mk(N, 3), mk(N)
+    if N == 0:                                  # empty tensors have no data pointer to hand over
+        return PV, PE, PS, albedo, rendered, vsum
     check(_lib.load().snb_composite_fwd(_ptr(rho), _ptr(deltas), _ptr(col), _ptr(vis), _ptr(sky), int(per_sample), N, S,
                                         int(classic), _ptr(PV), _ptr(PE), _ptr(PS), _ptr(albedo), _ptr(rendered),
                                         _ptr(vsum), _stream()))
@@ -200,6 +204,8 @@ def cli_composite(rho, deltas, base, vis, adj, cls, exact_vis=None):
     ins = [x.contiguous() for x in (rho, deltas, base, vis, adj)]
     ev = None if exact_vis is None else exact_vis.contiguous()
     cls = _cuda(cls, torch.float64).contiguous()
+    if N == 0:
+        return base_img, season, extreme, raw, raw_e
     check(_lib.load().snb_cli_composite(*[_ptr(x) for x in ins], _ptr(cls), _ptr(ev), dt, N, S, Cn, _ptr(base_img),
                                         _ptr(season), _ptr(extreme), _ptr(raw), _ptr(raw_e), _stream()))
     return base_img, season, extreme, raw, raw_e
@@ -232,6 +238,8 @@ def year_sweep(rho, deltas, base, adj, cls, shade=None, out=None, ps_weight=None
         shade = _cuda(shade, torch.float64, "shade").contiguous()
     if ps_weight is not None:
         ps_weight = _cuda(ps_weight, rho.dtype, "ps_weight").contiguous()
+    if N == 0 or T == 0:
+        return out
     check(_lib.load().snb_year_sweep(*[_ptr(x) for x in ins], _ptr(cls), _ptr(shade), _ptr(ps_weight), _DT[rho.dtype], N, S, Cn, T,
                                      _ptr(out), _stream()))
     return out

@@ -401,3 +401,46 @@ def test_supervised_sample_bit_exact_vs_oracle():
     net.hm[:] = 2.0
     assert bool((net.Supervised_Sample(pts.cuda(), delta.cuda()) > 0).all())
     assert net.Supervised_Sample(pts[:0].cuda(), delta[:0].cuda()).shape == (0, 1)
+
+
+def test_composite_full_size_properties_and_empty_inputs():
+    """BASELINE-size compositing (2^20 rays x 96 samples) through size-independent properties of Eval_Tools_2.py:187-215:
+    PV starts at 1 and never increases, the surface probabilities of a ray sum to 1 - (final transmittance), the albedo is
+    linear in the colours, colours in [0,1] give renders in [0,1], results do not depend on the launch (determinism);
+    zero rays and zero points are accepted by every bandwidth-bound entry point."""
+    from season_nerf_b200 import ops
+    N, Sx = 1 << 20, 96
+    g = t.Generator(device="cuda").manual_seed(11)
+    rho = t.rand(N, Sx, device="cuda", generator=g) * 6
+    rho[::7] = 0                                                   # empty rays
+    dl = (t.rand(N, 1, device="cuda", generator=g) * 0.03).expand(N, Sx).contiguous()
+    col = t.rand(N, Sx, 3, device="cuda", generator=g)
+    col2 = t.rand(N, Sx, 3, device="cuda", generator=g)
+    vis = t.rand(N, Sx, device="cuda", generator=g)
+    sky = t.rand(N, 3, device="cuda", generator=g)
+    PV, PE, PS, alb, ren, vsum = ops.composite_fwd(rho, dl, col, vis, sky)
+    assert bool((PV[:, 0] == 1).all()) and bool((PV[:, 1:] <= PV[:, :-1]).all()) and bool((PV >= 0).all())
+    total = PS.double().sum(1)
+    t_end = (PV[:, -1] * (1 - PE[:, -1])).double()
+    assert float((total + t_end - 1).abs().max()) < 2e-5
+    assert bool((total[::7] == 0).all()) and bool((ren[::7] == 0).all())
+    assert float(ren.min()) >= 0 and float(ren.max()) <= 1 + 1e-6 and float(alb.max()) <= 1 + 1e-6
+    _, _, _, alb2, _, _ = ops.composite_fwd(rho, dl, col2, vis, sky, want_pv=False)
+    _, _, _, alb12, _, _ = ops.composite_fwd(rho, dl, col + col2, vis, sky, want_pv=False)
+    assert float((alb12 - alb - alb2).abs().max()) < 3e-5          # linearity
+    again = ops.composite_fwd(rho, dl, col, vis, sky)
+    assert all(t.equal(a, b) for a, b in zip(again, (PV, PE, PS, alb, ren, vsum)))
+    assert float((vsum.double() - (PS * vis).double().sum(1)).abs().max()) < 2e-5
+    # ---- empty inputs ----
+    z = lambda *s: t.zeros(*s, device="cuda")
+    out = ops.composite_fwd(z(0, Sx), z(0, Sx), z(0, Sx, 3), z(0, Sx), z(0, 3))
+    assert out[3].shape == (0, 3) and out[0].shape == (0, Sx)
+    pts, d = ops.sample_rays(z(0, 3), z(0, 3), t.linspace(0, 1, Sx, device="cuda"))
+    assert pts.shape == (0, Sx, 3) and d.shape == (0, Sx)
+    assert ops.march_transmittance(z(0, Sx), z(0, Sx)).shape == (0,)
+    b, s_, e, r, _ = ops.cli_composite(z(0, Sx), z(0, Sx), z(0, Sx, 3), z(0, Sx), z(0, Sx, 4, 3), t.zeros(4, dtype=t.float64, device="cuda"))
+    assert b.shape == (0, 3) and e.shape == (4, 0, 3) and r.shape == (0,)
+    sw = ops.year_sweep(z(0, Sx), z(0, Sx), z(0, Sx, 3), z(0, Sx, 4, 3), t.zeros(5, 4, dtype=t.float64, device="cuda"))
+    assert sw.shape == (5, 0, 3)
+    sw0 = ops.year_sweep(z(3, Sx), z(3, Sx), z(3, Sx, 3), z(3, Sx, 4, 3), t.zeros(0, 4, dtype=t.float64, device="cuda"))
+    assert sw0.shape == (0, 3, 3)
