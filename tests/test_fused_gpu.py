@@ -92,3 +92,34 @@ def test_ray_sharded_render_equals_unsharded(params0):
     assert parts[0][0] == 0 and parts[-1][1] == 120 and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
     cat = t.cat([p[2] for p in parts], 0).reshape(12, 10, 3).cpu().numpy()
     assert maxabs(cat, ref) < 1e-6
+
+
+def test_fused_full_size_permutation_and_chunk_invariance(params0):
+    """BASELINE.json configs[2] size (512 x 512 rays x 96 samples = 25.2 M points, rendered in the API's 4 M-point calls):
+    every point is evaluated independently of its tile, of the CTA pair that renders it and of the call it falls in -
+    a permuted batch gives the permuted outputs BIT FOR BIT, two half calls give the whole call, and all outputs are
+    finite.  Size-independent properties of the fused kernel where the CPU oracle cannot follow."""
+    from season_nerf_b200 import fused
+    net = make_net(params0, "bf16")
+    M = 1 << 22                                     # one API call of the render path
+    g = t.Generator(device="cuda").manual_seed(21)
+    sun = t.tensor([[0.3, -0.4, 0.866]], device="cuda")
+    total, checksum = 0, 0.0
+    with t.no_grad():
+        for call in range(6):                       # 6 x 4.19 M = 25.2 M points
+            pts = t.rand(M, 3, device="cuda", generator=g) * 2 - 1
+            _, pos4, vis, adj = fused.run(net, pts, sun, M)
+            assert bool(t.isfinite(pos4).all()) and bool(t.isfinite(vis).all()) and bool(t.isfinite(adj).all())
+            total += M
+            checksum += float(pos4.double().sum())
+            if call == 0:
+                perm = t.randperm(M, device="cuda", generator=g)
+                _, p2, v2, a2 = fused.run(net, pts[perm], sun, M)
+                assert t.equal(p2, pos4[perm]) and t.equal(v2, vis[perm]) and t.equal(a2, adj[perm])
+                h = M // 2 + 77                      # ragged split: the second call starts inside a 256-point tile
+                _, pa, va, aa = fused.run(net, pts[:h], sun, h)
+                _, pb, vb, ab = fused.run(net, pts[h:], sun, M - h)
+                assert t.equal(t.cat([pa, pb]), pos4) and t.equal(t.cat([va, vb]), vis) and t.equal(t.cat([aa, ab]), adj)
+                rho, _, _, _ = fused.run(net, pts, None, M, sigma_only=True)
+                assert float((rho - pos4[:, 0]).abs().max()) == 0.0      # the sigma-only program is the same trunk
+    assert total == 6 * M and np.isfinite(checksum)
