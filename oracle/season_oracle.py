@@ -235,6 +235,18 @@ def forward_seperate(p, X, sun, Time, training=False):
 forward_full_eval = forward_seperate  # T_NeRF_net_v2.py:184-204 returns the same tuple
 
 
+def approx_solar(p, X, X_solar, Time, training=False):
+    """T_NeRF.approx_Solar, T_NeRF_net_v2.py:107-128: one trunk pass over [X; X_solar], adjust branch on the X part."""
+    n = X.shape[0]
+    n_classes = p["get_class_layer.weight"].shape[0]
+    x_enc, rho, col = forward_position(p, t.cat([X, X_solar], 0), training)
+    cls = time_classes(p, Time, training)
+    adj = adjust_branch(p, x_enc[0:n], n_classes, training)
+    adjust_col = t.sum(adj * cls.unsqueeze(2), 1)
+    rho = t.nn.functional.softplus(rho)
+    return rho[0:n], rho[n:], t.sigmoid(col[0:n] + adjust_col), cls, adjust_col
+
+
 def forward_solar(p, X, sun, Time=None, training=False):
     """T_NeRF.forward_Solar, T_NeRF_net_v2.py:154-157 + G_NeRF.py:141-145:
     trunk + sigma head under no_grad, solar/sky heads with grad, RAW sky."""
@@ -343,6 +355,19 @@ def create_solar_rays_uniform(n, WC, W2L_H, np_rng=None, torch_gen=None):
     return starts, ends, vec, times, az_el
 
 
+def create_solar_rays_given_vec(n, solar_angle_vec, torch_gen=None):
+    """create_solor_rays_uniform.create_given_vec(n, vec, include_times=True), Eval_Tools_2.py:50-70."""
+    delta = 2 * (solar_angle_vec / solar_angle_vec[2::])
+    starts = t.ones(n, 3)
+    starts[:, 0] = 2 * t.rand(n, generator=torch_gen) - 1
+    starts[:, 1] = 2 * t.rand(n, generator=torch_gen) - 1
+    ends = (starts - np.expand_dims(delta, 0)).float()
+    vec = t.stack([t.tensor(solar_angle_vec).float()] * n, 0)
+    f = t.rand(n, 2, generator=torch_gen) * 2 * np.pi
+    times = t.stack([t.cos(f[:, 0]), t.sin(f[:, 0]), t.cos(f[:, 1]), t.sin(f[:, 1])], 1)
+    return starts, ends, vec, times
+
+
 # --------------------------------------------------------------------------
 # render / loss engine (T_NeRF_Full_2/Eval_Tools_2.py)
 # --------------------------------------------------------------------------
@@ -396,6 +421,29 @@ def engine_eval(args, data, p, current_step, train_mode, jitter=None, use_prior=
                   "PS_Merged": PS_M, "Rendered_Col_Merged": Rend_M, "Rho_Merged": Rho_M,
                   "Albedo_Color": Albedo})
     return R
+
+
+def engine_full_eval(args, data, p):
+    """All_in_One_Eval.full_eval, Eval_Tools_2.py:127-163: eval-mode sampling, `forward` (activated colour), and the
+    colour passes through Sigmoid a second time inside the compositing (:155,158)."""
+    S = args.n_samples
+    Xs, deltas = sample_pt_coarse(data["Top"], data["Bot"], S, True)
+    N = Xs.shape[0]
+    sun = (t.ones_like(Xs) * data["Sun_Angle"].unsqueeze(1)).reshape(-1, 3)
+    tim = (t.ones(N, S, 4) * data["Time_Encoded"].unsqueeze(1)).reshape(-1, 4)
+    Rho, Col, Vis, Sky, Cls, Adj = forward(p, Xs.reshape(-1, 3), sun, tim)
+    Col, Rho, Vis = Col.reshape(N, S, -1), Rho.reshape(N, S, 1), Vis.reshape(N, S, 1)
+    Sky, Cls, Adj = Sky.reshape(N, S, -1), Cls.reshape(N, S, -1), Adj.reshape(N, S, -1)
+    PV = get_PV(Rho, deltas)
+    PE = 1 - t.exp(-Rho * deltas)
+    PS = PV * PE
+    if args.Solar_Type_2:
+        Rendered = t.sum(PS * t.sigmoid(Col) * (Vis + (1 - Vis) * Sky), 1)
+    else:
+        SV3 = t.sigmoid((t.sum(Vis.detach() * PS, 1) - .2) * 30)
+        Rendered = t.sum(PS * t.sigmoid(Col), 1) * (SV3 + (1 - SV3) * t.mean(Sky, 1))
+    return {"Rendered_Col": Rendered, "PE": PE, "PV": PV, "PS": PS, "Solar_Vis": Vis, "Sky_Col": Sky, "Classes": Cls,
+            "Adjust": Adj, "Rho": Rho, "Col": Col, "deltas": deltas, "sample_pts": Xs}
 
 
 def eval_rho_only(args, data, p, train_mode, current_step=0, jitter=None, use_prior=False, n_steps=1, hm=None):

@@ -308,3 +308,39 @@ def test_classic_shadow_images_and_alignment_golden(params0):
                                                           use_classic_shadows=True)
     assert abs(best_t - float(gc["best_t"])) < 1e-7
     assert tuple(sky.shape) == (1, 1, 3) and maxabs(sky, gc["sky"]) < 1e-4 and maxabs(adj, gc["adj_vec"]) < 1e-4
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_remaining_entry_points_golden(params0, precision):
+    """full_eval (both solar conventions), approx_Solar, forward_full_eval, forward_Position and create_given_vec against
+    the unmodified reference (fixture api_extra)."""
+    import season_nerf_b200 as snb
+    from oracle import season_oracle as so
+    g = load_golden("api_extra")
+    net = make_net(params0, precision)
+    tol = TOL[precision]
+    X, Xs, sun, Time = (T(g[k]) for k in ("X", "Xs", "sun", "Time"))
+    with t.no_grad():
+        ap = net.approx_Solar(X, Xs, Time)
+        fe = net.forward_full_eval(X, sun, Time)
+        fp = net.G_NeRF_net.forward_Position(X)
+    for i, (o, k) in enumerate(zip(ap, ["rho", "rho", "out", "out", "rho"])):
+        assert tuple(o.shape) == g["ap_%d" % i].shape and maxabs(o, g["ap_%d" % i]) < tol[k], ("approx_Solar", i, maxabs(o, g["ap_%d" % i]))
+    for i, (o, k) in enumerate(zip(fe, ["rho", "rho", "out", "out", "out", "rho"])):
+        assert tuple(o.shape) == g["fe_%d" % i].shape and maxabs(o, g["fe_%d" % i]) < tol[k], ("forward_full_eval", i)
+    for i, o in enumerate(fp):
+        assert tuple(o.shape) == g["fp_%d" % i].shape and maxabs(o, g["fp_%d" % i]) < tol["rho"], ("forward_Position", i)
+    d = _data(g)
+    for tag, classic in (("full", False), ("fullc", True)):
+        R = _tool(so.default_args(Solar_Type_2=classic)).full_eval(d, net, 0)
+        assert np.array_equal(R["sample_pts"].cpu().numpy(), g[tag + "_sample_pts"])
+        assert np.array_equal(R["deltas"].cpu().numpy(), g[tag + "_deltas"])
+        for k in ["Rendered_Col", "PE", "PV", "PS", "Solar_Vis", "Sky_Col", "Classes", "Adjust", "Rho", "Col"]:
+            assert tuple(R[k].shape) == g[tag + "_" + k].shape, (tag, k, tuple(R[k].shape))
+            lim = tol["rho"] if k in ("Rho", "Adjust") else tol["out"]
+            assert maxabs(R[k], g[tag + "_" + k]) < lim, (tag, k, maxabs(R[k], g[tag + "_" + k]))
+    tool = snb.create_solor_rays_uniform(so.oma_w2l_h(), so.OMA_W2C)
+    t.manual_seed(9)
+    st, en, sv, tm = tool.create_given_vec(12, g["gv_vec"].astype(np.float64), include_times=True)
+    assert np.array_equal(st.numpy(), g["gv_starts"]) and maxabs(en, g["gv_ends"]) < 1e-5
+    assert maxabs(sv, g["gv_sun"]) < 1e-7 and maxabs(tm, g["gv_times"]) < 1e-6

@@ -251,3 +251,35 @@ def test_classic_shadow_conventions_oracle_matches_reference(params0):
     adj, sky, best_t, _ = so.seasonal_align_v3_classic(P, D, g["target"], float(g["t0"]))
     assert abs(best_t - float(gc["best_t"])) < 1e-7
     assert np.abs(adj.numpy() - gc["adj_vec"]).max() < 1e-5 and np.abs(sky.numpy() - gc["sky"]).max() < 1e-4
+
+
+FULL_KEYS = ["Rendered_Col", "PE", "PV", "PS", "Solar_Vis", "Sky_Col", "Classes", "Adjust", "Rho", "Col", "deltas", "sample_pts"]
+
+
+def test_remaining_entry_points_oracle_matches_reference(params0):
+    """full_eval (both solar conventions), approx_Solar, forward_full_eval, forward_Position, create_given_vec:
+    restatements vs the unmodified reference (fixture api_extra)."""
+    from oracle import season_oracle as so
+    g = load_golden("api_extra")
+    X, Xs, sun, Time = (t.tensor(g[k]) for k in ("X", "Xs", "sun", "Time"))
+    with t.no_grad():
+        ap = so.approx_solar(params0, X, Xs, Time)
+        fe = so.forward_full_eval(params0, X, sun, Time)
+        fp = so.forward_position(params0, X, False)
+    for i, o in enumerate(ap):
+        close(o, g["ap_%d" % i])
+    for i, o in enumerate(fe):
+        assert tuple(o.shape) == g["fe_%d" % i].shape
+        close(o, g["fe_%d" % i])
+    for i, o in enumerate(fp):      # X_Encode after nine x30 SIREN layers: float32 summation order shows at 4e-6
+        close(o, g["fp_%d" % i], rtol=1e-4, atol=1e-5)
+    d = _data(g)
+    for tag, classic in (("full", False), ("fullc", True)):
+        with t.no_grad():
+            R = so.engine_full_eval(so.default_args(Solar_Type_2=classic), d, params0)
+        assert np.array_equal(R["sample_pts"].numpy(), g[tag + "_sample_pts"])
+        for k in FULL_KEYS:
+            close(R[k], g[tag + "_" + k], rtol=1e-4, atol=2e-6)
+    st, en, sv, tm = so.create_solar_rays_given_vec(12, g["gv_vec"].astype(np.float64), t.Generator().manual_seed(9))
+    assert np.array_equal(st.numpy(), g["gv_starts"]) and np.abs(tm.numpy() - g["gv_times"]).max() < 1e-6
+    assert np.abs(en.numpy() - g["gv_ends"]).max() < 1e-5 and np.abs(sv.numpy() - g["gv_sun"]).max() < 1e-7
