@@ -32,14 +32,26 @@ def shard_range(n, rank, world_size):
 
 
 def gather_rows(local, n_total, rank, world_size):
-    """all_gather of per-rank row blocks of unequal length (final gather of a ray-sharded render) -> [n_total, ...]."""
+    """all_gather of per-rank row blocks of unequal length (final gather of a ray-sharded render) -> [n_total, ...].
+    One collective into one flat buffer (equal, padded chunks); the valid rows are sliced out afterwards."""
     sizes = [shard_range(n_total, r, world_size)[1] - shard_range(n_total, r, world_size)[0] for r in range(world_size)]
     mx = max(sizes)
-    pad = t.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    pad[:local.shape[0]] = local
-    outs = [t.empty_like(pad) for _ in range(world_size)]
-    dist.all_gather(outs, pad)
-    return t.cat([o[:s] for o, s in zip(outs, sizes)], 0)
+    tail = tuple(local.shape[1:])
+    if local.shape[0] == mx:
+        pad = local.contiguous()
+    else:
+        pad = t.zeros((mx,) + tail, dtype=local.dtype, device=local.device)
+        pad[:local.shape[0]] = local
+    flat = t.empty((world_size * mx,) + tail, dtype=local.dtype, device=local.device)
+    try:
+        dist.all_gather_into_tensor(flat, pad)
+    except (RuntimeError, NotImplementedError, AttributeError):          # backend without the flat variant
+        outs = [t.empty_like(pad) for _ in range(world_size)]
+        dist.all_gather(outs, pad)
+        flat = t.cat(outs, 0)
+    if all(s_ == mx for s_ in sizes):
+        return flat
+    return t.cat([flat[r * mx:r * mx + s_] for r, s_ in enumerate(sizes)], 0)
 
 
 class TrainStep:
