@@ -51,7 +51,7 @@ class DeviceImgDict(dict):
 _STAGE = {}
 
 
-def device_to_numpy(x, chunk_bytes=128 << 20, threads=4):
+def device_to_numpy(x, chunk_bytes=128 << 20, threads=4, min_bytes=64 << 20):
     """Large device tensor -> numpy array of the same dtype / shape.  `x.cpu()` of a multi-GB result (the [T,H,W,3] float64
     year sweep is 9.2 GB at 365 x 1024^2) runs at ~2 GB/s: it copies through an internal staging buffer into freshly
     mapped pageable memory, page fault by page fault, on one thread.  Here the device->host copy goes through two cached
@@ -59,7 +59,7 @@ def device_to_numpy(x, chunk_bytes=128 << 20, threads=4):
     (first touch in parallel) while the next chunk is in flight."""
     x = x.detach().contiguous()
     nbytes = x.numel() * x.element_size()
-    if nbytes < (64 << 20) or not x.is_cuda:
+    if nbytes < min_bytes or not x.is_cuda:          # small results: the plain copy is as fast
         return x.cpu().numpy()
     from concurrent.futures import ThreadPoolExecutor
     key = (x.device.index, chunk_bytes)
@@ -390,7 +390,9 @@ def render_image_sharded(the_network, view_el_az, sun_el_az, time_frac, out_img_
         t.cuda.synchronize()
         t2 = time.perf_counter()
     # split on the device (strided host copies of a 33 MB array cost 30 ms per rank when 8 ranks do them at once)
-    out = both[:, :3].contiguous().cpu().numpy().reshape(H, W, 3), both[:, 3].contiguous().cpu().numpy().reshape(H, W)
+    # and leave through the pinned staging path: N ranks copying into fresh pageable memory at once contend on the host
+    out = (device_to_numpy(both[:, :3].contiguous(), chunk_bytes=32 << 20, min_bytes=4 << 20).reshape(H, W, 3),
+           device_to_numpy(both[:, 3].contiguous(), chunk_bytes=32 << 20, min_bytes=4 << 20).reshape(H, W))
     if timing:
         t3 = time.perf_counter()
         sys.stderr.write("[shard timing] rank %d: render %.1f ms, gather %.1f ms, to host %.1f ms\n"
