@@ -289,6 +289,9 @@ def run_ours(a):
         ts.network.eval()
         size_s = (1024, 1024, S)
         snb.render_image_sharded(ts.network, [80, 0], [45, 135], 184 / 365, (64, 64, S), W2C, H, dev, rank, world)   # warm-up
+        # one-off per process: the pinned staging buffers of the image D2H path (the 64 x 64 warm-up is below its threshold)
+        from season_nerf_b200.render import device_to_numpy
+        device_to_numpy(t.zeros(1 << 20, dtype=t.float64, device=dev), chunk_bytes=32 << 20, min_bytes=4 << 20)
         barrier()
         e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
         e0.record()
