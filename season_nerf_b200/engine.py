@@ -176,9 +176,15 @@ class All_in_One_Eval():
             trust = self._trust(current_step)
             with t.no_grad():
                 Rho_S = Network.Supervised_Sample(Xs.reshape(-1, 3), deltas.reshape(-1, 1)).reshape(N, S, 1)
-            PV_S, PE_S, PS_S, _, Rend_S = self._shade(Rho_S, deltas, Col, Vis, Sky_ray)
+            PV_S, PE_S, PS_S, Albedo_S, Rend_S = self._shade(Rho_S, deltas, Col, Vis, Sky_ray)
             Rho_M = Rho * trust + Rho_S * (1 - trust)
             PV_M, PE_M, PS_M, Albedo_M, Rend_M = self._shade(Rho_M, deltas, Col, Vis, Sky_ray)
+            if not self.use_classic_solar:
+                # Eval_Tools_2.py:214,231,243: Solar_Vis3 is computed ONCE, from the network's own (unmerged) PS, and shades
+                # all three colours; its gradient reaches rho through that PS only
+                sv3 = self.Sigmoid((t.sum(Vis.detach() * PS, 1) - .2) * 30)
+                shade = sv3 + (1 - sv3) * Sky_ray
+                Rend_S, Rend_M = Albedo_S * shade, Albedo_M * shade
             R.update({"PV_Supervised": PV_S, "PE_Supervised": PE_S, "PS_Supervised": PS_S,
                       "Rendered_Col_Supervised": Rend_S, "PV_Merged": PV_M, "PE_Merged": PE_M, "PS_Merged": PS_M,
                       "Rendered_Col_Merged": Rend_M, "Rho_Merged": Rho_M, "Albedo_Color": Albedo_M})

@@ -347,3 +347,59 @@ def test_remaining_entry_points_golden(params0, precision):
     st, en, sv, tm = tool.create_given_vec(12, g["gv_vec"].astype(np.float64), include_times=True)
     assert np.array_equal(st.numpy(), g["gv_starts"]) and maxabs(en, g["gv_ends"]) < 1e-5
     assert maxabs(sv, g["gv_sun"]) < 1e-7 and maxabs(tm, g["gv_times"]) < 1e-6
+
+
+PRIOR_KEYS = ["Rendered_Col", "Albedo_Color", "PS", "PV_Supervised", "PE_Supervised", "PS_Supervised", "Rendered_Col_Supervised",
+              "PV_Merged", "PE_Merged", "PS_Merged", "Rendered_Col_Merged", "Rho_Merged"]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_engine_eval_prior_golden(params0, precision):
+    """DSM-guided section (Eval_Tools_2.py:217-246) vs the unmodified reference: the supervised and merged colours are shaded
+    with the Solar_Vis3 of the network's own PS (fixture engine_eval_prior)."""
+    import season_nerf_b200 as snb
+    g = load_golden("engine_eval_prior")
+    tol = TOL[precision]
+    for tag, train in (("ev_", False), ("tr_", True)):
+        net = snb.T_NeRF(512, 4, HM=g["hm"], precision=precision)
+        net.load_state_dict({k: v.clone() for k, v in params0.items()})
+        net = net.cuda().train(train)
+        with t.no_grad():
+            R = _tool(use_prior=True).eval(_data(g), net, 30, train, jitter=g["jitter"] if train else None)
+        for k in PRIOR_KEYS:
+            lim = tol["rho"] if k == "Rho_Merged" else tol["out"]
+            assert maxabs(R[k], g[tag + k]) < lim, (tag, k, maxabs(R[k], g[tag + k]))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_get_loss_prior_mse_golden(params0, precision):
+    """--Use_MSE_loss + prior: Rendered_Col_Merged is the training target, so the shading fix reaches the gradients."""
+    from oracle import season_oracle as so
+    import season_nerf_b200 as snb
+    g = load_golden("loss_prior_mse")
+    net = snb.T_NeRF(512, 4, HM=g["hm"], precision=precision)
+    net.load_state_dict({k: v.clone() for k, v in params0.items()})
+    net = net.cuda().train()
+    tool = _tool(so.default_args(Use_MSE_loss=True), True, None)
+    solar = tuple(t.tensor(g[k]) for k in ("s_top", "s_bot", "s_sun", "s_time"))
+    L = tool.get_loss(_data(g), net, 30, True, jitter=g["jitter"], solar=solar, solar_jitter=g["solar_jitter"])
+    assert set(L.keys()) == {k[5:] for k in g if k.startswith("loss_")}
+    for k in L:
+        ref = float(g["loss_" + k])
+        assert abs(float(L[k][0]) - ref) < (3e-3 if precision == "fp32" else 8e-2) * max(abs(ref), 1e-2), (k, float(L[k][0]), ref)
+    sum(L[k][0] * L[k][1] for k in L).backward()
+    norms = dict(zip(g["grad_names"].tolist(), g["grad_norms"].tolist()))
+    scale = max(norms.values())
+    tol = TOL[precision]
+    bad = []
+    for k, p in net.named_parameters():
+        n = 0.0 if p.grad is None else float(p.grad.norm())
+        if abs(n - norms[k]) > tol["grad"] * norms[k] + 1e-4 * scale:
+            bad.append((k, n, norms[k]))
+    assert not bad, bad
+    for k in g:
+        if k.startswith("grad_") and k not in ("grad_names", "grad_norms"):
+            p = dict(net.named_parameters())[k[5:]]
+            if float(np.abs(g[k]).max()) < 1e-4 * scale:
+                continue
+            assert relerr(p.grad, g[k]) < (5e-3 if precision == "fp32" else 0.15), (k, relerr(p.grad, g[k]))
