@@ -27,6 +27,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 S = 96
+METRIC = "training rays/s (4096-ray step, fwd+bwd)"
 TRAIN_FLOP_PER_RAY = 2.086e9          # 1 image ray fwd+bwd + 1 solar ray, algorithmic
 RENDER_FLOP_PER_RAY = 556_750_336     # 96*5,793,792 + 546,304
 RENDER_FLOP_PER_POINT = 5_793_792
@@ -97,6 +98,35 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def workload_config(a, world):
+    """the workload of the headline metric - IDENTICAL in both arms (`--impl ours` / `--impl reference`): the reference arm
+    steps a bounded sample of this workload and says so in cpu_baseline.sample"""
+    n = a.rays
+    return {"workload": "train step, %d synthetic OMA_281-shaped rays + %d solar rays per GPU, S=96, Barron + solar losses, "
+                        "Adam+OneCycle (BASELINE.json configs[%d])" % (n, n, 3 if n >= 65536 else 1),
+            "rays_per_gpu": n, "micro_batch": a.micro_batch, "samples_per_ray": S, "weights": "random-init T_NeRF(512,4)",
+            "launch": "GPU arm: " + ("eager launches" if a.no_graph else "whole step captured once in a CUDA graph, replayed per step"),
+            "l2": "GPU arm: per-step working set (~10 GB of activations) far exceeds the 126 MB L2; no explicit flush",
+            "solar_rays": "GPU arm: drawn and built on the device every step (TrainStep solar_rng='device')",
+            "batchnorm": ("SyncBN: statistics over the rays of all ranks" if (a.sync_bn and world > 1) else
+                          "per-rank batch statistics (DDP semantics)" if world > 1 else "one batch")}
+
+
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+
+
+def ncu_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel, from the NAMED summary of the committed
+    `ncu --set full` captures (profiles/r02_ncu_traffic.json, written by scripts/ncu_traffic.py from the .ncu-rep files);
+    None when the file has no entry - a stale constant cannot survive a kernel change silently"""
+    try:
+        d = json.load(open(TRAFFIC_FILE))
+        e = d.get(key)
+        return None if e is None else float(e["dram_bytes"])
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def bench_args():
     import types
     return types.SimpleNamespace(n_samples=S, Use_Reg=True, Solar_Type_2=False, Use_MSE_loss=False, sc_lambda=0.03,
@@ -105,23 +135,17 @@ def bench_args():
 
 
 # ---------------------------------------------------------------------------------------------------------
-def run_reference(a):
-    """The reference algorithm on the host CPU (oracle port, all host threads): bounded sample per step."""
+def _oracle_stepper(n):
+    """one oracle training step (fwd + bwd) on n image + n solar rays -> callable"""
+    import numpy as np
     import torch as t
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
     from oracle import barron_loss
     from oracle import season_oracle as so
-    cores = os.cpu_count() or 1
-    t.set_num_threads(cores)
-    n = a.ref_rays
     args = so.default_args()
     P = so.init_params(seed=0)
     leaves = [v.requires_grad_(True) for k, v in P.items() if v.is_floating_point() and "running" not in k]
     ada = barron_loss.AdaptiveLossFunction(3, t.float32, "cpu", alpha_hi=2.99, alpha_init=2.0, scale_init=0.03, scale_lo=0.01)
     batch = so.synthetic_batch(n, seed=1)
-    import numpy as np
     H, WC = so.oma_w2l_h(), so.OMA_W2C
 
     def step():
@@ -130,7 +154,36 @@ def run_reference(a):
         for v in leaves:
             v.grad = None
         so.total_loss(L).backward()
+    return step
 
+
+def _best_cpu_sample(sizes=(256, 512, 1024)):
+    """the CPU's rays/s is not flat in the batch size (thread scaling vs cache): time one warm step per candidate sample
+    size and keep the FASTEST, so that the GPU arm is compared with the CPU's best -> (n, {n: rays/s})"""
+    seen = {}
+    for n in sizes:
+        step = _oracle_stepper(n)
+        step()
+        t0 = time.perf_counter()
+        step()
+        seen[n] = n / (time.perf_counter() - t0)
+    return max(seen, key=seen.get), seen
+
+
+def run_reference(a):
+    """The reference algorithm on the host CPU (oracle port, all host threads): bounded sample per step."""
+    import torch as t
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    t.set_num_threads(cores)
+    if a.ref_rays:
+        n, seen = a.ref_rays, {}
+    else:
+        n, seen = _best_cpu_sample()
+    step = _oracle_stepper(n)
     for _ in range(a.warmup):
         step()
     t0 = time.perf_counter()
@@ -138,44 +191,53 @@ def run_reference(a):
         step()
     dt = time.perf_counter() - t0
     val = n * a.steps / dt
-    sample = "%d image + %d solar rays per step, S=%d, Barron+solar loss, fwd+bwd, torch CPU fp32" % (n, n, S)
-    line = ({"impl": "reference", "metric": "training rays/s (4096-ray step, fwd+bwd)", "value": val, "unit": "rays/s",
-                      "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps,
-                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                      "config": {"workload": "train step, 4096 synthetic OMA_281-shaped rays + 4096 solar rays per GPU, S=96, "
-                                             "Barron + solar losses (BASELINE.json configs[1]); reference arm: bounded sample"},
-                      "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
-                      "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    sample = "%d image + %d solar rays per step (the fastest of the sample sizes tried: %s rays/s), S=%d, Barron+solar loss, " \
+             "fwd+bwd, torch CPU fp32, %d threads" % (n, n, {k: round(v, 1) for k, v in seen.items()}, S, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "rays/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(a, world),
+            "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), file=a.out, flush=True)
 
 
-def cpu_baseline(n_rays=512):
-    """oracle train step timed on the host cores (rank 0, N=1): ~10-30 s of CPU work."""
-    import numpy as np
+def cpu_baseline(render_legs=True):
+    """the oracle timed on the host cores (rank 0, N=1), bounded samples: the training step at the CPU's best sample size
+    (best of 3 after a warm-up) and - BASELINE.md section 3, C1 - the CLI render of a 64x64x96 view with estimated shadows
+    (mg_Img_Eval.py:96-115) and with the exact shadow march (:57-70) on a 16x16 crop (the full 64x64 took 709 s on 8 cores)"""
     import torch as t
-    from oracle import barron_loss
     from oracle import season_oracle as so
     cores = os.cpu_count() or 1
     t.set_num_threads(cores)
-    args = so.default_args()
-    P = so.init_params(seed=0)
-    leaves = [v.requires_grad_(True) for k, v in P.items() if v.is_floating_point() and "running" not in k]
-    ada = barron_loss.AdaptiveLossFunction(3, t.float32, "cpu", alpha_hi=2.99, alpha_init=2.0, scale_init=0.03, scale_lo=0.01)
-    batch = so.synthetic_batch(n_rays, seed=1)
-    st, en, vec, tm, _ = so.create_solar_rays_uniform(n_rays, so.OMA_W2C, so.oma_w2l_h(), np.random.RandomState(3),
-                                                      t.Generator().manual_seed(3))
+    n, seen = _best_cpu_sample((512, 1024))
+    step = _oracle_stepper(n)
     best = None
-    for i in range(4):
+    for i in range(3):
         t0 = time.perf_counter()
-        L, _ = so.get_loss(args, batch, P, 30, True, ada, solar=(st, en, vec, tm))
-        for v in leaves:
-            v.grad = None
-        so.total_loss(L).backward()
+        step()
         dt = time.perf_counter() - t0
-        if i > 0:
-            best = dt if best is None else min(best, dt)
-    return {"value": n_rays / best, "unit": "rays/s", "cores": cores, "kind": "port",
-            "sample": "%d image + %d solar rays, one train step (fwd+bwd), best of 3 after 1 warm-up, torch CPU fp32 oracle" % (n_rays, n_rays)}
+        best = dt if best is None else min(best, dt)
+    out = {"value": n / best, "unit": "rays/s", "cores": cores, "kind": "port",
+           "sample": "%d image + %d solar rays, one train step (fwd+bwd), best of 3 after warm-up, torch CPU fp32 oracle; "
+                     "one-step probes %s rays/s" % (n, n, {k: round(v, 1) for k, v in seen.items()})}
+    if render_legs:
+        P = so.init_params(seed=0)
+        W2C, H = so.OMA_W2C, so.oma_w2l_h()
+        t0 = time.perf_counter()
+        D = so.component_render_by_dir(P, [80, 0], [45, 135], 184 / 365, (64, 64, S), W2C, H, include_exact_solar=False)
+        so.get_imgs_from_img_dict(D, (64, 64, S))
+        d64 = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        D = so.component_render_by_dir(P, [80, 0], [45, 135], 184 / 365, (16, 16, S), W2C, H, include_exact_solar=True)
+        so.get_imgs_from_img_dict(D, (16, 16, S))
+        d16 = time.perf_counter() - t0
+        out["render"] = {"view_64x64x96_estimated_shadows": {"rays": 4096, "seconds": d64, "rays_per_s": 4096 / d64,
+                                                               "workload": "BASELINE.json configs[0]: component_render_by_dir + get_imgs_from_Img_Dict"},
+                         "view_16x16x96_exact_shadow_march": {"rays": 256, "seconds": d16, "rays_per_s": 256 / d16,
+                                                                "workload": "16x16 crop of configs[0]/[2] with the exact solar march (x16 for 64x64)"},
+                         "unit": "rays/s", "cores": cores, "kind": "port"}
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -283,56 +345,75 @@ def run_ours(a):
     if rank == 0 and not a.no_render:
         render = bench_render(snb, ts.network, dev, H, W2C, peaks)
         ts.network.train()
-    # ---- ray-sharded render at N GPUs (strong scaling of one fixed 1024x1024 view; final gather of 12 B/ray) -------------
+    # ---- ray-sharded render at N GPUs (strong scaling of one fixed 1024x1024 view; final gather of 12 B/ray to rank 0) ----
     sharded = None
     if not a.no_render:
         ts.network.eval()
         size_s = (1024, 1024, S)
-        snb.render_image_sharded(ts.network, [80, 0], [45, 135], 184 / 365, (64, 64, S), W2C, H, dev, rank, world)   # warm-up
-        # one-off per process: the pinned staging buffers of the image D2H path (the 64 x 64 warm-up is below its threshold)
-        from season_nerf_b200.render import device_to_numpy
-        device_to_numpy(t.zeros(1 << 20, dtype=t.float64, device=dev), chunk_bytes=32 << 20, min_bytes=4 << 20)
-        barrier()
-        e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
-        e0.record()
-        img, _ = snb.render_image_sharded(ts.network, [80, 0], [45, 135], 184 / 365, size_s, W2C, H, dev, rank, world)
-        e1.record()
-        barrier()
-        ms_r = e0.elapsed_time(e1)
-        if world > 1:
-            tt = t.tensor([ms_r], device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            ms_r = float(tt)
-        sharded = {"workload": "1024x1024x96 novel view (estimated shadows), rays sharded over %d GPU(s), float64 composite, "
-                               "final gather of the image (season_nerf_b200.render_image_sharded)" % world,
-                   "rays": size_s[0] * size_s[1], "ms": ms_r, "rays_per_s": size_s[0] * size_s[1] / (ms_r * 1e-3),
-                   "scaling": "strong", "finite": bool((img == img).all()),
-                   "mlp_tflops_algorithmic": size_s[0] * size_s[1] * RENDER_FLOP_PER_RAY / (ms_r * 1e-3) / 1e12}
+
+        def max_over_ranks(ms_):
+            if world > 1:
+                tt = t.tensor([ms_], device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                return float(tt)
+            return ms_
+
+        def timed_call(fn):
+            barrier()
+            e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+            w0 = time.perf_counter()
+            e0.record()
+            r = fn()
+            e1.record()
+            t.cuda.synchronize()                     # the call ends with the image on the host (rank 0): wall == device span
+            w1 = time.perf_counter()
+            barrier()
+            return r, max_over_ranks(max(e0.elapsed_time(e1), (w1 - w0) * 1e3))
+
+        render_full = lambda: snb.render_image_sharded(ts.network, [80, 0], [45, 135], 184 / 365, size_s, W2C, H, dev, rank, world)
+        render_full()                                # warm-up at the EXACT shape: gather buffers, NCCL channel set-up, pinned staging
+        reps_r = []
+        for _ in range(5):
+            (img, _), ms_r = timed_call(render_full)
+            reps_r.append(ms_r)
+        ms_r = sorted(reps_r)[len(reps_r) // 2]
+        n_view = size_s[0] * size_s[1]
+        sharded = {"workload": "1024x1024x96 novel view (estimated shadows), rays sharded over %d GPU(s), float64 composite, image "
+                               "gathered to rank 0 and copied to the host (season_nerf_b200.render_image_sharded)" % world,
+                   "rays": n_view, "ms": ms_r, "ms_reps": reps_r, "timing": "median of 5 after a same-shape warm-up; max over ranks; "
+                   "host copy of the image inside", "rays_per_s": n_view / (ms_r * 1e-3),
+                   "scaling": "strong", "finite": bool((img == img).all()) if img is not None else None,
+                   "mlp_tflops_algorithmic": n_view * RENDER_FLOP_PER_RAY / (ms_r * 1e-3) / 1e12}
         # ---- BASELINE.json configs[4] at N GPUs: 365 time-of-year renders of the same view, ray-sharded; every rank keeps its
-        # [T, rays/N, 3] float64 slab on the device (no gather: SURVEY 8e), time = max over ranks
+        # [T, rays/N, 3] float64 slab on the device (no gather: SURVEY 8e), time = max over ranks, median of 3
         T_year = 365
         times = np.stack([snb.encode_time(k / T_year) for k in range(T_year)], 0)
         with t.no_grad():
             cls_year = ts.network.get_class_only(t.tensor(times, dtype=t.float32, device=dev)).double().cpu().numpy()
-        barrier()
-        e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
-        e0.record()
-        lo_, hi_, slab, _ = snb.render_shard(ts.network, [80, 0], [45, 135], 0.0, size_s, W2C, H, dev, rank, world, class_vecs=cls_year)
-        e1.record()
-        barrier()
-        ms_y = e0.elapsed_time(e1)
+        sweep = lambda: snb.render_shard(ts.network, [80, 0], [45, 135], 0.0, size_s, W2C, H, dev, rank, world, class_vecs=cls_year)
+        reps_y = []
+        slab = None
+        for i in range(4):
+            del slab
+            (lo_, hi_, slab, _), ms_y = timed_call(sweep)
+            if i:
+                reps_y.append(ms_y)
+        ms_y = sorted(reps_y)[len(reps_y) // 2]
         fin = t.tensor([float(bool(t.isfinite(slab).all()))], device=dev)
         if world > 1:
-            tt = t.tensor([ms_y], device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            ms_y = float(tt)
             dist.all_reduce(fin, op=dist.ReduceOp.MIN)
         sharded["year_sweep"] = {"workload": "%d time-of-year renders of the 1024x1024 view (BASELINE.json configs[4]), rays sharded over "
                                              "%d GPU(s), each rank keeps its [T, rays/N, 3] float64 slab on the device" % (T_year, world),
-                                 "times": T_year, "ms": ms_y, "ray_renders_per_s": T_year * size_s[0] * size_s[1] / (ms_y * 1e-3),
+                                 "times": T_year, "ms": ms_y, "ms_reps": reps_y, "ray_renders_per_s": T_year * n_view / (ms_y * 1e-3),
                                  "slab_shape": list(slab.shape), "finite": bool(fin.item() > 0), "scaling": "strong"}
         del slab
         ts.network.train()
+
+    # ---- BASELINE.json configs[3]: 65 536 rays per GPU as 8 gradient-accumulating micro-batches of 8192, one optimiser step,
+    # NCCL gradient all-reduce at N > 1 (each micro-batch is its own BatchNorm batch: one 65 536-ray batch would need ~225 GB)
+    configs3 = None
+    if not a.no_configs3 and a.rays == 4096 and a.precision == "bf16":
+        configs3 = bench_configs3(snb, args, dev, H, W2C, world, rank, barrier, a)
 
     extras = None
     if rank == 0 and world == 1 and not a.no_extras:
@@ -377,7 +458,7 @@ def run_ours(a):
     achieved = flops_step / (gemm_ms * 1e-3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
     roofline = {"bound": "tensor", "kernel": "gemm2_bf16_kernel (tcgen05 cta_group::2, fused SIREN epilogues)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": 978.0e6, "peak_source": peaks["source"] + " sustained cuBLAS bf16",
+                "frac": achieved / peak, "traffic": ncu_traffic("gemm2_trunk_mean"), "traffic_source": os.path.relpath(TRAFFIC_FILE, ROOT), "peak_source": peaks["source"] + " sustained cuBLAS bf16",
                 "launches_per_step": n_gemm, "kernel_ms_per_step": gemm_ms, "step_ms": ms / a.steps,
                 "kernel_share_of_step": gemm_ms / (ms / a.steps),
                 "note": "achieved = algorithmic 2.086 GFLOP/ray-pair x rays per step / summed CUDA-event time of the GEMM launches of one step"}
@@ -386,36 +467,58 @@ def run_ours(a):
     # `traffic` = dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of that variant at M = 393216 from the
     # ncu --set full capture committed as profiles/r01_ncu_gemm2_variants_v4.txt (scripts/profile_gpu.sh step 2)
     if not a.no_trunk:
-        roofline["trunk_launches"] = bench_trunk_gemms(min(n, a.micro_batch or n) * S, peak, {"fwd_bn_stats": 760.9e6, "fwd_sin": 1153.3e6,
-                                                                      "dgrad_cos_bnsums": 1182.5e6, "wgrad_splitk": 823.7e6})
-    roofline["traffic_note"] = "achieved aggregates all tcgen05 GEMM launches of a step; traffic = dram bytes per launch averaged over " \
-                               "the 63 trunk-shaped launches of a step (16 fwd+stats, 15 fwd+sin, 17 dgrad, 15 wgrad; ncu --set full, " \
-                               "profiles/r01_ncu_gemm2_variants_v4.txt); per-variant figures next to their algorithmic bytes under trunk_launches"
+        roofline["trunk_launches"] = bench_trunk_gemms(min(n, a.micro_batch or n) * S, peak, {k: ncu_traffic("gemm2_" + k) for k in
+                                                                      ("fwd_bn_stats", "fwd_sin", "dgrad_cos_bnsums", "wgrad_splitk")})
+    roofline["traffic_note"] = "dram bytes per launch, mean over the trunk-shaped launches of a step (ncu --set full); per variant under trunk_launches"
 
-    out = {"metric": "training rays/s (4096-ray step, fwd+bwd)", "value": value, "unit": "rays/s", "n_gpus": world,
+    out = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world,
            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "bf16" if a.precision == "bf16" else "f32", "data": "synthetic",
-           "config": {"workload": "train step, %d synthetic OMA_281-shaped rays + %d solar rays per GPU, S=96, Barron + solar "
-                                  "losses, Adam+OneCycle (BASELINE.json configs[%d])" % (n, n, 3 if n >= 65536 else 1),
-                      "rays_per_gpu": n, "micro_batch": a.micro_batch, "samples_per_ray": S, "weights": "random-init T_NeRF(512,4)",
-                      "launch": "eager" if a.no_graph else "whole step captured once in a CUDA graph, replayed per step",
-                      "l2": "per-step working set (~10 GB of activations) far exceeds the 126 MB L2; no explicit flush",
-                      "solar_rays": "drawn and built on the device every step (TrainStep solar_rng='device')",
-                      "batchnorm": ("SyncBN: statistics over the rays of all ranks" if (a.sync_bn and world > 1) else
-                                    "per-rank batch statistics (DDP semantics)" if world > 1 else "one batch")},
+           "config": workload_config(a, world),
            "clocks": clocks, "gpu_launches": int(launches),
            "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                    "ms_per_step": ms_e / a.steps},
            "roofline": roofline}
+    if rank == 0 and world == 1 and not a.no_cpu:
+        out["cpu_baseline"] = cpu_baseline()
     if render is not None:
         out["render"] = render
     if sharded is not None:
         out["render_sharded"] = sharded
+    if configs3 is not None:
+        out["configs3"] = configs3
     if extras is not None:
         out.update(extras)
+    # compact digest of the secondary measurements, LAST in the line (the driver keeps the tail of stdout)
+    r3 = lambda x: None if x is None else float("%.4g" % x)
+    summ = {"train_ms": r3(ms / a.steps), "train_rays_s": r3(value), "e2e_rays_s": r3(e2e), "gemm_frac_sustained": r3(roofline["frac"]),
+            "step_tflops_frac_sustained": r3(flops_step / (ms / a.steps * 1e-3) / 1e12 / peak)}
+    if render is not None:
+        summ["render512_kernel_frac_burst"] = r3(render["roofline"]["frac"])
+        summ["render512_api_rays_s"] = r3(render["e2e_rays_per_s"])
+    if sharded is not None:
+        summ["render1024_ms_N%d" % world] = r3(sharded["ms"])
+        summ["render1024_rays_s"] = r3(sharded["rays_per_s"])
+        summ["year365_ms_N%d" % world] = r3(sharded["year_sweep"]["ms"])
+        summ["year365_ray_renders_s"] = r3(sharded["year_sweep"]["ray_renders_per_s"])
+    if configs3 is not None:
+        summ["configs3_ms"] = r3(configs3["ms_per_step"])
+        summ["configs3_rays_s"] = r3(configs3["value"])
+    if extras is not None:
+        summ["composite_fwd_frac_hbm"] = r3(extras["composite"]["fwd"]["frac"])
+        summ["composite_bwd_frac_hbm"] = r3(extras["composite"]["bwd"]["frac"])
+        summ["shadow512_s"] = r3(extras["shadow_march"]["seconds"])
+        summ["shadow512_frac_burst"] = r3(extras["shadow_march"]["roofline"]["frac"])
+        summ["year_sweep_kernel_ms"] = r3(extras["year_sweep"]["sweep_kernel_ms"])
+    cb = out.get("cpu_baseline")
+    if cb is not None:
+        summ["cpu_train_rays_s"] = r3(cb["value"])
+        if "render" in cb:
+            summ["cpu_render64_rays_s"] = r3(cb["render"]["view_64x64x96_estimated_shadows"]["rays_per_s"])
+            summ["cpu_exact16_rays_s"] = r3(cb["render"]["view_16x16x96_exact_shadow_march"]["rays_per_s"])
+        summ["cpu_cores"] = cb["cores"]
+    out["summary"] = summ
     if rank == 0:
-        if world == 1 and not a.no_cpu:
-            out["cpu_baseline"] = cpu_baseline()
         print(json.dumps(out), file=a.out, flush=True)
     if world > 1:
         # the captured step graphs hold NCCL kernels: release them before the communicator goes away (tearing the process
@@ -427,6 +530,59 @@ def run_ours(a):
         t.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bench_configs3(snb, args, dev, H, W2C, world, rank, barrier, a, rays=65536, micro=8192, steps=3):
+    """BASELINE.json configs[3]: data-parallel step with 65 536 rays per GPU (+ as many solar rays), 8 micro-batches of 8192
+    whose gradients accumulate before ONE NCCL all-reduce and ONE optimiser step; device-resident inputs; the same barrier /
+    CUDA-event / max-over-ranks timing as the headline"""
+    import numpy as np
+    import torch as t
+    import torch.distributed as dist
+    t.manual_seed(0)
+    ts3 = snb.TrainStep(args, dev, H, W2C, world_size=world, precision="bf16", use_graph=not a.no_graph, micro_batch=micro)
+    if world > 1:
+        for p_ in ts3.params + ts3.ada_params:
+            dist.broadcast(p_.data, 0)
+    g = t.Generator().manual_seed(11 + rank)
+    xy = (t.rand(rays, 2, generator=g) * 2 - 1) * 0.8
+    dxy = (t.rand(rays, 2, generator=g) * 2 - 1) * 0.2
+    el = t.deg2rad(20 + 50 * t.rand(41, generator=g))
+    az = 2 * np.pi * t.rand(41, generator=g)
+    sun = t.stack([t.cos(el) * t.sin(az), t.cos(el) * t.cos(az), t.sin(el)], 1)
+    f = t.rand(41, generator=g)
+    tim = t.stack([t.cos(2 * np.pi * f), t.sin(2 * np.pi * f), t.full_like(f, np.cos(2 * np.pi * .7)), t.full_like(f, np.sin(2 * np.pi * .7))], 1)
+    img = t.randint(0, 41, (rays,), generator=g)
+    batch = {"Top": t.cat([xy, t.ones(rays, 1)], 1), "Bot": t.cat([xy + dxy, -t.ones(rays, 1)], 1), "Sun_Angle": sun[img],
+             "Time_Encoded": tim[img], "GT_Color": t.rand(rays, 3, generator=g)}
+    batch = {k: v.contiguous().to(dev) for k, v in batch.items()}
+    for i in range(4):                    # 2 eager steps, the capture, one replay
+        ts3.step(batch, i)
+    barrier()
+    e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        ts3.step(batch, 4 + i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tt = t.tensor([ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt)
+    loss = float(ts3.last_loss)
+    out = {"workload": "BASELINE.json configs[3]: %d rays + %d solar rays per GPU per step, %d micro-batches of %d (gradient accumulation, "
+                       "each its own BatchNorm batch), NCCL gradient all-reduce over %d GPU(s), Adam+OneCycle" % (rays, rays, rays // micro, micro, world),
+           "rays_per_gpu": rays, "micro_batch": micro, "n_gpus": world, "steps": steps, "ms_per_step": ms / steps,
+           "value": world * rays * steps / (ms * 1e-3), "unit": "rays/s", "scaling": "weak", "loss_finite": bool(loss == loss),
+           "tflops_algorithmic_per_gpu": TRAIN_FLOP_PER_RAY * rays * steps / (ms * 1e-3) / 1e12}
+    ts3._graphs.clear()
+    del ts3
+    import gc
+    gc.collect()
+    t.cuda.synchronize()
+    t.cuda.empty_cache()
+    return out
 
 
 def bench_trunk_gemms(M, peak, traffic, reps=5):
@@ -520,7 +676,7 @@ def bench_render(snb, net, dev, H, W2C, peaks, size=512, reps=3):
     return {"workload": "%dx%dx%d view render, estimated shadows (BASELINE.json configs[2] without the exact march)" % (size, size, S),
             "kernel_rays_per_s": pts_total / S / (k_ms * 1e-3), "e2e_rays_per_s": N / e2e_s,
             "roofline": {"bound": "tensor", "kernel": "fused_eval2_kernel (tcgen05 cta_group::2)", "achieved": achieved, "peak": peak,
-                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": 460.3e6,
+                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_traffic("fused_eval2_full"),
                          "peak_source": peaks["source"] + " burst cuBLAS bf16", "launches": len(times),
                          "ms_per_launch": k_ms / len(times),
                          "frac_of_sustained_peak": achieved / peaks["bf16_tflops_sustained"],
@@ -547,7 +703,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=4096)
-    ap.add_argument("--ref-rays", type=int, default=256, dest="ref_rays")
+    ap.add_argument("--ref-rays", type=int, default=0, dest="ref_rays",
+                    help="rays per CPU sample step of the reference arm (0 = probe 256 / 512 / 1024 and keep the fastest)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-render", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -558,6 +715,7 @@ def main():
                          "--rays 65536 (BASELINE.json configs[3]): one 65536-ray BatchNorm batch would need ~225 GB of activations")
     ap.add_argument("--sync-bn", action="store_true", dest="sync_bn",
                     help="N > 1: BatchNorm statistics over the rays of all ranks (the reference's single-batch semantics)")
+    ap.add_argument("--no-configs3", action="store_true", dest="no_configs3", help="skip the 65536-ray micro-batched step (BASELINE.json configs[3])")
     ap.add_argument("--no-graph", action="store_true", help="eager kernel launches instead of the captured CUDA graph")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else max(a.warmup, 1)

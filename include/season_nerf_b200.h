@@ -26,6 +26,8 @@ extern "C" {
 
 /* library / device info ------------------------------------------------------------------- */
 int snb_version(void);
+/* multiprocessor count of the current CUDA device (queried once per device): sizes every persistent grid */
+int snb_num_sms(void);
 /* number of kernels this library has launched since load (bench.py "gpu_launches") */
 long long snb_launch_count(void);
 const char* snb_error_string(int code);
@@ -189,22 +191,16 @@ int snb_convert(const void* src, int src_dtype, int lds, void* dst, int dst_dtyp
                 void* stream);
 
 /* ---- fused eval-mode network (render): T_NeRF_net_v2.py:75-105,131-151,169-170 + G_NeRF.py:74-133 --------------
- * One persistent tcgen05 kernel runs encoding -> trunk -> sigma/colour heads -> solar branch -> adjust branch for
- * tiles of 128 sample points with activations kept in shared memory / TMEM.  `program` is the device image built by
- * season_nerf_b200/packing.py (schedule tables + biases + BatchNorm-folded bf16 weights pre-swizzled into the
- * shared-memory tile layout); the *_off arguments are byte offsets of its sections, n_mma / n_epi the table lengths.
+ * One persistent tcgen05 kernel runs encoding -> trunk -> sigma/colour heads -> solar branch -> adjust branch with the
+ * activations kept in shared memory / TMEM: two CTAs of a cluster render a tile of 256 sample points with
+ * tcgen05.mma.cta_group::2 and stage half of every weight tile each.  `program` is the device image built by
+ * season_nerf_b200/packing2.py: schedule tables, biases and the BatchNorm-folded bf16 weights as ONE row-major
+ * [w_rows, 64] matrix (TMA applies the 128-byte swizzle); the *_off arguments are byte offsets of its sections,
+ * n_mma / n_epi the table lengths.
  *   pts [M,3] f32; sun [ceil(M/S),3] f32 (one solar direction per S consecutive points; S=1: per point; may be
  *   NULL for a sigma-only program).
  * outputs (float32, any may be NULL): rho_raw [M], pos4 [M,4] = (sigma, colour[3]), vis_raw [M], adj [M,12]
  * (class-major [C,3]), all BEFORE softplus / sigmoid. */
-int snb_fused_eval(const void* program, unsigned n_mma, unsigned n_epi, unsigned mma_off, unsigned epi_off,
-                   unsigned bias_off, unsigned w_off, const float* pts, long long M, int S, const float* sun,
-                   float* rho_raw, float* pos4, float* vis_raw, float* adj, void* stream);
-
-/* CTA-pair edition of the fused render kernel (the one the product dispatches to): two CTAs of a cluster render a
- * tile of 256 points with tcgen05.mma.cta_group::2 and stage half of every weight tile each.  `program` is the device
- * image built by season_nerf_b200/packing2.py: schedule tables, biases and the BatchNorm-folded bf16 weights as ONE
- * row-major [w_rows, 64] matrix (TMA applies the 128-byte swizzle).  Same inputs / outputs as snb_fused_eval. */
 int snb_fused_eval2(const void* program, unsigned n_mma, unsigned n_epi, unsigned mma_off, unsigned epi_off,
                     unsigned bias_off, unsigned w_off, unsigned w_rows, const float* pts, long long M, int S,
                     const float* sun, float* rho_raw, float* pos4, float* vis_raw, float* adj, void* stream);

@@ -16,6 +16,7 @@ _p, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 # name -> argtypes; every function returns int (0 = ok) unless listed in _RESTYPES
 SIGNATURES = {
     "snb_version": [],
+    "snb_num_sms": [],
     "snb_launch_count": [],
     "snb_error_string": [_i],
     "snb_sample_rays": [_p, _p, _p, _i, _i, _i, _p, _p, _p],
@@ -42,7 +43,6 @@ SIGNATURES = {
     "snb_sine_bwd_reduce": [_p, _i, _p, _i, _p, _p, _p, _p, _ll, _i, _i, _p, _p, _p],
     "snb_sine_bwd_apply": [_p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _ll, _i, _i, _p],
     "snb_convert": [_p, _i, _i, _p, _i, _i, _ll, _i, _p],
-    "snb_fused_eval": [_p, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, _p, _ll, _i, _p, _p, _p, _p, _p, _p],
     "snb_fused_eval2": [_p, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, _p, _ll, _i, _p, _p, _p, _p, _p, _p],
 }
 _RESTYPES = {"snb_launch_count": _ll, "snb_error_string": C.c_char_p}
@@ -59,14 +59,15 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        from . import build as _build
-        try:
-            _build.build()
-        except Exception as e:  # no silent fallback: the product path needs the CUDA library
-            raise SeasonNerfCudaError(
-                "season_nerf_b200: CUDA library %s is missing and could not be built (%s). "
-                "Run `python -m season_nerf_b200.build`; there is no CPU fallback." % (LIB_PATH, e))
+    # build() is a no-op when lib/build.stamp equals the digest of the current sources: a library left over from older
+    # sources (stale in-tree .so next to new ctypes signatures = undefined behaviour) is rebuilt here, loudly or not at all
+    from . import build as _build
+    try:
+        _build.build()
+    except Exception as e:  # no silent fallback: the product path needs the CUDA library
+        raise SeasonNerfCudaError(
+            "season_nerf_b200: CUDA library %s is missing or stale and could not be built (%s). "
+            "Run `python -m season_nerf_b200.build`; there is no CPU fallback." % (LIB_PATH, e))
     lib = C.CDLL(LIB_PATH)
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError here = header/library mismatch: fail loudly

@@ -21,7 +21,9 @@
 
 namespace snb {
 
-constexpr int kNumSMs = 148;  // B200
+// SM count of the current device, queried once per device (a full B200 has 148; a MIG slice or another SKU has fewer:
+// every persistent grid and split-K factor is sized from this, never from a compile-time constant)
+int num_sms();
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -53,7 +55,7 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(flo
 
 inline int grid_for(long long work_items, int per_block, int max_waves = 32) {
   long long b = (work_items + per_block - 1) / per_block;
-  long long cap = (long long)kNumSMs * max_waves;
+  long long cap = (long long)num_sms() * max_waves;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (int)b;

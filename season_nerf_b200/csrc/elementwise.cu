@@ -450,7 +450,7 @@ static inline VecLaunch vec_launch(long long M, int N, int ld0, int ld1, int ld2
   if (ty < 1) ty = 1;
   v.block = dim3(tx, ty);
   long long gx = (M + ty - 1) / ty;
-  long long cap = (long long)kNumSMs * max_waves;
+  long long cap = (long long)num_sms() * max_waves;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   v.grid = dim3((unsigned)gx, by);

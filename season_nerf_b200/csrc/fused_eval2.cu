@@ -375,7 +375,7 @@ extern "C" int snb_fused_eval2(const void* program, unsigned n_mma, unsigned n_e
       return (int)e;
     }
   }
-  const int num_pairs = kNumSMs / 2;
+  const int num_pairs = num_sms() / 2;
   const int grid = 2 * (p.num_tiles < num_pairs ? p.num_tiles : num_pairs);
   if (epi_warps == 8)
     f2::fused_eval2_kernel<8><<<grid, 32 * 10, f2::kSmem, st>>>(t128, t8, p);

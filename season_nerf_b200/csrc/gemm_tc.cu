@@ -288,7 +288,7 @@ int snb_gemm_bf16_tc(const void* A, int lda, int a_t, const void* B, int ldb, in
   int splits = 1;
   if (accumulate == 2) {  // split-K for the (few output tiles, huge K) weight-gradient shape
     const int tiles = p.tiles_m * p.tiles_n;
-    splits = (2 * kNumSMs + tiles - 1) / tiles;
+    splits = (2 * num_sms() + tiles - 1) / tiles;
     if (splits > num_kb) splits = num_kb;
     if (splits < 1) splits = 1;
   }
@@ -306,7 +306,7 @@ int snb_gemm_bf16_tc(const void* A, int lda, int a_t, const void* B, int ldb, in
   if (rc) return rc;
 
   const int total = p.tiles_m * p.tiles_n * p.splits;
-  const int grid = total < kNumSMs ? total : kNumSMs;
+  const int grid = total < num_sms() ? total : num_sms();
 #define SNB_LAUNCH_GEMM(AT, BT)                                                                             \
   do {                                                                                                      \
     static bool attr_set = false;                                                                           \

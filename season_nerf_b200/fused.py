@@ -1,16 +1,12 @@
-"""Host side of the fused render kernel (csrc/fused_eval.cu): program cache + dispatch.
+"""Host side of the fused render kernel (csrc/fused_eval2.cu): program cache + dispatch.
 
-The packed program (packing.build_program) is a derived cache of the module's parameters and BatchNorm buffers,
+The packed program (packing2.build_program) is a derived cache of the module's parameters and BatchNorm buffers,
 rebuilt whenever any of them changes (tensor version counters) and kept resident in HBM."""
 import ctypes as C
-import os
 
 import torch as t
 
-from . import _lib, ops, packing, packing2
-
-# SNB_FUSED_V1=1 selects the single-CTA kernel (csrc/fused_eval.cu); default is the CTA-pair kernel (fused_eval2.cu)
-USE_V1 = os.environ.get("SNB_FUSED_V1", "0") == "1"
+from . import _lib, ops, packing2
 
 
 def usable(net, pts):
@@ -28,17 +24,17 @@ def _versions(net):
 
 def _program(net, sigma_only, device):
     cache = net.__dict__.setdefault("_fused_programs", {})
-    key = (bool(sigma_only), str(device), USE_V1)
+    key = (bool(sigma_only), str(device))
     ver = _versions(net)
     hit = cache.get(key)
     if hit is not None and hit[0] == ver:
         return hit[1], hit[2]
     sd = {k: v.detach().float().cpu() for k, v in net.state_dict().items()}
-    pk = packing if USE_V1 else packing2
+    pk = packing2
     blob, info = pk.build_program(sd, sigma_only=sigma_only)
     dev_blob = t.from_numpy(blob).to(device)
     hdr = blob[:pk.HEADER_DT.itemsize].view(pk.HEADER_DT)[0]
-    meta = tuple(int(hdr[k]) for k in ("n_mma", "n_epi", "mma_off", "epi_off", "bias_off", "w_off") + (() if USE_V1 else ("w_rows",)))
+    meta = tuple(int(hdr[k]) for k in ("n_mma", "n_epi", "mma_off", "epi_off", "bias_off", "w_off", "w_rows"))
     cache[key] = (ver, dev_blob, meta)
     return dev_blob, meta
 
@@ -56,7 +52,7 @@ def run(net, pts, sun, S, sigma_only=False):
         rho, pos4, vis, adj = None, mk(M, 4), mk(M), mk(M, 12)
         sun = sun.float().contiguous()
     p = lambda x: None if x is None else C.c_void_p(x.data_ptr())
-    fn = _lib.load().snb_fused_eval if USE_V1 else _lib.load().snb_fused_eval2
+    fn = _lib.load().snb_fused_eval2
     _lib.check(fn(p(blob), *meta, p(pts), M, int(S), p(sun), p(rho), p(pos4), p(vis), p(adj),
                                           ops._stream()))
     return rho, pos4, vis, adj

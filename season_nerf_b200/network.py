@@ -30,6 +30,7 @@ FUSE_EPILOGUES = _os.environ.get("SNB_FUSE_EPILOGUES", "1") != "0"
 OVERLAP = _os.environ.get("SNB_OVERLAP", "0") == "1"
 _side_streams = {}
 _consts = {}
+_capture_epoch = [0]        # bumped by train.TrainStep before every CUDA-graph capture (see _Pass._wc)
 
 
 def const_vec(n, value, device):
@@ -451,7 +452,11 @@ class _Pass:
         of the spec; a CUDA-graph replay bumps the version counters, see train.TrainStep)."""
         key = (tuple((l.weight._version, l.bias._version, l.weight.data_ptr()) for l in spec.lin), self.dt, spec.kp)
         hit = spec.lin[0].__dict__.get("_snb_wc")
-        if hit is not None and hit[0] == key:
+        capturing = t.cuda.is_current_stream_capturing()
+        # inside a CUDA-graph capture the staging MUST be recorded (a warm cache would freeze the weights of every replay
+        # while the in-graph optimiser updates the fp32 parameters); the first pass of a capture restages, later passes of
+        # the same capture (solar pass after the image pass) reuse what that capture staged
+        if hit is not None and hit[0] == key and (not capturing or hit[3] == _capture_epoch[0]):
             return hit[1], hit[2]
         W = t.cat([l.weight for l in spec.lin], 0) if len(spec.lin) > 1 else spec.lin[0].weight
         if spec.kp == W.shape[1]:
@@ -461,7 +466,7 @@ class _Pass:
         ops.convert(W.detach(), Wc[:, :W.shape[1]])
         b = t.cat([l.bias for l in spec.lin], 0) if len(spec.lin) > 1 else spec.lin[0].bias
         b = b.detach().float().contiguous()
-        spec.lin[0].__dict__["_snb_wc"] = (key, Wc, b)
+        spec.lin[0].__dict__["_snb_wc"] = (key, Wc, b, _capture_epoch[0] if capturing else None)
         return Wc, b
 
     def _buf(self, name, rows, width, dtype=None, zero=False):

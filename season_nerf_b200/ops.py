@@ -203,6 +203,9 @@ def cli_composite(rho, deltas, base, vis, adj, cls, exact_vis=None):
     raw_e = mk(N) if exact_vis is not None else None
     ins = [x.contiguous() for x in (rho, deltas, base, vis, adj)]
     ev = None if exact_vis is None else exact_vis.contiguous()
+    if any(x.dtype != rho.dtype for x in ins) or (ev is not None and ev.dtype != rho.dtype):
+        raise TypeError("cli_composite: all components (exact_vis included) must share one dtype, got %s"
+                        % [str(x.dtype) for x in ins + ([ev] if ev is not None else [])])
     cls = _cuda(cls, torch.float64).contiguous()
     if N == 0:
         return base_img, season, extreme, raw, raw_e
@@ -225,6 +228,10 @@ def cli_classic_shadow(rho, deltas, base, vis, adj, sky, cls):
     return out
 
 
+# limits of snb_year_sweep (csrc/composite.cu): checked here so that callers fail before any rendering work
+YEAR_SWEEP_MAX_S, YEAR_SWEEP_MAX_C, YEAR_SWEEP_MAX_CLS_BYTES = 128, 4, 40 * 1024
+
+
 def year_sweep(rho, deltas, base, adj, cls, shade=None, out=None, ps_weight=None):
     """mg_Img_Eval.py:192-228 recombination for T class vectors at once -> [T,N,3] f64 (times shade [N,3] f64 if given).
     ps_weight [N,S] (same dtype as rho) multiplies PS per sample (classic-shadow alignment, mg_Img_Eval.py:448-449)."""
@@ -232,7 +239,13 @@ def year_sweep(rho, deltas, base, adj, cls, shade=None, out=None, ps_weight=None
     Cn, T = adj.shape[2], cls.shape[0]
     if out is None:
         out = torch.empty(T, N, 3, device=rho.device, dtype=torch.float64)
+    if S > YEAR_SWEEP_MAX_S or Cn > YEAR_SWEEP_MAX_C or T * Cn * 8 > YEAR_SWEEP_MAX_CLS_BYTES:
+        raise ValueError("year_sweep: the register-resident recombination kernel takes S <= %d samples per ray, C <= %d classes and "
+                         "T*C*8 <= %d bytes of class vectors per launch (got S=%d, C=%d, T=%d); split T or render with fewer samples"
+                         % (YEAR_SWEEP_MAX_S, YEAR_SWEEP_MAX_C, YEAR_SWEEP_MAX_CLS_BYTES, S, Cn, T))
     ins = [x.contiguous() for x in (rho, deltas, base, adj)]
+    if any(x.dtype != rho.dtype for x in ins):
+        raise TypeError("year_sweep: all components must share one dtype")
     cls = _cuda(cls, torch.float64).contiguous()
     if shade is not None:
         shade = _cuda(shade, torch.float64, "shade").contiguous()

@@ -25,7 +25,6 @@ fallback.
 import numpy as np
 import torch as t
 
-from .packing import fold_layer
 
 N_SLOTS = 9
 N_REGIONS = 2
@@ -46,6 +45,19 @@ assert MMA_DT.itemsize == 16 and EPI_DT.itemsize == 16
 HEADER_DT = np.dtype([("magic", "<u4"), ("n_mma", "<u4"), ("n_epi", "<u4"), ("mma_off", "<u4"), ("epi_off", "<u4"),
                       ("bias_off", "<u4"), ("w_off", "<u4"), ("w_rows", "<u4"), ("total", "<u4")])
 MAGIC = 0x534E4232
+
+
+def fold_layer(sd, name, omega=30.0, eps=1e-5):
+    """-> (W' [out,in] f32, b' [out] f32) with eval-mode BatchNorm and omega folded in."""
+    W = sd[name + ".linear.weight"].detach().float().cpu()
+    b = sd[name + ".linear.bias"].detach().float().cpu()
+    if (name + ".norm.weight") in sd:
+        inv = 1.0 / t.sqrt(sd[name + ".norm.running_var"].detach().float().cpu() + eps)
+        a = sd[name + ".norm.weight"].detach().float().cpu() * inv
+        c = sd[name + ".norm.bias"].detach().float().cpu() - sd[name + ".norm.running_mean"].detach().float().cpu() * a
+    else:
+        a, c = t.ones_like(b), t.zeros_like(b)
+    return (a * omega).unsqueeze(1) * W, a * omega * b + c
 
 
 def build_program(sd, sigma_only=False):

@@ -234,8 +234,11 @@ def get_imgs_from_Img_Dict(Img_Dict, out_img_size: tuple, use_classic_shadows: b
     """mg_Img_Eval.py:123-190: float64 compositing of the cached components into images."""
     has_exact = "Exact_Solar" in Img_Dict.keys()
     keys = ["Rho", "Deltas", "Base_Col", "Est_Solar_Vis", "Adjust_col", "Output_class", "Sky_Col"]
-    rho, dl, base, vis, adj, ocl, skyc = _device_components(Img_Dict, keys)
-    ev = _device_components(Img_Dict, ["Exact_Solar"])[0] if has_exact else None
+    # ONE fetch for all components (Exact_Solar included): either every array is the resident float32 device tensor or -
+    # as soon as the caller replaced any of them - every array is uploaded as float64; never a mix of element types
+    comps = _device_components(Img_Dict, keys + (["Exact_Solar"] if has_exact else []))
+    rho, dl, base, vis, adj, ocl, skyc = comps[:7]
+    ev = comps[7] if has_exact else None
     N, S = rho.shape[0], rho.shape[1]
     Sky_Col = skyc[0, 0].double().cpu().numpy()                                   # ray 0 / sample 0 (:125-126)
     cls = ocl[0, 0].double()
@@ -366,9 +369,12 @@ def render_shard(the_network, view_el_az, sun_el_az, time_frac, out_img_size, W2
 
 
 def render_image_sharded(the_network, view_el_az, sun_el_az, time_frac, out_img_size, W2C, W2L_H, device, rank=0,
-                         world_size=1, include_exact_solar=False):
-    """Ray-sharded novel-view render with the final gather (12 bytes of colour + a mask value per ray): every rank returns
-    the full [H,W,3] float64 image and the [H,W] shadow mask.  world_size 1 needs no process group."""
+                         world_size=1, include_exact_solar=False, dst=0):
+    """Ray-sharded novel-view render with the final gather (12 bytes of colour + a mask value per ray).
+    dst=r (default 0): rank r returns the full [H,W,3] float64 image and the [H,W] shadow mask, every other rank returns
+    (None, None) - ONE gather to one GPU and ONE device->host copy of the image.  dst=None: every rank returns the image
+    (all_gather + a host copy per rank: world_size times the PCIe / host traffic; kept for callers that need it).
+    world_size 1 needs no process group."""
     from .train import gather_rows
     import os
     import sys
@@ -385,14 +391,15 @@ def render_image_sharded(the_network, view_el_az, sun_el_az, time_frac, out_img_
         t1 = time.perf_counter()
     both = t.cat([rgb, mask.unsqueeze(1)], 1)                   # colour + mask travel together: one gather, one D2H copy
     if world_size > 1:
-        both = gather_rows(both, H * W, rank, world_size)
+        both = gather_rows(both, H * W, rank, world_size, dst=dst)
     if timing:
         t.cuda.synchronize()
         t2 = time.perf_counter()
-    # split on the device (strided host copies of a 33 MB array cost 30 ms per rank when 8 ranks do them at once)
-    # and leave through the pinned staging path: N ranks copying into fresh pageable memory at once contend on the host
-    out = (device_to_numpy(both[:, :3].contiguous(), chunk_bytes=32 << 20, min_bytes=4 << 20).reshape(H, W, 3),
-           device_to_numpy(both[:, 3].contiguous(), chunk_bytes=32 << 20, min_bytes=4 << 20).reshape(H, W))
+    out = (None, None)
+    if both is not None:
+        # split on the device (strided host copies of a 33 MB array cost 30 ms) and leave through the pinned staging path
+        out = (device_to_numpy(both[:, :3].contiguous(), chunk_bytes=32 << 20, min_bytes=4 << 20).reshape(H, W, 3),
+               device_to_numpy(both[:, 3].contiguous(), chunk_bytes=32 << 20, min_bytes=4 << 20).reshape(H, W))
     if timing:
         t3 = time.perf_counter()
         sys.stderr.write("[shard timing] rank %d: render %.1f ms, gather %.1f ms, to host %.1f ms\n"

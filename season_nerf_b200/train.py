@@ -31,9 +31,11 @@ def shard_range(n, rank, world_size):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def gather_rows(local, n_total, rank, world_size):
-    """all_gather of per-rank row blocks of unequal length (final gather of a ray-sharded render) -> [n_total, ...].
-    One collective into one flat buffer (equal, padded chunks); the valid rows are sliced out afterwards."""
+def gather_rows(local, n_total, rank, world_size, dst=None):
+    """Final gather of a ray-sharded render: per-rank row blocks of unequal length -> [n_total, ...].
+    dst=None: every rank receives the rows (all_gather).  dst=r: only rank r receives them (`gather`; the other ranks
+    return None) - the image leaves the box once, from one GPU, instead of world_size redundant device->host copies.
+    One collective on equal, padded chunks; the valid rows are sliced out afterwards."""
     sizes = [shard_range(n_total, r, world_size)[1] - shard_range(n_total, r, world_size)[0] for r in range(world_size)]
     mx = max(sizes)
     tail = tuple(local.shape[1:])
@@ -42,6 +44,12 @@ def gather_rows(local, n_total, rank, world_size):
     else:
         pad = t.zeros((mx,) + tail, dtype=local.dtype, device=local.device)
         pad[:local.shape[0]] = local
+    if dst is not None:
+        outs = [t.empty_like(pad) for _ in range(world_size)] if rank == dst else None
+        dist.gather(pad, outs, dst=dst)
+        if rank != dst:
+            return None
+        return t.cat([o[:s_] for o, s_ in zip(outs, sizes)], 0)
     flat = t.empty((world_size * mx,) + tail, dtype=local.dtype, device=local.device)
     try:
         dist.all_gather_into_tensor(flat, pad)
@@ -255,6 +263,8 @@ class TrainStep:
             from . import _lib
             l0 = _lib.launch_count()
             g_fb = t.cuda.CUDAGraph()
+            from . import network as _nw
+            _nw._capture_epoch[0] += 1          # weights staged by earlier passes / captures are not reused inside this one
             with t.cuda.graph(g_fb):
                 st["loss"], st["total"] = self._fwd_bwd(st["batch"], current_step, 1.0 / k, solar=st["solar"],
                                                         ts=st["ts_img"], solar_ts=st["ts_sol"])

@@ -39,6 +39,9 @@ def _worker(rank, world, port, q):
     full = t.arange(n * 3, dtype=t.float32).reshape(n, 3)
     out = gather_rows(full[lo:hi].clone(), n, rank, world)
     ok = ok and t.equal(out, full)
+    # gather to ONE rank (final gather of render_image_sharded): rank 1 receives every row, rank 0 nothing
+    out1 = gather_rows(full[lo:hi].clone(), n, rank, world, dst=1)
+    ok = ok and ((out1 is None) if rank == 0 else t.equal(out1, full))
     # SyncBN plumbing: column statistics summed over the ranks; the Albedo_Color minimum is owned by exactly one rank
     from season_nerf_b200.network import _allreduce_pair
     from season_nerf_b200.engine import owns_global_min

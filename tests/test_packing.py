@@ -4,7 +4,6 @@ import numpy as np
 import torch as t
 
 from oracle import season_oracle as so
-from season_nerf_b200 import packing
 
 
 def _inputs(n, seed=1):
@@ -21,11 +20,11 @@ import pytest
 from season_nerf_b200 import packing2
 
 
-@pytest.mark.parametrize("pk", [packing, packing2])
+@pytest.mark.parametrize("pk", [packing2])
 def test_program_matches_oracle_network(params0, pk):
     packing = pk
     blob, info = packing.build_program(params0)
-    assert info["n_mma"] == (370 if pk.__name__.endswith("packing") else 193) and blob.nbytes % 128 == 0
+    assert info["n_mma"] == 193 and blob.nbytes % 128 == 0
     hdr = blob[:packing.HEADER_DT.itemsize].view(packing.HEADER_DT)[0]
     assert int(hdr["magic"]) == packing.MAGIC and int(hdr["w_off"]) % 1024 == 0
     X, sun, Time, enc, senc = _inputs(192)
@@ -37,7 +36,7 @@ def test_program_matches_oracle_network(params0, pk):
     assert float((outs[packing.OUT_ADJ] - adj.reshape(-1, 12)).abs().max()) < 3e-2
 
 
-@pytest.mark.parametrize("pk", [packing, packing2])
+@pytest.mark.parametrize("pk", [packing2])
 def test_sigma_only_program(params0, pk):
     packing = pk
     _, info = packing.build_program(params0, sigma_only=True)
@@ -49,7 +48,7 @@ def test_sigma_only_program(params0, pk):
     assert all(int(e["kind"]) != packing.K_ENC_SUN for e in info["epi"])
 
 
-@pytest.mark.parametrize("pk", [packing, packing2])
+@pytest.mark.parametrize("pk", [packing2])
 def test_schedule_checker_catches_hazards(params0, pk):
     packing = pk
     _, info = packing.build_program(params0)
