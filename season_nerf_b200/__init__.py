@@ -7,6 +7,7 @@ Public surface mirrors the reference's Python API for this path (SURVEY.md secti
   component_render_by_dir/_by_P, _internal_render,
   get_imgs_from_Img_Dict, get_imgs_from_Img_Dict_t_step       <- T_NeRF_Eval_Utils/mg_Img_Eval.py
   Quick_Run_Net, encode_time                                  <- T_NeRF_Full_2/Quick_Run.py
+  T_NeRF_Net_Tool, Net_tool                                   <- T_NeRF_Full_2/Net_Tool_2.py, mg_run_NeRF.py
   world_angle_2_local_vec                                     <- all_NeRF/mg_unit_converter.py
 `season_nerf_b200.compat.install()` registers these under the reference's module names.
 """
@@ -16,6 +17,7 @@ from .data import RayTable, data_to_dict
 from .engine import (All_in_One_Eval, create_solor_rays_uniform, get_PV, sample_pt_coarse, sample_ts,
                      zero_invalid_pts)
 from .geometry import LLA_get_vec, encode_time, ray_table_from_P, world_angle_2_local_vec
+from .net_tool import ColorTable, Net_tool, T_NeRF_Net_Tool
 from .network import G_NeRF_Net_Classic, PE_Encode, SineLayer, T_NeRF
 from .quick_run import Quick_Run_Net
 from .render import (DeviceImgDict, _internal_render, component_render_by_dir, component_render_by_P,

@@ -19,11 +19,15 @@ _HOT = {
     "T_NeRF_Full_2.Eval_Tools_2": ("engine", ["All_in_One_Eval", "get_PV", "create_solor_rays_uniform", "sample_pt_coarse"]),
     "T_NeRF_Full_2.Quick_Run": ("quick_run", ["Quick_Run_Net", "encode_time", "All_in_One_Eval", "create_solor_rays_uniform"]),
 }
+# the training driver: `from T_NeRF_Full_2.Net_Tool_2 import T_NeRF_Net_Tool` (main.py:12) -> season_nerf_b200.net_tool
+_NET_TOOL = {"T_NeRF_Full_2.Net_Tool_2": ("net_tool", ["T_NeRF_Net_Tool", "Net_tool", "T_NeRF", "All_in_One_Eval", "AdaptiveLossFunction",
+                                                        "get_output_loc_lin_first"])}
 _PATCH = {
     "misc": ("engine", ["sample_pt_coarse", "zero_invalid_pts"], "network", ["SineLayer", "PE_Encode"]),
     "T_NeRF_Eval_Utils.mg_Img_Eval": ("render", ["_internal_render", "component_render_by_dir", "component_render_by_P",
                                                  "get_imgs_from_Img_Dict", "get_imgs_from_Img_Dict_t_step"]),
     "all_NeRF.mg_unit_converter": ("geometry", ["world_angle_2_local_vec", "LLA_get_vec"]),
+    "mg_run_NeRF": ("net_tool", ["Net_tool"]),
 }
 
 
@@ -31,10 +35,29 @@ def _ours(modname):
     return importlib.import_module("season_nerf_b200." + modname)
 
 
-def install(patch_existing=True):
-    """Returns the list of module names that now resolve to season_nerf_b200."""
+def install(patch_existing=True, net_tool="ours"):
+    """Returns the list of module names that now resolve to season_nerf_b200.
+    net_tool="ours" (default): `T_NeRF_Full_2.Net_Tool_2` resolves to season_nerf_b200.net_tool, whose T_NeRF_Net_Tool runs
+    every section's step - optimiser updates included - from one captured CUDA graph.
+    net_tool="reference": the reference's own Net_Tool_2.py is left to load; its imports (`T_NeRF`, `All_in_One_Eval`,
+    `mg_run_NeRF.Net_tool`, `AdaptiveLossFunction`) resolve here, so the UNMODIFIED reference class drives this package:
+    its reset_eval builds the eval tool / optimisers, our Net_tool.train_step adopts them (graph for forward + backward)."""
+    if net_tool not in ("ours", "reference"):
+        raise ValueError("net_tool must be 'ours' or 'reference'")
     done = []
-    for name, (src, symbols) in _HOT.items():
+    try:
+        importlib.import_module("robust_loss_pytorch")
+    except Exception:
+        m = types.ModuleType("robust_loss_pytorch")
+        m.__doc__ = "season_nerf_b200.adaptive_loss standing in for the absent robust_loss_pytorch package"
+        m.AdaptiveLossFunction = _ours("adaptive_loss").AdaptiveLossFunction
+        m.__dict__["__season_nerf_b200__"] = True
+        sys.modules["robust_loss_pytorch"] = m
+        done.append("robust_loss_pytorch")
+    hot = dict(_HOT)
+    if net_tool == "ours":
+        hot.update(_NET_TOOL)
+    for name, (src, symbols) in hot.items():
         m = types.ModuleType(name)
         m.__doc__ = "season_nerf_b200 drop-in for the reference module " + name
         o = _ours(src)

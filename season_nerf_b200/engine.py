@@ -235,10 +235,12 @@ class All_in_One_Eval():
         return {"PE": PE, "PV_Exact": PV, "Solar_Vis": Vis, "Sky_Col": Sky}
 
     def _trust(self, current_step):
-        """trust = step / n_steps (Eval_Tools_2.py:218); a device scalar `trust_tensor` (set by the CUDA-graph training
-        step, refreshed before each replay) takes precedence over the Python number"""
+        """trust = step / n_steps (Eval_Tools_2.py:218); inside a CUDA-graph capture the device scalar
+        `trust_tensor` (set by the graphed training step, refreshed before each replay) stands in for the Python number"""
         tt = getattr(self, "trust_tensor", None)
-        return tt if tt is not None else current_step / self.n_steps
+        if tt is not None and t.cuda.is_current_stream_capturing():
+            return tt
+        return current_step / self.n_steps
 
     def _pv_autograd(self, Rho, deltas):
         N, S = Rho.shape[0], Rho.shape[1]

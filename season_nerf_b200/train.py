@@ -68,7 +68,7 @@ class TrainStep:
 
     def __init__(self, args, device, H, WC, network=None, training_DSM=None, use_prior=False, total_steps=None,
                  world_size=1, precision="bf16", use_graph=False, graph_warmup=2, micro_batch=None, solar_rng="device",
-                 sync_bn=False):
+                 sync_bn=False, trust_steps=None, ada_init=None, base_solar_vecs=None):
         """use_graph: after `graph_warmup` eager steps at a given batch size, the whole step (sampling, network forward,
         losses, backward and - single GPU - both Adam updates) is captured once into a CUDA graph and replayed; inputs live
         in static device buffers refreshed before each replay.  The arithmetic and kernel sequence are those of the eager
@@ -80,7 +80,10 @@ class TrainStep:
         sync_bn (world_size > 1): BatchNorm batch statistics - forward sums and the two backward sums of every layer - and
         the batch minimum of the Albedo_Color term are all-reduced over the ranks, so that N ranks with B/N rays each take
         the step the reference takes on one device with B rays (SURVEY 8e caveats 1-2); without it each rank normalises
-        with its own shard (DistributedDataParallel semantics).  Ranks must hold equal numbers of rays."""
+        with its own shard (DistributedDataParallel semantics).  Ranks must hold equal numbers of rays.
+        trust_steps: n_steps of the section's All_in_One_Eval (the prior's trust factor is step / n_steps,
+        Net_Tool_2.py:88-90 passes the section END); default total_steps.  ada_init = (alpha, scale): start values of the
+        colour loss carried over from the previous section (Net_Tool_2.py:70-78)."""
         if solar_rng not in ("device", "host"):
             raise ValueError("solar_rng must be 'device' or 'host'")
         self.solar_rng = solar_rng
@@ -98,17 +101,18 @@ class TrainStep:
             **({} if training_DSM is None else {"HM": training_DSM}), precision=precision).to(self.device)
         self.network.train()
         total_steps = total_steps or args.max_train_steps
-        mk = lambda d, si, sl: AdaptiveLossFunction(d, t.float32, self.device, alpha_hi=2.99, alpha_init=2.0,
-                                                    scale_init=si, scale_lo=sl)
+        a_init, s_init = ada_init if ada_init is not None else (2.0, .03)
+        mk = lambda d, ai, si, sl: AdaptiveLossFunction(d, t.float32, self.device, alpha_hi=2.99, alpha_init=ai,
+                                                        scale_init=si, scale_lo=sl)
         if args.Use_MSE_loss:
             ada, ada_params = None, []
         elif use_prior:                                                            # Net_Tool_2.py:69,82
-            ada = [mk(3, .03, 0.01), mk(1, 0.5, 0.05)]
+            ada = [mk(3, a_init, s_init, 0.01), mk(1, 2.0, 0.5, 0.05)]
             ada_params = list(ada[0].parameters()) + list(ada[1].parameters())
         else:                                                                      # Net_Tool_2.py:78
-            ada = mk(3, .03, 0.01)
+            ada = mk(3, a_init, s_init, 0.01)
             ada_params = list(ada.parameters())
-        self.eval_tool = All_in_One_Eval(args, self.device, total_steps, use_prior, ada, H, WC)
+        self.eval_tool = All_in_One_Eval(args, self.device, trust_steps or total_steps, use_prior, ada, H, WC, base_solar_vecs)
         self.eval_tool.solar_on_device = solar_rng == "device"
         self.sync_bn = bool(sync_bn) and world_size > 1
         if self.sync_bn:
@@ -129,9 +133,41 @@ class TrainStep:
         self.sched = t.optim.lr_scheduler.OneCycleLR(self.optim, max_lr=args.lr, **oc)
         self.sched2 = t.optim.lr_scheduler.OneCycleLR(self.optim2, max_lr=args.lr * args.lr_alpha_scale, **oc) \
             if self.optim2 is not None else None
+        self.capture_optim = True       # the optimiser updates ride in the captured graph (capturable Adam)
         self._flat = None
         self.last_loss = None
         self._versioned = [v for v in self.network.state_dict(keep_vars=True).values()] + list(ada_params)
+
+    @classmethod
+    def adopt(cls, args, device, network, eval_tool, optim, optim2=None, sched=None, sched2=None, use_graph=True,
+              graph_warmup=2, world_size=1):
+        """A step around objects somebody else built - the way the reference's own `T_NeRF_Net_Tool.reset_eval`
+        (Net_Tool_2.py:63-129) creates `eval_tool`, `optim`, `optim2`, `sched`, `sched2` itself and then calls
+        `train_step`.  Forward + backward are still captured in a CUDA graph; the adopted optimisers are ordinary
+        (non-capturable) torch optimisers, so their updates run eagerly after each replay."""
+        self = cls.__new__(cls)
+        self.solar_rng = "device" if getattr(eval_tool, "solar_on_device", False) else "host"
+        self.args, self.device = args, t.device(device)
+        self.world_size = world_size
+        self.use_graph = bool(use_graph) and self.device.type == "cuda"
+        self.use_prior = bool(eval_tool.use_prior)
+        self.graph_warmup = max(1, graph_warmup)
+        self.micro_batch = None
+        self._graphs, self._eager_calls = {}, {}
+        self.launches_replayed = 0
+        self.network = network
+        self.eval_tool = eval_tool
+        self.sync_bn = False
+        ada = eval_tool.ada_loss
+        ada = [] if ada is None else (list(ada) if isinstance(ada, (list, tuple)) else [ada])
+        self.params = [p for p in network.parameters()]
+        self.ada_params = [p for a in ada for p in a.parameters()]
+        self.optim, self.optim2, self.sched, self.sched2 = optim, optim2, sched, sched2
+        self.capture_optim = False
+        self._flat = None
+        self.last_loss = None
+        self._versioned = [v for v in network.state_dict(keep_vars=True).values()] + list(self.ada_params)
+        return self
 
     # ---- checkpoint / resume (the reference saves only network.state_dict(), mg_run_NeRF.py:225: no resume path) --------
     def state_dict(self):
@@ -251,7 +287,7 @@ class TrainStep:
                 self.eval_tool.trust_tensor = t.zeros((), device=self.device, dtype=t.float32)
             self.eval_tool.trust_tensor.fill_(current_step / self.eval_tool.n_steps)
         # one chunk: the gradient all-reduce (NCCL, capturable) and the optimiser updates ride in the same graph
-        fused_opt = k == 1
+        fused_opt = k == 1 and self.capture_optim
         if k > 1 and self.graph_warmup < 1:
             raise ValueError("micro-batched graph capture needs graph_warmup >= 1 (the eager step creates the .grad tensors)")
         if "g_fb" not in st:
@@ -274,11 +310,16 @@ class TrainStep:
                     self._optim_step()
             st["g_fb"] = g_fb
             st["launches"] = _lib.launch_count() - l0
-            if not fused_opt:
+            # the gradient tensors the graph writes: a caller's `optim.zero_grad()` (set_to_none) drops them from the
+            # parameters between steps; they are re-attached after every replay
+            st["grads"] = [(p_, p_.grad) for p_ in self.params + self.ada_params if p_.grad is not None]
+            if not fused_opt and self.capture_optim:
                 g_opt = t.cuda.CUDAGraph()
                 with t.cuda.graph(g_opt, pool=g_fb.pool()):
                     self._optim_step()
                 st["g_opt"] = g_opt
+        for p_, g_ in st["grads"]:
+            p_.grad = g_
         if k > 1:
             self._zero_grads(to_none=False)
         losses, totals = [], []
@@ -295,8 +336,12 @@ class TrainStep:
         if not fused_opt:
             if self.world_size > 1:
                 self._allreduce_grads()
-            st["g_opt"].replay()
-        self.sched.step()
+            if self.capture_optim:
+                st["g_opt"].replay()
+            else:
+                self._optim_step()
+        if self.sched is not None:
+            self.sched.step()
         if self.sched2 is not None:
             self.sched2.step()
         loss, self.last_loss = (st["loss"], st["total"]) if k == 1 else self._merge(losses, totals)
@@ -355,7 +400,8 @@ class TrainStep:
         if self.world_size > 1:
             self._allreduce_grads()
         self._optim_step()
-        self.sched.step()
+        if self.sched is not None:
+            self.sched.step()
         if self.sched2 is not None:
             self.sched2.step()
         self.last_loss = total
