@@ -54,6 +54,30 @@ def get_output_loc_lin_first(n_steps, n_outputs, min_gap):
     return ans
 
 
+def section_schedule(n_steps, n_saves):
+    """Net_Tool_2.py:15-54: the four learning-mode sections (20 % DSM-guided, then - two empty sections later - mode 4 for the
+    rest) -> section_starts, section_Ends, Section_Steps, sub_section_outputs (the save points of each section)."""
+    ps = [0.2, 0.0, 0.0]
+    ps.append(1 - np.sum(ps))
+    p1 = int(ps[0] * n_steps)
+    p2 = int(ps[1] * n_steps)
+    p3 = int(ps[2] * n_steps)
+    p4 = n_steps - p3 - p2 - p1
+    pi = [p1, p2, p3, p4]
+    section_starts = np.array([0, p1, p1 + p2, p1 + p2 + p3])
+    section_Ends = np.array([p1, p1 + p2, p1 + p2 + p3, n_steps])
+    Section_Steps = []
+    for i in range(section_starts.shape[0] - 1):
+        Section_Steps.append(int(section_starts[i + 1] - section_starts[i]))
+    Section_Steps.append(int(n_steps - section_starts[-1]))
+    sub_section_outputs = []
+    for i in range(section_starts.shape[0]):
+        output_points = get_output_loc_lin_first(pi[i], int(n_saves * ps[i]), min_gap=1000)
+        sub_section_outputs.append(section_starts[i] + output_points)
+    sub_section_outputs[-1][-1] = n_steps
+    return section_starts, section_Ends, Section_Steps, sub_section_outputs
+
+
 class ColorTable:
     """The attributes of NN_loaders.mg_Color_Loader.pt_loader (:40-105) that the training loop reads, over an in-memory
     [n,22] ray table: `all_data`, `img_ids`, `full_img_size`, `img_names`, `solar_vecs`, `get_id`, `[j]`, `len`."""
@@ -329,26 +353,8 @@ class T_NeRF_Net_Tool(Net_tool):
 
     def __init__(self, args, training_DSM, GT_DSM, device, H, WC, network=None, **kw):
         super(T_NeRF_Net_Tool, self).__init__(args, device, training_DSM, GT_DSM, init_network=False, has_weight_term=True, **kw)
-        n_steps = args.max_train_steps
-        ps = [0.2, 0.0, 0.0]
-        ps.append(1 - np.sum(ps))
-        p1 = int(ps[0] * n_steps)
-        p2 = int(ps[1] * n_steps)
-        p3 = int(ps[2] * n_steps)
-        p4 = n_steps - p3 - p2 - p1
-        pi = [p1, p2, p3, p4]
-        self.section_starts = np.array([0, p1, p1 + p2, p1 + p2 + p3])
-        self.section_Ends = np.array([p1, p1 + p2, p1 + p2 + p3, n_steps])
-        self.Section_Steps = []
-        for i in range(self.section_starts.shape[0] - 1):
-            self.Section_Steps.append(int(self.section_starts[i + 1] - self.section_starts[i]))
-        self.Section_Steps.append(int(n_steps - self.section_starts[-1]))
-        self.sub_section_outputs = []
-        for i in range(self.section_starts.shape[0]):
-            output_points = get_output_loc_lin_first(pi[i], int(args.n_saves * ps[i]), min_gap=1000)
-            self.sub_section_outputs.append(self.section_starts[i] + output_points)
-        if len(self.sub_section_outputs[-1]):
-            self.sub_section_outputs[-1][-1] = n_steps
+        self.section_starts, self.section_Ends, self.Section_Steps, self.sub_section_outputs = section_schedule(
+            args.max_train_steps, args.n_saves)
         self.learning_mode = -1
         self.network = network if network is not None else T_NeRF(
             args.fc_units, n_classes=args.number_low_frequency_cases, HM=training_DSM, precision=self.precision).to(self.device)
