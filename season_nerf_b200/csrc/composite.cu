@@ -3,6 +3,7 @@
 // so that every load/store of a warp covers one contiguous span of the ray's record; the
 // exclusive transmittance prefix is a warp-shuffle scan carried across 32-sample chunks.
 //   reference: Eval_Tools_2.py:13-16 (get_PV), :187-215 (eval), mg_Img_Eval.py:68-70, :123-228.
+#include <cstdlib>
 #include "common.cuh"
 #include "api.h"
 
@@ -452,6 +453,132 @@ year_sweep_kernel(const TI* __restrict__ rho, const TI* __restrict__ deltas, con
   }
 }
 
+
+// ---- year sweep, float32 components: one lane per TIME STEP ------------------------------------------------------------
+// The kernel above gives each lane 3 samples of the ray and pays a cross-lane float64 reduction (3 x 5 double shuffles) per
+// (ray, time step); ncu (profiles/r02_ncu_year_sweep_v1.txt): 97 ms for 365 x 1024^2, issue slots 76 % busy, XU 57 % -
+// instruction-issue bound.  Here a warp still owns one ray, but its lanes own 32 different time steps: the ray's
+// 96 x (PS, base[3], adj[4][3]) land in shared memory once (6 KB per warp), every lane walks the samples in order and
+// accumulates its own time steps, so there is NO cross-lane reduction, the ray data arrive as 4 broadcast LDS.128 per sample
+// for kTJ time steps per lane, and the three sigmoids of a sample share one reciprocal:
+//     1/(1+a), 1/(1+b), 1/(1+c) = r*(1+b)(1+c), r*(1+a)(1+c), r*(1+a)(1+b),  r = 1/((1+a)(1+b)(1+c))
+// (4 MUFU per 3 sigmoids instead of 6; the logit is clamped at -28 so that the product stays finite: sigmoid(-28) = 7e-13).
+// Base colours and class vectors are pre-scaled by -log2(e): the class mix lands directly in the exponent of ex2.approx.
+// Per-lane sums run in float32 over 16 samples and are flushed into float64 accumulators (|error| of a [0,1] colour < 5e-7).
+// kSweepTJ = time steps per lane and pass (32 * kSweepTJ per pass: 6 -> two passes for a year)
+__device__ __forceinline__ float ex2_approx(float x) {      // one MUFU.EX2 (2 ulp), no range fix-up: |x| <= 28*log2(e) here
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int kSweepTJ>
+__global__ void __launch_bounds__(128)
+year_sweep_lanes_kernel(const float* __restrict__ rho, const float* __restrict__ deltas, const float* __restrict__ base,
+                        const float* __restrict__ adj, const double* __restrict__ cls, const double* __restrict__ shade,
+                        const float* __restrict__ ps_weight, int N, int S, int C, int T, int T_pad, double* __restrict__ out) {
+  extern __shared__ float4 sweep_sm[];
+  float4* wsm = sweep_sm;                                        // [T_pad] class vectors * -log2(e), zero beyond T and C
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  float4* ray = sweep_sm + T_pad + (size_t)warp * S * 4;         // [S][4] float4: (PS, b0', b1', b2'), adj[0..11]
+  float* rayf = reinterpret_cast<float*>(ray);
+  const float kNegLog2e = -1.4426950408889634f;
+  for (int i = threadIdx.x; i < T_pad; i += blockDim.x) {
+    float w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = (i < T && k < C) ? kNegLog2e * (float)cls[(long long)i * C + k] : 0.f;
+    wsm[i] = make_float4(w[0], w[1], w[2], w[3]);
+  }
+  __syncthreads();
+  const int chunks = (S + 31) >> 5;
+  for (int n = blockIdx.x * wpb + warp; n < N; n += gridDim.x * wpb) {
+    // ---- stage the ray: float64 transmittance scan (as above), then the 16 floats of every sample ----
+    double carry = 0.0;
+    for (int c = 0; c < chunks; ++c) {
+      const int s_ = c * 32 + lane;
+      const bool ok = s_ < S;
+      const long long o = (long long)n * S + s_;
+      double psd = ps_chunk_d(ok ? (double)rho[o] * (double)deltas[o] : 0.0, lane, carry);
+      if (ps_weight && ok) psd *= (double)ps_weight[o];
+      if (ok) {
+        rayf[s_ * 16 + 0] = (float)psd;
+        rayf[s_ * 16 + 1] = kNegLog2e * base[3 * o + 0];
+        rayf[s_ * 16 + 2] = kNegLog2e * base[3 * o + 1];
+        rayf[s_ * 16 + 3] = kNegLog2e * base[3 * o + 2];
+      }
+    }
+    {
+      // adj [S][C][3] is contiguous per ray: coalesced reads, scattered into the 12 floats after (PS, base) of each sample
+      const float* a = adj + (long long)n * S * C * 3;
+      const int per = C * 3;
+      for (int i = lane; i < S * per; i += 32) {
+        const int s_ = i / per, r = i - s_ * per;
+        rayf[s_ * 16 + 4 + r] = a[i];
+      }
+      if (C < 4)
+        for (int i = lane; i < S * (12 - per); i += 32) {
+          const int s_ = i / (12 - per), r = i - s_ * (12 - per);
+          rayf[s_ * 16 + 4 + per + r] = 0.f;
+        }
+    }
+    double sh[3] = {1.0, 1.0, 1.0};
+    if (shade) sh[0] = shade[3 * (long long)n], sh[1] = shade[3 * (long long)n + 1], sh[2] = shade[3 * (long long)n + 2];
+    __syncwarp();
+    for (int t0 = 0; t0 < T; t0 += 32 * kSweepTJ) {
+      float4 w[kSweepTJ];
+      float acc[kSweepTJ][3];
+      double accd[kSweepTJ][3];
+#pragma unroll
+      for (int j = 0; j < kSweepTJ; ++j) {
+        w[j] = wsm[t0 + j * 32 + lane];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) acc[j][d] = 0.f, accd[j][d] = 0.0;
+      }
+      for (int s_ = 0; s_ < S; ++s_) {
+        const float4 p = ray[s_ * 4], a0 = ray[s_ * 4 + 1], a1 = ray[s_ * 4 + 2], a2 = ray[s_ * 4 + 3];
+#pragma unroll
+        for (int j = 0; j < kSweepTJ; ++j) {
+          // x_d = -log2(e) * (base_d + sum_k cls_k * adj[k][d]);  adj floats: k0:(a0.x a0.y a0.z) k1:(a0.w a1.x a1.y)
+          // k2:(a1.z a1.w a2.x) k3:(a2.y a2.z a2.w)
+          float x0 = fmaf(w[j].x, a0.x, fmaf(w[j].y, a0.w, fmaf(w[j].z, a1.z, fmaf(w[j].w, a2.y, p.y))));
+          float x1 = fmaf(w[j].x, a0.y, fmaf(w[j].y, a1.x, fmaf(w[j].z, a1.w, fmaf(w[j].w, a2.z, p.z))));
+          float x2 = fmaf(w[j].x, a0.z, fmaf(w[j].y, a1.y, fmaf(w[j].z, a2.x, fmaf(w[j].w, a2.w, p.w))));
+          const float kClamp = 28.f * 1.4426950408889634f;          // -log2(e) * (-28)
+          x0 = fminf(x0, kClamp), x1 = fminf(x1, kClamp), x2 = fminf(x2, kClamp);
+          const float A = 1.f + ex2_approx(x0), B = 1.f + ex2_approx(x1), Cc = 1.f + ex2_approx(x2);
+          const float AB = A * B;
+          const float r = rcp_approx(AB * Cc);
+          acc[j][0] = fmaf(p.x, r * (B * Cc), acc[j][0]);
+          acc[j][1] = fmaf(p.x, r * (A * Cc), acc[j][1]);
+          acc[j][2] = fmaf(p.x, r * AB, acc[j][2]);
+        }
+        if ((s_ & 15) == 15 || s_ == S - 1) {
+#pragma unroll
+          for (int j = 0; j < kSweepTJ; ++j)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) accd[j][d] += (double)acc[j][d], acc[j][d] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kSweepTJ; ++j) {
+        const int t = t0 + j * 32 + lane;
+        if (t < T) {
+          double* o = out + ((long long)t * N + n) * 3;
+          o[0] = accd[j][0] * sh[0], o[1] = accd[j][1] * sh[1], o[2] = accd[j][2] * sh[2];
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace snb
 
 using namespace snb;
@@ -589,6 +716,39 @@ extern "C" int snb_year_sweep(const void* rho, const void* deltas, const void* b
   SNB_CHECK_ARG(in_dtype == SNB_F32 || in_dtype == SNB_F64);
   if (C < 1 || C > 4 || S > 128 || (long long)T * C * 8 > 40 * 1024) return SNB_ERR_UNSUPPORTED;
   if (N == 0 || T == 0) return SNB_OK;
+  if (in_dtype == SNB_F32) {
+    // float32 components (the resident network outputs): lane-per-time-step kernel
+    static int tj = 0;
+    if (tj == 0) {
+      const char* e = getenv("SNB_SWEEP_TJ");           // A/B switch for measurements: 4, 6 (default) or 8 time steps per lane
+      tj = e ? atoi(e) : 6;
+      if (tj != 4 && tj != 8) tj = 6;
+    }
+    const int per_pass = 32 * tj;
+    const int T_pad = (T + per_pass - 1) / per_pass * per_pass;
+    const size_t sm = ((size_t)T_pad + (size_t)4 * S * 4) * sizeof(float4);          // class vectors + 4 warps x [S][4] float4
+    if (sm > 96 * 1024) return SNB_ERR_UNSUPPORTED;
+    const int grid = grid_for(N, 4, 16);
+#define SNB_SWEEP_LANES(TJ)                                                                                                  \
+  do {                                                                                                                       \
+    static bool attr_set = false;                                                                                            \
+    if (!attr_set) {                                                                                                         \
+      cudaError_t e = cudaFuncSetAttribute(year_sweep_lanes_kernel<TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); \
+      if (e != cudaSuccess) return (int)e;                                                                                   \
+      attr_set = true;                                                                                                       \
+    }                                                                                                                        \
+    year_sweep_lanes_kernel<TJ><<<grid, 128, sm, (cudaStream_t)stream>>>(                                                    \
+        (const float*)rho, (const float*)deltas, (const float*)base, (const float*)adj, cls, shade, (const float*)ps_weight, N, S, \
+        C, T, T_pad, out);                                                                                                   \
+  } while (0)
+    if (tj == 4) SNB_SWEEP_LANES(4);
+    else if (tj == 8) SNB_SWEEP_LANES(8);
+    else SNB_SWEEP_LANES(6);
+#undef SNB_SWEEP_LANES
+    count_launch();
+    SNB_LAUNCH_CHECK();
+    return SNB_OK;
+  }
   const int grid = grid_for(N, 4, 16);
   const int chunks = (S + 31) / 32;
   if (in_dtype == SNB_F64) launch_sweep<double>(chunks, grid, (cudaStream_t)stream, rho, deltas, base, adj, cls, shade, ps_weight, N, S, C, T, out);

@@ -444,3 +444,27 @@ def test_composite_full_size_properties_and_empty_inputs():
     assert sw.shape == (5, 0, 3)
     sw0 = ops.year_sweep(z(3, Sx), z(3, Sx), z(3, Sx, 3), z(3, Sx, 4, 3), t.zeros(0, 4, dtype=t.float64, device="cuda"))
     assert sw0.shape == (0, 3, 3)
+
+
+@pytest.mark.parametrize("N,S,C,T", [(1000, 96, 4, 365), (37, 40, 3, 7), (5, 128, 4, 193), (3, 7, 1, 1)])
+def test_year_sweep_float32_lanes_kernel_vs_float64_kernel(N, S, C, T):
+    """the float32 recombination (lane per time step, shared reciprocal, ex2.approx; composite.cu year_sweep_lanes_kernel)
+    against the float64 kernel - the reference's numpy arithmetic, mg_Img_Eval.py:192-228 - on the same float32 components:
+    <= 1e-6 on a [0,1] colour, also with the shade factor and the per-sample PS weight of the classic-shadow alignment"""
+    from season_nerf_b200 import ops
+    g = t.Generator(device="cuda").manual_seed(N + S)
+    rho = t.rand(N, S, device="cuda", generator=g) * 6
+    dl = t.full((N, S), 2.0 / S, device="cuda")
+    dl[::5, S // 2:] = 0                                   # samples outside the cube (zeroed step length)
+    base = t.randn(N, S, 3, device="cuda", generator=g) * 3
+    base[0, 0] = t.tensor([-60., 50., -100.])              # saturated logits: the clamp of the shared-reciprocal sigmoid
+    adj = t.randn(N, S, C, 3, device="cuda", generator=g) * 2
+    cls = t.softmax(t.randn(T, C, device="cuda", generator=g, dtype=t.float64) * 2, 1)
+    shade = t.rand(N, 3, device="cuda", generator=g, dtype=t.float64)
+    w = t.rand(N, S, device="cuda", generator=g)
+    for kw in ({}, {"shade": shade}, {"ps_weight": w}):
+        kw64 = {k: (v.double() if k == "ps_weight" else v) for k, v in kw.items()}
+        got = ops.year_sweep(rho, dl, base, adj, cls, **kw)
+        ref = ops.year_sweep(rho.double(), dl.double(), base.double(), adj.double(), cls, **kw64)
+        assert got.shape == (T, N, 3) and got.dtype == t.float64
+        assert float((got - ref).abs().max()) < 1e-6, (kw.keys(), float((got - ref).abs().max()))

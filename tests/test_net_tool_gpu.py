@@ -117,7 +117,9 @@ def _check(tool, rec, logs, vt, g, precision, obs_key):
         assert o.dtype == np.float64 and o.shape == ref.shape
         assert np.array_equal(np.isnan(o), np.isnan(ref))
         m = ~np.isnan(ref)
-        assert np.abs(o[m] - ref[m]).max() < 1e-6
+        # the fixture stores float32; the float32 running sum of the 96 step lengths (t.cumsum) associates differently on
+        # the device: a few float32 ulps of a distance of ~1
+        assert np.abs(o[m] - ref[m]).max() < 5e-6
     modes, ada_state = [], []
     for i in range(case.N_STEPS_RUN):
         tool.step()
@@ -154,14 +156,21 @@ def _check(tool, rec, logs, vt, g, precision, obs_key):
     P0 = so.init_params(seed=0, perturb_bn=True)
     dn_ref = dict(zip(g["w_names"].tolist(), g["w_delta_norms"].tolist()))
     dn_err = 0.0
+    # A bias in front of a train-mode BatchNorm (fc2 .. fc9) has an analytically ZERO gradient: the normalisation subtracts
+    # whatever the bias adds.  The reference's autograd leaves rounding noise (~1e-9) there, which Adam normalises to full
+    # +-lr steps - a random walk without any effect on the network function.  This package returns the exact zero, so these
+    # eight vectors do not move; they are checked for that and left out of the comparison.
+    bn_bias = {"G_NeRF_net.fc%d.linear.bias" % i for i in range(2, 10)}
+    for k in bn_bias:
+        assert float((sd[k].cpu() - P0[k]).abs().max()) == 0.0, k
     for k, ref in dn_ref.items():
         ours = float((sd[k].cpu() - P0[k]).norm())
-        if ref > 1e-7:
+        if ref > 1e-7 and k not in bn_bias:
             dn_err = max(dn_err, abs(ours - ref) / ref)
     obs["weight_delta_norm_max_rel"] = dn_err
     el = 0.0
     for k in g:
-        if k.startswith("w_") and k not in ("w_names", "w_delta_norms"):
+        if k.startswith("w_") and k not in ("w_names", "w_delta_norms") and k[2:] not in bn_bias:
             name = k[2:]
             d_ref = g[k].astype(np.float64) - P0[name].numpy().astype(np.float64)
             d_our = sd[name].cpu().numpy().astype(np.float64) - P0[name].numpy().astype(np.float64)
@@ -177,8 +186,9 @@ def _check(tool, rec, logs, vt, g, precision, obs_key):
         pass
     # Adam normalises every element's step to ~lr: an element whose gradient is noise-level takes a full step in a
     # rounding-dependent direction, so the element-wise bar is far looser than the gradient bars of the other tests
-    assert dn_err < (2e-2 if fp32 else 0.25), obs
-    assert el < (5e-2 if fp32 else 0.6), obs
+    # observed on B200: fp32 1.2e-3 (fc2.norm.weight), bf16 0.15
+    assert dn_err < (1e-2 if fp32 else 0.2), obs
+    assert el < (5e-3 if fp32 else 0.3), obs
 
 
 @pytest.mark.gpu
