@@ -190,6 +190,44 @@ int snb_sine_bwd_apply(const void* dY, int ldd, const void* Z, int ldz, const fl
 int snb_convert(const void* src, int src_dtype, int lds, void* dst, int dst_dtype, int ldd, long long M, int N,
                 void* stream);
 
+/* ---- output image of the render CLI from the RAW heads of a block of rays: T_NeRF_net_v2.py:139-151 activations +
+ * mg_Img_Eval.py:123-160 float64 sums, main_run_Season_NeRF.py:90-92.  pos4 [M,4], vis_raw [M], adj [M,C,3] contiguous
+ * float32, deltas [M] (zero outside the cube), cls [C] float64 (the image's class vector), exact_vis [M] or NULL
+ * -> season_img [N,3], raw_shadow [N] (, raw_shadow_exact [N]) float64. */
+int snb_render_composite_raw(const float* pos4, const float* vis_raw, const float* adj, const float* deltas,
+                             const double* cls, const float* exact_vis, int N, int S, int C, double* season_img,
+                             double* raw_shadow, double* raw_shadow_exact, void* stream);
+
+/* year sweep (snb_year_sweep) fed by the RAW pos4 [M,4] = (sigma, base colour logits) of the network instead of activated
+ * rho / base arrays: mg_Img_Eval.py:192-228 without materialising the component dict. */
+int snb_year_sweep_raw(const float* pos4, const float* deltas, const float* adj, const double* cls, const double* shade, int N,
+                       int S, int C, int T, double* out, void* stream);
+
+/* ---- head activations fused with the compositing scan: T_NeRF_net_v2.py:87-98 + Eval_Tools_2.py:187-215 --------------
+ * Reads the RAW network heads once - pos4 [M,4] = (sigma, colour logits), vis_raw [M], adj [M,C,3] (row pitches ld_* in
+ * floats: 4 / 1 / 3C when contiguous), sky_raw [N,3], cls_logits [N,C], deltas [N,S] - applies softplus / softmax + class
+ * mix / sigmoid in registers and composites: albedo [N,3], rendered [N,3] (classic = Solar_Type_2, else the Solar_Vis3
+ * gate), sky_act [N,3] = sigmoid(sky_raw), vis_sum [N] = sum_s vis*PS, optional PV / PE / PS [N,S].  C <= 4, S <= 128. */
+int snb_heads_composite_fwd(const float* pos4, int ld_pos, const float* vis_raw, int ld_vis, const float* adj, int ld_adj,
+                            const float* sky_raw, const float* cls_logits, const float* deltas, int N, int S, int C,
+                            int classic, float* albedo, float* rendered, float* sky_act, float* vis_sum, float* PV, float* PE,
+                            float* PS, void* stream);
+/* gradients of the raw heads given d_albedo, d_rendered, d_sky_act (any may be NULL): d_pos4 [M,4], d_adj [M,C,3],
+ * d_sky_raw [N,3], d_cls_logits [N,C] (softmax Jacobian applied), d_vis_raw [M] only if classic (vis is detached in the
+ * non-classic colour formula, Eval_Tools_2.py:214, while its PS weight is not). */
+int snb_heads_composite_bwd(const float* pos4, int ld_pos, const float* vis_raw, int ld_vis, const float* adj, int ld_adj,
+                            const float* sky_raw, const float* cls_logits, const float* deltas, int N, int S, int C,
+                            int classic, const float* d_albedo, const float* d_rendered, const float* d_sky_act,
+                            float* d_pos4, float* d_vis_raw, float* d_adj, float* d_sky_raw, float* d_cls_logits,
+                            void* stream);
+/* solar pass of get_loss (Eval_Tools_2.py:297-337, :353-368) from the raw heads of forward_Solar: per ray
+ * err = sum_s (sigmoid(vis_raw) - PV)^2 and absorb = 1 - sum_s PE*PV*sigmoid(vis_raw), rho = softplus(rho_raw); PV and PE
+ * are detached there, so the backward only has d_vis_raw [M] = (g_err*2(vis-PV) - g_abs*PE*PV) * vis(1-vis). */
+int snb_solar_loss_fwd(const float* rho_raw, int ld_rho, const float* vis_raw, int ld_vis, const float* deltas, int N, int S,
+                       float* err, float* absorb, void* stream);
+int snb_solar_loss_bwd(const float* rho_raw, int ld_rho, const float* vis_raw, int ld_vis, const float* deltas, int N, int S,
+                       const float* g_err, const float* g_abs, float* d_vis_raw, void* stream);
+
 /* ---- fused eval-mode network (render): T_NeRF_net_v2.py:75-105,131-151,169-170 + G_NeRF.py:74-133 --------------
  * One persistent tcgen05 kernel runs encoding -> trunk -> sigma/colour heads -> solar branch -> adjust branch with the
  * activations kept in shared memory / TMEM: two CTAs of a cluster render a tile of 256 sample points with

@@ -831,3 +831,55 @@ def synthetic_batch(n_rays, seed=1, n_images=41):
     img = t.randint(0, n_images, (n_rays,), generator=g)
     return {"Top": top, "Bot": bot, "Sun_Angle": sun_img[img], "Time_Encoded": time_img[img],
             "GT_Color": t.rand(n_rays, 3, generator=g)}
+
+
+# --------------------------------------------------------------------------
+# sigma-only volume consumers (T_NeRF_Eval_Utils/mg_Shadow_Eval.py, Eval_funcs.py)
+def eval_shadow_data(p, shadow_angles, ground_points, Z_points, WC, W2L_H):
+    """eval_shadow_data, mg_Shadow_Eval.py:72-104 -> Vis_Exact [A,G,Z,1], Vis_Est [A,G,Z,1], Sky_Col [A,3] (float64)."""
+    A, G = shadow_angles.shape[0], ground_points.shape[0]
+    vec0 = np.array([world_angle_2_local_vec(shadow_angles[i, 0], shadow_angles[i, 1], WC, W2L_H) for i in range(A)])
+    vec = vec0 / vec0[:, -1::]
+    gp3 = np.expand_dims(np.concatenate([ground_points, np.zeros([G, 1])], 1), 0)
+    tops = t.tensor(gp3 + np.expand_dims(vec, 1)).float()
+    bots = t.tensor(gp3 - np.expand_dims(vec, 1)).float()
+    ve, vs, sk = np.zeros([A, G, Z_points, 1]), np.zeros([A, G, Z_points, 1]), np.zeros([A, 3])
+    with t.no_grad():
+        for i in range(A):
+            Xs, deltas = sample_pt_coarse(tops[i], bots[i], Z_points, eval_mode=True)
+            deltas[invalid_pts(Xs)] = 0.
+            sv = t.tensor(vec0[i]).float().reshape(1, 3).expand(G * Z_points, 3)
+            rho, vis, sky = forward_solar(p, Xs.reshape(-1, 3), sv, None)
+            rho = rho.reshape(G, Z_points, 1)
+            ve[i] = get_PV(rho, deltas).numpy()
+            vs[i] = vis.reshape(G, Z_points, 1).numpy()
+            sk[i] = sky.reshape(G, Z_points, -1)[0, 0].numpy()
+    return ve, vs, sk
+
+
+def eval_hm_head(p, GT, h_range, n_samples):
+    """eval_HM up to the scores before alignment, Eval_funcs.py:298-395 (the confidence loop :315-330 verbatim in structure)
+    -> GT in metres, shifted estimated height map, conf_range [H,W,3], scores dict."""
+    rho, pe, pv, ps, _ = gen_results(p, GT.shape, n_samples)
+    est = np.sum(ps * np.linspace(1, -1, n_samples).reshape([1, 1, -1]), 2) / np.sum(ps, 2)
+    pdf = ps / np.sum(ps, 2, keepdims=True)
+    conf = np.zeros([pdf.shape[0], pdf.shape[1], 3])
+    for i in range(conf.shape[0]):
+        for j in range(conf.shape[1]):
+            z0 = int(np.argmax(pdf[i, j]))
+            z1 = z0 + 1
+            value = pdf[i, j, z0]
+            while value < .67 and (z0 != 0 or z1 != pdf.shape[2]):
+                z0, z1 = max(0, z0 - 1), min(z1 + 1, pdf.shape[2])
+                value = np.sum(pdf[i, j, z0:z1])
+            conf[i, j, 0], conf[i, j, 1] = z0, z1
+    conf[:, :, 2] = (conf[:, :, 1] - conf[:, :, 0]) / pdf.shape[2] * (h_range[1] - h_range[0])
+    h0, h1 = h_range
+    est = (est + 1) / 2 * (h1 - h0) + h0
+    GTm = (GT + 1) / 2 * (h1 - h0) + h0
+    est = est + np.nanmean((GTm - est).ravel())
+    diff = est - GTm
+    diff = np.ravel(diff[diff == diff])
+    scores = {"MAE": np.mean(np.abs(diff)), "RMSE": np.sqrt(np.mean(diff ** 2)),
+              "Acc_1_m": np.sum(np.abs(diff) <= 1) / diff.shape[0], "Median": np.median(np.abs(diff))}
+    return GTm, est, conf, scores

@@ -23,6 +23,7 @@ from .quick_run import Quick_Run_Net
 from .render import (DeviceImgDict, _internal_render, component_render_by_dir, component_render_by_P,
                      get_imgs_from_Img_Dict, get_imgs_from_Img_Dict_t_step, render_image_sharded, render_shard)
 from .train import TrainStep
-from .volume import gen_results, height_map
+from .shadow_eval import Test_Shadow_Points, eval_shadow_data, shadow_anaylysis
+from .volume import confidence_range, eval_HM, gen_results, height_map
 
 __version__ = "0.1.0"

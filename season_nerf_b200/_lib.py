@@ -27,6 +27,12 @@ SIGNATURES = {
     "snb_solar_tops": [_p, _ll, C.POINTER(C.c_double), _i, _p, _p],
     "snb_composite_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
     "snb_composite_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "snb_heads_composite_fwd": [_p, _i, _p, _i, _p, _i, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p],
+    "snb_heads_composite_bwd": [_p, _i, _p, _i, _p, _i, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "snb_solar_loss_fwd": [_p, _i, _p, _i, _p, _i, _i, _p, _p, _p],
+    "snb_solar_loss_bwd": [_p, _i, _p, _i, _p, _i, _i, _p, _p, _p, _p],
+    "snb_render_composite_raw": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p],
+    "snb_year_sweep_raw": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p],
     "snb_march_transmittance": [_p, _p, _ll, _i, _p, _p],
     "snb_cli_composite": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p],
     "snb_cli_classic_shadow": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p],

@@ -28,6 +28,8 @@ _PATCH = {
                                                  "get_imgs_from_Img_Dict", "get_imgs_from_Img_Dict_t_step"]),
     "all_NeRF.mg_unit_converter": ("geometry", ["world_angle_2_local_vec", "LLA_get_vec"]),
     "mg_run_NeRF": ("net_tool", ["Net_tool"]),
+    "T_NeRF_Eval_Utils.mg_Shadow_Eval": ("shadow_eval", ["eval_shadow_data", "Test_Shadow_Points", "shadow_anaylysis"]),
+    "T_NeRF_Eval_Utils.Eval_funcs": ("volume", ["gen_results"]),
 }
 
 

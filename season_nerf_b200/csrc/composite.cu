@@ -356,6 +356,57 @@ cli_composite_kernel(const T* __restrict__ rho, const T* __restrict__ deltas, co
   }
 }
 
+// The output image of the render CLI (main_run_Season_NeRF.py:90-92 = Season_Adj_Img * Shadow_Adjust) straight from the
+// RAW network heads of a block of rays: pos4 [M,4] = (sigma, base colour logits), vis_raw [M], adj [M,C,3], deltas [M]
+// (already zero outside the cube).  softplus / sigmoid are applied in float32 like the network's own activations
+// (T_NeRF_net_v2.py:139-151), the sums run in float64 like get_imgs_from_Img_Dict (mg_Img_Eval.py:123-160); the base /
+// extreme images of the component API are not formed (3 float64 sigmoids per sample instead of 18), and the eight
+// element-wise torch launches + activated copies of the component path (render.py _internal_render) disappear.
+__global__ void __launch_bounds__(128)
+render_composite_raw_kernel(const float* __restrict__ pos4, const float* __restrict__ vis_raw, const float* __restrict__ adj,
+                            const float* __restrict__ deltas, const double* __restrict__ cls,
+                            const float* __restrict__ exact_vis, int N, int S, int C, double* __restrict__ season_img,
+                            double* __restrict__ raw_shadow, double* __restrict__ raw_shadow_exact) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  double cw[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) cw[c] = c < C ? cls[c] : 0.0;
+  for (int n = blockIdx.x * wpb + (threadIdx.x >> 5); n < N; n += gridDim.x * wpb) {
+    double carry = 0.0, se[3] = {0, 0, 0}, sh = 0, she = 0;
+    for (int s0 = 0; s0 < S; s0 += 32) {
+      const int s = s0 + lane;
+      const bool ok = s < S;
+      const long long o = (long long)n * S + s;
+      float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok) p = __ldg(reinterpret_cast<const float4*>(pos4) + o);
+      const double ps = ps_chunk_d(ok ? (double)softplusf_(p.x) * (double)deltas[o] : 0.0, lane, carry);
+      if (ok) {
+        sh += ps * (double)sigmoidf_(__ldg(vis_raw + o));
+        if (exact_vis) she += ps * (double)exact_vis[o];
+        const float bc[3] = {p.y, p.z, p.w};
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          double mix = 0;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (c < C) mix += cw[c] * (double)__ldg(adj + (o * C + c) * 3 + d);
+          se[d] += ps * sigd((double)bc[d] + mix);
+        }
+      }
+    }
+    sh = warp_sum_d(sh);
+    if (exact_vis) she = warp_sum_d(she);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) se[d] = warp_sum_d(se[d]);
+    if (lane == 0) {
+      raw_shadow[n] = sh;
+      if (exact_vis && raw_shadow_exact) raw_shadow_exact[n] = she;
+      for (int d = 0; d < 3; ++d) season_img[3 * n + d] = se[d];
+    }
+  }
+}
+
 // mg_Img_Eval.py:166-181 (use_classic_shadows): classic[n,:] = sum_s PS * sigmoid(base + class . adjust) * (vis + (1 - vis) * sky)
 // with the per-sample sky colour of the component dict, float64 sums like the reference's numpy.
 template <typename T>
@@ -465,7 +516,7 @@ year_sweep_kernel(const TI* __restrict__ rho, const TI* __restrict__ deltas, con
 // (4 MUFU per 3 sigmoids instead of 6; the logit is clamped at -28 so that the product stays finite: sigmoid(-28) = 7e-13).
 // Base colours and class vectors are pre-scaled by -log2(e): the class mix lands directly in the exponent of ex2.approx.
 // Per-lane sums run in float32 over 16 samples and are flushed into float64 accumulators (|error| of a [0,1] colour < 5e-7).
-// kSweepTJ = time steps per lane and pass (32 * kSweepTJ per pass: 6 -> two passes for a year)
+// kSweepTJ = time steps per lane and pass (32 * kSweepTJ per pass: 4 -> three passes for a year)
 __device__ __forceinline__ float ex2_approx(float x) {      // one MUFU.EX2 (2 ulp), no range fix-up: |x| <= 28*log2(e) here
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -481,7 +532,10 @@ template <int kSweepTJ>
 __global__ void __launch_bounds__(128)
 year_sweep_lanes_kernel(const float* __restrict__ rho, const float* __restrict__ deltas, const float* __restrict__ base,
                         const float* __restrict__ adj, const double* __restrict__ cls, const double* __restrict__ shade,
-                        const float* __restrict__ ps_weight, int N, int S, int C, int T, int T_pad, double* __restrict__ out) {
+                        const float* __restrict__ ps_weight, int raw_pos4, int N, int S, int C, int T, int T_pad,
+                        double* __restrict__ out) {
+  // raw_pos4: `rho` points at the network's raw pos4 [M,4] = (sigma, base colour logits) and `base` is unused: softplus is
+  // applied here (float32, like the network's own activation) and no activated copy of the heads is ever made
   extern __shared__ float4 sweep_sm[];
   float4* wsm = sweep_sm;                                        // [T_pad] class vectors * -log2(e), zero beyond T and C
   const int lane = threadIdx.x & 31;
@@ -505,13 +559,17 @@ year_sweep_lanes_kernel(const float* __restrict__ rho, const float* __restrict__
       const int s_ = c * 32 + lane;
       const bool ok = s_ < S;
       const long long o = (long long)n * S + s_;
-      double psd = ps_chunk_d(ok ? (double)rho[o] * (double)deltas[o] : 0.0, lane, carry);
+      float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok) p4 = raw_pos4 ? __ldg(reinterpret_cast<const float4*>(rho) + o)
+                            : make_float4(rho[o], base[3 * o + 0], base[3 * o + 1], base[3 * o + 2]);
+      const float rho_s = raw_pos4 ? softplusf_(p4.x) : p4.x;
+      double psd = ps_chunk_d(ok ? (double)rho_s * (double)deltas[o] : 0.0, lane, carry);
       if (ps_weight && ok) psd *= (double)ps_weight[o];
       if (ok) {
         rayf[s_ * 16 + 0] = (float)psd;
-        rayf[s_ * 16 + 1] = kNegLog2e * base[3 * o + 0];
-        rayf[s_ * 16 + 2] = kNegLog2e * base[3 * o + 1];
-        rayf[s_ * 16 + 3] = kNegLog2e * base[3 * o + 2];
+        rayf[s_ * 16 + 1] = kNegLog2e * p4.y;
+        rayf[s_ * 16 + 2] = kNegLog2e * p4.z;
+        rayf[s_ * 16 + 3] = kNegLog2e * p4.w;
       }
     }
     {
@@ -678,6 +736,20 @@ extern "C" int snb_cli_composite(const void* rho, const void* deltas, const void
   return SNB_OK;
 }
 
+extern "C" int snb_render_composite_raw(const float* pos4, const float* vis_raw, const float* adj, const float* deltas,
+                                        const double* cls, const float* exact_vis, int N, int S, int C, double* season_img,
+                                        double* raw_shadow, double* raw_shadow_exact, void* stream) {
+  SNB_CHECK_ARG(pos4 && vis_raw && adj && deltas && cls && season_img && raw_shadow && N >= 0 && S > 0);
+  SNB_CHECK_ARG((((uintptr_t)pos4) & 15) == 0);
+  if (C < 1 || C > 4) return SNB_ERR_UNSUPPORTED;
+  if (N == 0) return SNB_OK;
+  render_composite_raw_kernel<<<grid_for(N, 4, 16), 128, 0, (cudaStream_t)stream>>>(pos4, vis_raw, adj, deltas, cls, exact_vis, N, S, C,
+                                                                                   season_img, raw_shadow, raw_shadow_exact);
+  count_launch();
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
 extern "C" int snb_cli_classic_shadow(const void* rho, const void* deltas, const void* base, const void* vis, const void* adj,
                                       const void* sky, const double* cls, int in_dtype, int N, int S, int C, double* out,
                                       void* stream) {
@@ -709,9 +781,26 @@ static void launch_sweep(int chunks, int grid, cudaStream_t st, const void* rho,
   else year_sweep_kernel<TI, 4><<<grid, 128, sm, st>>>(r, d, b, a, cls, shade, w, N, S, C, T, out);
 }
 
+static int year_sweep_impl(const void* rho, const void* deltas, const void* base, const void* adj, const double* cls,
+                           const double* shade, const void* ps_weight, int in_dtype, int raw_pos4, int N, int S, int C, int T,
+                           double* out, void* stream);
+
 extern "C" int snb_year_sweep(const void* rho, const void* deltas, const void* base, const void* adj,
                               const double* cls, const double* shade, const void* ps_weight, int in_dtype, int N, int S,
                               int C, int T, double* out, void* stream) {
+  SNB_CHECK_ARG(base);
+  return year_sweep_impl(rho, deltas, base, adj, cls, shade, ps_weight, in_dtype, 0, N, S, C, T, out, stream);
+}
+
+extern "C" int snb_year_sweep_raw(const float* pos4, const float* deltas, const float* adj, const double* cls,
+                                  const double* shade, int N, int S, int C, int T, double* out, void* stream) {
+  SNB_CHECK_ARG(pos4 && (((uintptr_t)pos4) & 15) == 0);
+  return year_sweep_impl(pos4, deltas, pos4, adj, cls, shade, nullptr, SNB_F32, 1, N, S, C, T, out, stream);
+}
+
+static int year_sweep_impl(const void* rho, const void* deltas, const void* base, const void* adj, const double* cls,
+                           const double* shade, const void* ps_weight, int in_dtype, int raw_pos4, int N, int S, int C, int T,
+                           double* out, void* stream) {
   SNB_CHECK_ARG(rho && deltas && base && adj && cls && out && N >= 0 && S > 0 && T >= 0);
   SNB_CHECK_ARG(in_dtype == SNB_F32 || in_dtype == SNB_F64);
   if (C < 1 || C > 4 || S > 128 || (long long)T * C * 8 > 40 * 1024) return SNB_ERR_UNSUPPORTED;
@@ -720,9 +809,12 @@ extern "C" int snb_year_sweep(const void* rho, const void* deltas, const void* b
     // float32 components (the resident network outputs): lane-per-time-step kernel
     static int tj = 0;
     if (tj == 0) {
-      const char* e = getenv("SNB_SWEEP_TJ");           // A/B switch for measurements: 4, 6 (default) or 8 time steps per lane
-      tj = e ? atoi(e) : 6;
-      if (tj != 4 && tj != 8) tj = 6;
+      // A/B switch for measurements: 4 (default), 6 or 8 time steps per lane.  Measured for 365 x 1024^2 on B200
+      // (profiles/r02_year_sweep_tj.txt): 54.6 / 60.2 / 77.8 ms - occupancy (96 / 128 / 168 registers) beats the amortised
+      // ray loads
+      const char* e = getenv("SNB_SWEEP_TJ");
+      tj = e ? atoi(e) : 4;
+      if (tj != 6 && tj != 8) tj = 4;
     }
     const int per_pass = 32 * tj;
     const int T_pad = (T + per_pass - 1) / per_pass * per_pass;
@@ -738,8 +830,8 @@ extern "C" int snb_year_sweep(const void* rho, const void* deltas, const void* b
       attr_set = true;                                                                                                       \
     }                                                                                                                        \
     year_sweep_lanes_kernel<TJ><<<grid, 128, sm, (cudaStream_t)stream>>>(                                                    \
-        (const float*)rho, (const float*)deltas, (const float*)base, (const float*)adj, cls, shade, (const float*)ps_weight, N, S, \
-        C, T, T_pad, out);                                                                                                   \
+        (const float*)rho, (const float*)deltas, (const float*)base, (const float*)adj, cls, shade, (const float*)ps_weight,     \
+        raw_pos4, N, S, C, T, T_pad, out);                                                                                                   \
   } while (0)
     if (tj == 4) SNB_SWEEP_LANES(4);
     else if (tj == 8) SNB_SWEEP_LANES(8);

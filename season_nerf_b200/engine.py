@@ -7,11 +7,18 @@ the network and compositing run in the sm_100a library; only the O(N) loss arith
 Extra keyword arguments (`jitter=`, `solar=`, `solar_jitter=`) inject the random draws of the reference for parity
 tests; when omitted the same draws are made from the same global RNGs in the same order as the reference.
 """
+import os
+
 import numpy as np
 import torch as t
 
 from . import ops
 from .geometry import world_angle_2_local_vec
+
+# get_loss without the prior: head activations + compositing + the solar-pass sums run in fused kernels on the RAW heads
+# (ops.heads_composite / ops.solar_loss) instead of ~65 element-wise torch launches and their autograd nodes.
+# SNB_FAST_LOSS=0 keeps the general path (eval / eval_Rho_Only dictionaries) for A/B tests.
+FAST_LOSS = os.environ.get("SNB_FAST_LOSS", "1") != "0"
 
 
 def _dev(x, device):
@@ -234,6 +241,33 @@ class All_in_One_Eval():
         PV = get_PV(Rho.detach(), deltas) if not Rho.requires_grad else self._pv_autograd(Rho, deltas)
         return {"PE": PE, "PV_Exact": PV, "Solar_Vis": Vis, "Sky_Col": Sky}
 
+    def _eval_fast(self, data_dict, Network, train_mode, jitter=None, ts=None):
+        """eval() reduced to what get_loss reads without the prior (Rendered_Col, Albedo_Color, the per-ray sky colour), from
+        the raw heads in ONE kernel (Eval_Tools_2.py:165-215)."""
+        S = self.args.n_samples
+        dev = self.device
+        Xs, deltas = sample_pt_coarse(data_dict["Top"], data_dict["Bot"], S, not train_mode, jitter=jitter, device=dev, ts=ts)
+        N = Xs.shape[0]
+        sun, tim = _dev(data_dict["Sun_Angle"], dev), _dev(data_dict["Time_Encoded"], dev)
+        pos, vis, adj, sky, cl = Network.forward_rays(Xs.reshape(-1, 3), sun, tim, S)
+        if sky.shape[0] != N:
+            sky = sky.expand(N, sky.shape[1])
+        if cl.shape[0] != N:
+            cl = cl.expand(N, cl.shape[1])
+        albedo, rendered, sky_act, _ = ops.heads_composite(pos, vis, adj, sky, cl, deltas.reshape(N, S), self.use_classic_solar)
+        return {"Rendered_Col": rendered, "Albedo_Color": albedo, "Sky_Col": sky_act}
+
+    def _solar_fast(self, data_dict, Network, train_mode, jitter=None, ts=None):
+        """eval_Rho_Only + the two solar sums of get_loss (Eval_Tools_2.py:297-337, :353-368) -> err [N], absorb [N]"""
+        S = self.args.n_samples
+        dev = self.device
+        Xs, deltas = sample_pt_coarse(data_dict["Top"], data_dict["Bot"], S, not train_mode, include_end_pt=True,
+                                      jitter=jitter, device=dev, ts=ts)
+        N = Xs.shape[0]
+        sun = _dev(data_dict["Sun_Angle"], dev)
+        rho_raw, vis_raw, _ = Network.forward_rays(Xs.reshape(-1, 3), sun, None, S, mode="solar")
+        return ops.solar_loss(rho_raw.detach(), vis_raw, deltas.reshape(N, S))
+
     def _trust(self, current_step):
         """trust = step / n_steps (Eval_Tools_2.py:218); inside a CUDA-graph capture the device scalar
         `trust_tensor` (set by the graphed training step, refreshed before each replay) stands in for the Python number"""
@@ -307,8 +341,14 @@ class All_in_One_Eval():
             main = t.cuda.current_stream()
             fork = t.cuda.Event()
             fork.record(main)
+        fast = (FAST_LOSS and not self.use_prior and not overlap and hasattr(Network, "forward_rays")
+                and ops.heads_composite_usable(args.n_samples, getattr(Network, "n_classes", 99)))
+        sol = sol_fast = None
         try:
-            out = self.eval(data_dict, Network, current_step, train_mode, jitter=jitter, ts=ts)
+            if fast:
+                out = self._eval_fast(data_dict, Network, train_mode, jitter=jitter, ts=ts)
+            else:
+                out = self.eval(data_dict, Network, current_step, train_mode, jitter=jitter, ts=ts)
             if args.Use_Solar:
                 if solar is None and self.solar_on_device:
                     starts, ends, svec, stime = self.solar_creation_tool.on_device(n_rays, device, include_times=True)
@@ -317,7 +357,9 @@ class All_in_One_Eval():
                 else:
                     starts, ends, svec, stime = solar
                 sdict = {"Top": starts, "Bot": ends, "Sun_Angle": svec, "Time_Encoded": stime}
-                if overlap:
+                if fast:
+                    sol_fast = self._solar_fast(sdict, Network, train_mode, jitter=solar_jitter, ts=solar_ts)
+                elif overlap:
                     side = _nw.side_stream(("solar", main.cuda_stream))
                     side.wait_event(fork)
                     with t.cuda.stream(side):
@@ -332,9 +374,12 @@ class All_in_One_Eval():
             if overlap:
                 Network._bn_order = None
         if args.Use_Solar:
-            err = t.mean(t.sum((sol["Solar_Vis"] - sol["PV_Exact"].detach()) ** 2, 1))
+            if sol_fast is not None:
+                err, absorb = t.mean(sol_fast[0]), t.mean(sol_fast[1])
+            else:
+                err = t.mean(t.sum((sol["Solar_Vis"] - sol["PV_Exact"].detach()) ** 2, 1))
+                absorb = t.mean(1 - t.sum(sol["PE"].detach() * sol["PV_Exact"].detach() * sol["Solar_Vis"], 1))
             Loss["Solar_Correction"] = [err, weight["Solar_Correction"]]
-            absorb = t.mean(1 - t.sum(sol["PE"].detach() * sol["PV_Exact"].detach() * sol["Solar_Vis"], 1))
             Loss["Solar_Correction_2"] = [absorb if args.Solar_Type_2 else absorb.detach(), weight["Solar_Correction"]]
             if args.Solar_Type_2 is False:
                 alb = out["Albedo_Color"]
@@ -345,6 +390,8 @@ class All_in_One_Eval():
                     # all-reduce then equals the single-batch term  sum_c (1 - min_c/.2)^2 / N_total)
                     m = m * owns_global_min(sk_alb)
                 alb_loss = t.sum(m * (1. - sk_alb / .2) ** 2) / alb.shape[0]
+                # Sky_Col is [N,S,3] in the reference (one colour per ray, repeated over its samples); the fast path keeps
+                # the [N,3] rows: sum / numel is the same mean
                 sk = (out["Sky_Col"] - .5) / .5
                 sk_loss = t.sum(t.relu(sk) ** 2) / float(np.prod(sk.shape))
                 if self.use_prior:

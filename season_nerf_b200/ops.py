@@ -192,6 +192,127 @@ def composite(rho, deltas, col, vis, sky, classic=False):
     return _Composite.apply(rho, deltas, col, vis, sky, bool(classic))
 
 
+def _rows(x, cols, name):
+    """2-D float32 CUDA matrix whose rows hold `cols` contiguous floats -> (tensor, row pitch in floats); a strided view
+    (the layer-wise path keeps its narrow heads in 16-float-wide rows) is passed through without a copy"""
+    _cuda(x, torch.float32, name)
+    if x.dim() == 1:
+        x = x.unsqueeze(1)
+    if x.dim() != 2 or x.shape[1] != cols or (cols > 1 and x.stride(1) != 1) or (x.data_ptr() % 16 and cols >= 4):
+        x = x.reshape(x.shape[0], -1).contiguous()
+        if x.shape[1] != cols:
+            raise ValueError("%s must have %d columns, got %s" % (name, cols, tuple(x.shape)))
+    ld = x.stride(0) if x.shape[0] > 1 else max(cols, x.stride(0))
+    if ld < cols or (cols >= 4 and ld % 4):
+        x = x.contiguous()
+        ld = cols
+    return x, int(ld)
+
+
+HEADS_MAX_S, HEADS_MAX_C = 128, 4
+
+
+def heads_composite_usable(S, C):
+    return S <= HEADS_MAX_S and 1 <= C <= HEADS_MAX_C
+
+
+def heads_composite_fwd(pos4, vis_raw, adj, sky_raw, cls_logits, deltas, classic=False, want_pv=False):
+    """raw heads -> (albedo [N,3], rendered [N,3], sky_act [N,3], vis_sum [N], PV, PE, PS [N,S] or None)
+    (T_NeRF_net_v2.py:87-98 activations + Eval_Tools_2.py:187-215 compositing in one kernel)."""
+    N, S = deltas.shape[0], deltas.shape[1]
+    C = cls_logits.shape[1]
+    pos4, ldp = _rows(pos4, 4, "pos4")
+    vis_raw, ldv = _rows(vis_raw, 1, "vis_raw")
+    adj, lda = _rows(adj, 3 * C, "adj")
+    sky_raw = _cuda(sky_raw, torch.float32, "sky_raw").contiguous()
+    cls_logits = _cuda(cls_logits, torch.float32, "cls_logits").contiguous()
+    deltas = _cuda(deltas, torch.float32, "deltas").contiguous()
+    dev = deltas.device
+    mk = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+    albedo, rendered, sky_act, vsum = mk(N, 3), mk(N, 3), mk(N, 3), mk(N)
+    PV, PE, PS = (mk(N, S), mk(N, S), mk(N, S)) if want_pv else (None, None, None)
+    if N:
+        check(_lib.load().snb_heads_composite_fwd(_ptr(pos4), ldp, _ptr(vis_raw), ldv, _ptr(adj), lda, _ptr(sky_raw),
+                                                  _ptr(cls_logits), _ptr(deltas), N, S, C, int(classic), _ptr(albedo),
+                                                  _ptr(rendered), _ptr(sky_act), _ptr(vsum), _ptr(PV), _ptr(PE), _ptr(PS), _stream()))
+    return albedo, rendered, sky_act, vsum, PV, PE, PS
+
+
+class _HeadsComposite(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos4, vis_raw, adj, sky_raw, cls_logits, deltas, classic):
+        albedo, rendered, sky_act, vsum, _, _, _ = heads_composite_fwd(pos4, vis_raw, adj, sky_raw, cls_logits, deltas, classic)
+        ctx.save_for_backward(pos4, vis_raw, adj, sky_raw, cls_logits, deltas)
+        ctx.set_materialize_grads(False)
+        ctx.classic = classic
+        ctx.mark_non_differentiable(vsum)
+        return albedo, rendered, sky_act, vsum
+
+    @staticmethod
+    def backward(ctx, d_albedo, d_rendered, d_sky_act, _dvs):
+        pos4, vis_raw, adj, sky_raw, cls_logits, deltas = ctx.saved_tensors
+        N, S = deltas.shape[0], deltas.shape[1]
+        C = cls_logits.shape[1]
+        M = N * S
+        p4, ldp = _rows(pos4, 4, "pos4")
+        vr, ldv = _rows(vis_raw, 1, "vis_raw")
+        ad, lda = _rows(adj, 3 * C, "adj")
+        c = lambda g: None if g is None else g.float().contiguous()
+        d_albedo, d_rendered, d_sky_act = c(d_albedo), c(d_rendered), c(d_sky_act)
+        dev = deltas.device
+        mk = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+        d_pos, d_adj, d_sky, d_cls = mk(M, 4), mk(M, 3 * C), mk(N, 3), mk(N, C)
+        d_vis = mk(M, 1) if ctx.classic else None
+        # contiguous copies are bound to names: a temporary inside the argument list would be freed - and its block handed to
+        # the next temporary - before the kernel runs
+        sky_c, cls_c, dl_c = sky_raw.contiguous(), cls_logits.contiguous(), deltas.contiguous()
+        check(_lib.load().snb_heads_composite_bwd(_ptr(p4), ldp, _ptr(vr), ldv, _ptr(ad), lda, _ptr(sky_c),
+                                                  _ptr(cls_c), _ptr(dl_c), N, S, C, int(ctx.classic),
+                                                  _ptr(d_albedo), _ptr(d_rendered), _ptr(d_sky_act), _ptr(d_pos), _ptr(d_vis),
+                                                  _ptr(d_adj), _ptr(d_sky), _ptr(d_cls), _stream()))
+        return (d_pos.view_as(pos4) if pos4.shape == d_pos.shape else d_pos.reshape(pos4.shape),
+                None if d_vis is None else d_vis.reshape(vis_raw.shape), d_adj.reshape(adj.shape), d_sky, d_cls, None, None)
+
+
+def heads_composite(pos4, vis_raw, adj, sky_raw, cls_logits, deltas, classic=False):
+    """differentiable in pos4, adj, sky_raw, cls_logits (and vis_raw if classic) -> albedo, rendered, sky_act [N,3], vis_sum [N]"""
+    return _HeadsComposite.apply(pos4, vis_raw, adj, sky_raw, cls_logits, deltas, bool(classic))
+
+
+class _SolarLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rho_raw, vis_raw, deltas):
+        N, S = deltas.shape[0], deltas.shape[1]
+        rr, ldr = _rows(rho_raw, 1, "rho_raw")
+        vr, ldv = _rows(vis_raw, 1, "vis_raw")
+        deltas = _cuda(deltas, torch.float32, "deltas").contiguous()
+        err = torch.empty(N, device=deltas.device, dtype=torch.float32)
+        absorb = torch.empty(N, device=deltas.device, dtype=torch.float32)
+        if N:
+            check(_lib.load().snb_solar_loss_fwd(_ptr(rr), ldr, _ptr(vr), ldv, _ptr(deltas), N, S, _ptr(err), _ptr(absorb), _stream()))
+        ctx.save_for_backward(rho_raw, vis_raw, deltas)
+        ctx.set_materialize_grads(False)
+        return err, absorb
+
+    @staticmethod
+    def backward(ctx, g_err, g_abs):
+        rho_raw, vis_raw, deltas = ctx.saved_tensors
+        N, S = deltas.shape[0], deltas.shape[1]
+        rr, ldr = _rows(rho_raw, 1, "rho_raw")
+        vr, ldv = _rows(vis_raw, 1, "vis_raw")
+        c = lambda g: None if g is None else g.float().contiguous()
+        g_err, g_abs = c(g_err), c(g_abs)
+        d_vis = torch.empty(N * S, 1, device=deltas.device, dtype=torch.float32)
+        check(_lib.load().snb_solar_loss_bwd(_ptr(rr), ldr, _ptr(vr), ldv, _ptr(deltas), N, S, _ptr(g_err), _ptr(g_abs), _ptr(d_vis), _stream()))
+        return None, d_vis.reshape(vis_raw.shape), None
+
+
+def solar_loss(rho_raw, vis_raw, deltas):
+    """solar pass of get_loss from the raw heads -> (err [N], absorb [N]); the only gradient is w.r.t. vis_raw (PV and PE
+    are detached in both terms, Eval_Tools_2.py:353-368)"""
+    return _SolarLoss.apply(rho_raw, vis_raw, deltas)
+
+
 def cli_composite(rho, deltas, base, vis, adj, cls, exact_vis=None):
     """mg_Img_Eval.py:123-190 sums in float64.  Inputs f32 or f64 device tensors; cls [C] f64."""
     N, S = rho.shape[0], rho.shape[1]
@@ -212,6 +333,26 @@ def cli_composite(rho, deltas, base, vis, adj, cls, exact_vis=None):
     check(_lib.load().snb_cli_composite(*[_ptr(x) for x in ins], _ptr(cls), _ptr(ev), dt, N, S, Cn, _ptr(base_img),
                                         _ptr(season), _ptr(extreme), _ptr(raw), _ptr(raw_e), _stream()))
     return base_img, season, extreme, raw, raw_e
+
+
+def render_composite_raw(pos4, vis_raw, adj, deltas, cls, exact_vis=None):
+    """CLI output-image sums from the raw heads of a block of rays (float64): -> season [N,3], raw_shadow [N], raw_shadow_exact
+    [N] or None.  pos4 [N*S,4], vis_raw [N*S], adj [N*S,C*3] float32 contiguous; deltas [N,S]; cls [C] float64."""
+    N, S = deltas.shape[0], deltas.shape[1]
+    Cn = cls.shape[0]
+    pos4 = _cuda(pos4, torch.float32, "pos4").contiguous()
+    vis_raw = _cuda(vis_raw, torch.float32, "vis_raw").contiguous()
+    adj = _cuda(adj, torch.float32, "adj").contiguous()
+    deltas = _cuda(deltas, torch.float32, "deltas").contiguous()
+    cls = _cuda(cls, torch.float64, "cls").contiguous()
+    ev = None if exact_vis is None else _cuda(exact_vis, torch.float32, "exact_vis").contiguous()
+    mk = lambda *s: torch.empty(*s, device=deltas.device, dtype=torch.float64)
+    season, raw = mk(N, 3), mk(N)
+    raw_e = mk(N) if ev is not None else None
+    if N:
+        check(_lib.load().snb_render_composite_raw(_ptr(pos4), _ptr(vis_raw), _ptr(adj), _ptr(deltas), _ptr(cls), _ptr(ev), N, S, Cn,
+                                                   _ptr(season), _ptr(raw), _ptr(raw_e), _stream()))
+    return season, raw, raw_e
 
 
 def cli_classic_shadow(rho, deltas, base, vis, adj, sky, cls):
@@ -255,6 +396,26 @@ def year_sweep(rho, deltas, base, adj, cls, shade=None, out=None, ps_weight=None
         return out
     check(_lib.load().snb_year_sweep(*[_ptr(x) for x in ins], _ptr(cls), _ptr(shade), _ptr(ps_weight), _DT[rho.dtype], N, S, Cn, T,
                                      _ptr(out), _stream()))
+    return out
+
+
+def year_sweep_raw(pos4, deltas, adj, cls, shade=None, out=None):
+    """year_sweep fed by the raw pos4 [N*S,4] (sigma, base colour logits) and adj [N*S,C*3] of the network -> [T,N,3] f64"""
+    N, S = deltas.shape[0], deltas.shape[1]
+    T, Cn = cls.shape[0], cls.shape[1]
+    if S > YEAR_SWEEP_MAX_S or Cn > YEAR_SWEEP_MAX_C or T * Cn * 8 > YEAR_SWEEP_MAX_CLS_BYTES:
+        raise ValueError("year_sweep_raw: S <= %d, C <= %d, T*C*8 <= %d bytes per launch (got S=%d, C=%d, T=%d)"
+                         % (YEAR_SWEEP_MAX_S, YEAR_SWEEP_MAX_C, YEAR_SWEEP_MAX_CLS_BYTES, S, Cn, T))
+    pos4 = _cuda(pos4, torch.float32, "pos4").contiguous()
+    adj = _cuda(adj, torch.float32, "adj").contiguous()
+    deltas = _cuda(deltas, torch.float32, "deltas").contiguous()
+    cls = _cuda(cls, torch.float64, "cls").contiguous()
+    if shade is not None:
+        shade = _cuda(shade, torch.float64, "shade").contiguous()
+    if out is None:
+        out = torch.empty(T, N, 3, device=deltas.device, dtype=torch.float64)
+    if N and T:
+        check(_lib.load().snb_year_sweep_raw(_ptr(pos4), _ptr(deltas), _ptr(adj), _ptr(cls), _ptr(shade), N, S, Cn, T, _ptr(out), _stream()))
     return out
 
 

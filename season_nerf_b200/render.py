@@ -337,31 +337,46 @@ def render_shard(the_network, view_el_az, sun_el_az, time_frac, out_img_size, W2
             block = max(1, min(block, 16384))
         cls_all = None if class_vecs is None else t.as_tensor(np.asarray(class_vecs), dtype=t.float64).to(device).contiguous()
         rgb_parts, mask_parts = [], []
+        S = out_img_size[2]
+        sun_np = np.asarray(sun_vec, dtype=np.float64)
+        sun = t.tensor(sun_np, dtype=t.float32, device=device).reshape(1, 3)
+        tim = t.tensor(encode_time(time_frac), dtype=t.float32, device=device).reshape(1, 4)
+        ts = sample_ts(S, eval_mode=True, include_end_pt=True).to(device)
+        step_exact = max(1, _points_per_call(the_network) // (S * S))
         for b0 in range(lo, max(hi, lo + 1), block):
             b1 = min(b0 + block, hi)
-            idx = t.arange(b0, b1, device=device)
-            xyz = t.stack([lin_h[idx // W], lin_w[idx % W], t.zeros(b1 - b0, dtype=t.float64, device=device)], 1)
-            tops, bots = (xyz + off).float(), (xyz - off).float()
-            D = _internal_render(the_network, tops, bots, sun_vec, time_frac, out_img_size, 150000, include_exact_solar, device)
-            keys = ["Rho", "Deltas", "Base_Col", "Est_Solar_Vis", "Adjust_col", "Output_class", "Sky_Col"]
-            rho, dl, base, vis, adj, ocl, skyc = [D.dev[k] for k in keys]
-            n, S = rho.shape[0], rho.shape[1]
-            if n == 0:
+            n = b1 - b0
+            if n <= 0:
                 rgb_parts.append(t.zeros((0, 3) if cls_all is None else (cls_all.shape[0], 0, 3), dtype=t.float64, device=device))
                 mask_parts.append(t.zeros(0, dtype=t.float64, device=device))
                 break
-            ev = D.dev["Exact_Solar"].reshape(n, S) if include_exact_solar else None
-            sky0 = skyc[0, 0].double()                  # sun direction and time are those of the whole image: every ray's
-            cls0 = ocl[0, 0].double().contiguous() if cls_all is None else cls_all[0].contiguous()      # value = ray 0's
-            _, season, _, raw, raw_e = ops.cli_composite(rho.reshape(n, S), dl.reshape(n, S), base, vis.reshape(n, S), adj, cls0, ev)
+            idx = t.arange(b0, b1, device=device)
+            xyz = t.stack([lin_h[idx // W], lin_w[idx % W], t.zeros(n, dtype=t.float64, device=device)], 1)
+            tops, bots = (xyz + off).float(), (xyz - off).float()
+            # the RAW heads of the block are composited right away (ops.render_composite_raw / year_sweep_raw): neither the
+            # activated copies nor the per-sample component arrays of _internal_render (28 floats per sample) are formed
+            pts, deltas = ops.sample_rays(tops, bots, ts, zero_oob=True)                        # mg_Img_Eval.py:40-42
+            pos, vis, adj, sky, cl = the_network.forward_rays(pts.reshape(-1, 3), sun, tim, S)
+            sky0 = the_network.Sigmoid(sky[0]).double()       # sun direction and time are those of the whole image: every
+            cls0 = the_network.SoftMax(cl[0:1])[0].double().contiguous() if cls_all is None else cls_all[0].contiguous()   # ray = ray 0
+            ev = None
+            if include_exact_solar:                                                             # mg_Img_Eval.py:57-70
+                ev = t.empty(n, S, device=device, dtype=t.float32)
+                for i in range(0, n, step_exact):
+                    e = min(i + step_exact, n)
+                    nb = pts[i:e].reshape(-1, 3)
+                    nt = ops.solar_tops(nb, sun_np, f64=True)
+                    _, nd = ops.sample_rays(nt, nb, ts, zero_oob=True, want_pts=False)
+                    ev[i:e] = ops.march_transmittance(_sigma_on_rays(the_network, nt, nb, ts, S), nd).reshape(e - i, S)
+            season, raw, raw_e = ops.render_composite_raw(pos, vis.reshape(-1), adj, deltas, cls0, ev)
             mask = t.sigmoid(((raw_e if include_exact_solar else raw) - .2) * 30)
             shade = (mask.unsqueeze(1) + (1 - mask.unsqueeze(1)) * sky0.reshape(1, 3)).contiguous()
             mask_parts.append(mask)
             if cls_all is None:
                 rgb_parts.append(season * shade)
             else:
-                rgb_parts.append(ops.year_sweep(rho.reshape(n, S), dl.reshape(n, S), base, adj, cls_all, shade=shade))
-            del D
+                rgb_parts.append(ops.year_sweep_raw(pos, deltas, adj, cls_all, shade=shade))
+            del pts, pos, vis, adj
         cat_dim = 0 if cls_all is None else 1
         rgb = rgb_parts[0] if len(rgb_parts) == 1 else t.cat(rgb_parts, cat_dim)
         mask = mask_parts[0] if len(mask_parts) == 1 else t.cat(mask_parts, 0)

@@ -68,3 +68,47 @@ def height_map(network, shape, n_samples, device, h_range=None):
     if h_range is not None:
         hm = (hm + 1) / 2 * (h_range[1] - h_range[0]) + h_range[0]
     return hm
+
+
+def confidence_range(P_Surf, h_range):
+    """The 67 % range loop of eval_HM (Eval_funcs.py:315-331), for all columns at once on the device: starting at the mode of
+    the surface PDF the window grows by one sample on each side (clamped) until it holds >= 0.67 of the mass or covers the
+    column.  -> conf_range [H,W,3] float64 = (z0, z1, (z1 - z0) / S * (h1 - h0)).  The window mass of step k is the difference of
+    two float64 prefix sums; the reference sums the slice - identical up to the last bit of a comparison against 0.67."""
+    pdf = P_Surf / t.sum(P_Surf, 2, keepdim=True)
+    H, W, S = pdf.shape
+    start = t.argmax(pdf, 2)                                            # first maximum, like np.argmax
+    csum = t.cat([t.zeros(H, W, 1, dtype=pdf.dtype, device=pdf.device), t.cumsum(pdf, 2)], 2)       # [H,W,S+1]
+    k = t.arange(S + 1, device=pdf.device).reshape(1, 1, -1)
+    z0 = (start.unsqueeze(-1) - k).clamp_min(0)                         # window of growth step k
+    z1 = (start.unsqueeze(-1) + 1 + k).clamp_max(S)
+    value = t.gather(csum, 2, z1) - t.gather(csum, 2, z0)
+    # step 0 is the mode alone; the loop stops at the first step whose window reaches 0.67 or spans the column.  A NaN PDF
+    # (all-zero column) never satisfies `value < .67`: the reference leaves the window at the mode
+    done = ~(value < .67) | ((z0 == 0) & (z1 == S))
+    first = t.argmax(done.to(t.int8), 2, keepdim=True)
+    a, b = t.gather(z0, 2, first).squeeze(-1).double(), t.gather(z1, 2, first).squeeze(-1).double()
+    return t.stack([a, b, (b - a) / S * (h_range[1] - h_range[0])], -1)
+
+
+def eval_HM(network, GT, h_range, n_samples, device, max_batch_size=None):
+    """Eval_funcs.py:298-395: expected height map of the density volume, its 67 % confidence range, the mean-shifted height
+    map in metres and the error scores against the ground-truth DSM *before alignment*.
+    -> (Imgs {"GT", "Est_HM_no_Shift", "Conf_Range"}, scores_before {"MAE", "RMSE", "Acc_1_m", "Median"}, conf_stats
+    (nanmean, nanmedian of the range in metres - the two numbers the reference prints)).  The shift / rotation alignment
+    search that follows in the reference (:397 ff., scipy image warps on the host) is evaluation tooling and is not part of
+    this package; the first two return values are the reference's first two."""
+    GT = np.asarray(GT, dtype=np.float64)
+    _, _, _, ps, _ = _volume(network, GT.shape[0], GT.shape[1], n_samples, device, False)
+    z = t.tensor(np.linspace(1, -1, n_samples), dtype=t.float64, device=ps.device).reshape(1, 1, -1)
+    est = (t.sum(ps * z, 2) / t.sum(ps, 2)).cpu().numpy()
+    conf = confidence_range(ps, h_range).cpu().numpy()
+    h0, h1 = h_range[0], h_range[1]
+    est = (est + 1) / 2 * (h1 - h0) + h0
+    GTm = (GT + 1) / 2 * (h1 - h0) + h0
+    est = est + np.nanmean((GTm - est).ravel())
+    diff = est - GTm
+    diff = np.ravel(diff[diff == diff])
+    scores = {"MAE": np.mean(np.abs(diff)), "RMSE": np.sqrt(np.mean(diff ** 2)), "Acc_1_m": np.sum(np.abs(diff) <= 1) / diff.shape[0],
+              "Median": np.median(np.abs(diff))}
+    return {"GT": GTm, "Est_HM_no_Shift": est, "Conf_Range": conf}, scores, (np.nanmean(conf[:, :, 2]), np.nanmedian(conf[:, :, 2]))

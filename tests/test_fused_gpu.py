@@ -92,6 +92,14 @@ def test_ray_sharded_render_equals_unsharded(params0):
     assert parts[0][0] == 0 and parts[-1][1] == 120 and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
     cat = t.cat([p[2] for p in parts], 0).reshape(12, 10, 3).cpu().numpy()
     assert maxabs(cat, ref) < 1e-6
+    # year sweep of the shard (raw heads -> ops.year_sweep_raw) vs the component path (get_imgs_from_Img_Dict_t_step)
+    tf = np.array([snb.encode_time(k / 5) for k in range(5)])
+    with t.no_grad():
+        cv = net.get_class_only(t.tensor(tf, dtype=t.float32, device=dev)).double().cpu().numpy()
+    sweep_ref = snb.get_imgs_from_Img_Dict_t_step(D, size, cv)
+    _, _, slab, _ = snb.render_shard(net, [80, 0], [45, 135], 184 / 365, size, so.OMA_W2C, so.oma_w2l_h(), dev, 0, 1,
+                                     include_exact_solar=True, class_vecs=cv)
+    assert maxabs(slab.reshape(5, 12, 10, 3), sweep_ref) < 2e-6
 
 
 def test_fused_full_size_permutation_and_chunk_invariance(params0):

@@ -468,3 +468,89 @@ def test_year_sweep_float32_lanes_kernel_vs_float64_kernel(N, S, C, T):
         ref = ops.year_sweep(rho.double(), dl.double(), base.double(), adj.double(), cls, **kw64)
         assert got.shape == (T, N, 3) and got.dtype == t.float64
         assert float((got - ref).abs().max()) < 1e-6, (kw.keys(), float((got - ref).abs().max()))
+
+
+def _heads_reference(pos, vis, adj, sky, cl, deltas, classic):
+    """torch restatement of T_NeRF_net_v2.py:87-98 + Eval_Tools_2.py:187-215 on the raw heads (autograd reference)"""
+    N, S = deltas.shape
+    C = cl.shape[1]
+    cls = t.softmax(cl, 1)
+    rho = t.nn.functional.softplus(pos[:, 0]).reshape(N, S)
+    mix = (adj.reshape(N, S, C, 3) * cls.reshape(N, 1, C, 1)).sum(2)
+    col = t.sigmoid(pos[:, 1:4].reshape(N, S, 3) + mix)
+    v = t.sigmoid(vis.reshape(N, S))
+    k = t.sigmoid(sky)
+    y = rho * deltas
+    pv = t.exp(-(t.cumsum(y, 1) - y))
+    pe = 1 - t.exp(-y)
+    ps = pv * pe
+    albedo = (ps.unsqueeze(-1) * col).sum(1)
+    if classic:
+        rendered = (ps.unsqueeze(-1) * col * (v.unsqueeze(-1) + (1 - v.unsqueeze(-1)) * k.unsqueeze(1))).sum(1)
+    else:
+        sv3 = t.sigmoid(((v.detach() * ps).sum(1, keepdim=True) - .2) * 30)
+        rendered = albedo * (sv3 + (1 - sv3) * k)
+    return albedo, rendered, k, (v * ps).sum(1), pv, pe, ps
+
+
+@pytest.mark.parametrize("classic", [False, True])
+@pytest.mark.parametrize("N,S,C,pitch", [(257, 96, 4, False), (33, 96, 4, True), (5, 40, 3, False), (2, 128, 1, False), (0, 96, 4, False)])
+def test_heads_composite_forward_backward_vs_torch(N, S, C, pitch, classic):
+    """fused head activations + compositing (csrc/heads.cu) against the torch restatement, double-precision autograd:
+    outputs <= 2e-6, every raw-head gradient <= 2e-5 relative"""
+    from season_nerf_b200 import ops
+    g = t.Generator(device="cuda").manual_seed(7 * N + S + C)
+    r = lambda *s: t.randn(*s, device="cuda", generator=g)
+    M = N * S
+    if pitch:           # the layer-wise path hands over 16-float-wide padded rows
+        Pb, Vb, Ab = r(M, 16), r(M, 16), r(M, 16)
+        pos, vis, adj = Pb[:, :4], Vb[:, :1], Ab[:, :3 * C]
+    else:
+        pos, vis, adj = r(M, 4), r(M, 1), r(M, 3 * C)
+    pos = pos * 2
+    sky, cl = r(N, 3), r(N, C) * 2
+    deltas = t.rand(N, S, device="cuda", generator=g) * (4.0 / S)
+    leaves = [x.clone().requires_grad_(True) for x in (pos, vis, adj, sky, cl)]
+    refl = [x.detach().double().requires_grad_(True) for x in (pos, vis, adj, sky, cl)]
+    albedo, rendered, sky_act, vsum = ops.heads_composite(*leaves, deltas, classic)
+    ra, rr, rk, rv, rpv, rpe, rps = _heads_reference(*refl, deltas.double(), classic)
+    if N == 0:
+        assert albedo.shape == (0, 3) and rendered.shape == (0, 3)
+        return
+    for got, ref in ((albedo, ra), (rendered, rr), (sky_act, rk), (vsum, rv)):
+        assert float((got.double() - ref).abs().max()) < 2e-6
+    _, _, _, _, PV, PE, PS = ops.heads_composite_fwd(pos, vis, adj, sky, cl, deltas, classic, want_pv=True)
+    for got, ref in ((PV, rpv), (PE, rpe), (PS, rps)):
+        assert float((got.double() - ref).abs().max()) < 2e-6
+    wa, wr, wk = r(N, 3), r(N, 3), r(N, 3)
+    (albedo * wa).sum().add((rendered * wr).sum()).add((sky_act * wk).sum()).backward()
+    (ra * wa.double()).sum().add((rr * wr.double()).sum()).add((rk * wk.double()).sum()).backward()
+    names = ["pos", "vis", "adj", "sky", "cls"]
+    for nm, a, b in zip(names, leaves, refl):
+        if nm == "vis" and not classic:
+            assert a.grad is None or float(a.grad.abs().max()) == 0.0          # detached (Eval_Tools_2.py:214)
+            continue
+        e = float((a.grad.double() - b.grad).norm() / b.grad.norm().clamp_min(1e-30))
+        assert e < 2e-5, (nm, e)
+
+
+@pytest.mark.parametrize("N,S", [(300, 96), (7, 33), (1, 128)])
+def test_solar_loss_forward_backward_vs_torch(N, S):
+    """solar-pass sums of get_loss from the raw heads (Eval_Tools_2.py:353-368): PV and PE detached, gradient only w.r.t. vis"""
+    from season_nerf_b200 import ops
+    g = t.Generator(device="cuda").manual_seed(N + S)
+    rho_raw = t.randn(N * S, 1, device="cuda", generator=g) * 2
+    vis_raw = t.randn(N * S, 1, device="cuda", generator=g).requires_grad_(True)
+    deltas = t.rand(N, S, device="cuda", generator=g) * (4.0 / S)
+    err, absorb = ops.solar_loss(rho_raw, vis_raw, deltas)
+    vd = vis_raw.detach().double().requires_grad_(True)
+    rho = t.nn.functional.softplus(rho_raw.double()).reshape(N, S)
+    y = rho * deltas.double()
+    pv, pe = t.exp(-(t.cumsum(y, 1) - y)), 1 - t.exp(-y)
+    v = t.sigmoid(vd.reshape(N, S))
+    err_r, abs_r = ((v - pv) ** 2).sum(1), 1 - (pe * pv * v).sum(1)
+    assert float((err.double() - err_r).abs().max()) < 1e-5 and float((absorb.double() - abs_r).abs().max()) < 2e-6
+    w1, w2 = t.rand(N, device="cuda", generator=g), t.rand(N, device="cuda", generator=g)
+    ((err * w1).sum() + (absorb * w2).sum()).backward()
+    ((err_r * w1.double()).sum() + (abs_r * w2.double()).sum()).backward()
+    assert float((vis_raw.grad.double() - vd.grad).norm() / vd.grad.norm()) < 2e-5

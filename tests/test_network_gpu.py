@@ -403,3 +403,64 @@ def test_get_loss_prior_mse_golden(params0, precision):
             if float(np.abs(g[k]).max()) < 1e-4 * scale:
                 continue
             assert relerr(p.grad, g[k]) < (5e-3 if precision == "fp32" else 0.15), (k, relerr(p.grad, g[k]))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("type2", [False, True])
+def test_get_loss_fused_heads_path_equals_general_path(params0, precision, type2):
+    """get_loss through the fused raw-head kernels (engine.FAST_LOSS, the default) vs the general dictionary path
+    (eval / eval_Rho_Only + torch activations): same losses, same gradients up to float32 summation order"""
+    from oracle import season_oracle as so
+    import season_nerf_b200 as snb
+    from season_nerf_b200 import engine
+    n = 64
+    batch = so.synthetic_batch(n, seed=5, n_images=7)
+    st, en, vec, tm, _ = so.create_solar_rays_uniform(n, so.OMA_W2C, so.oma_w2l_h(), np.random.RandomState(6), t.Generator().manual_seed(6))
+    jit = t.rand(S, generator=t.Generator().manual_seed(8))
+    res = {}
+    for fast in (True, False):
+        engine.FAST_LOSS = fast
+        try:
+            net = make_net(params0, precision, train=True)
+            ada = _ada(False)
+            tool = _tool(so.default_args(Solar_Type_2=type2), False, ada)
+            L = tool.get_loss(batch, net, 30, True, jitter=jit, solar=(st, en, vec, tm), solar_jitter=jit)
+            sum(L[k][0] * L[k][1] for k in L).backward()
+            res[fast] = ({k: float(L[k][0]) for k in L}, {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None},
+                         ada.latent_scale.grad.clone())
+        finally:
+            engine.FAST_LOSS = True
+    lf, gf, af = res[True]
+    lg, gg, ag = res[False]
+    assert lf.keys() == lg.keys() and gf.keys() == gg.keys()
+    for k in lf:
+        assert abs(lf[k] - lg[k]) <= (2e-5 if precision == "fp32" else 2e-3) * max(abs(lg[k]), 1e-2), (k, lf[k], lg[k])
+    scale = max(float(v.norm()) for v in gg.values())
+    worst = max(float((gf[k] - gg[k]).norm()) / max(float(gg[k].norm()), 1e-4 * scale) for k in gg)
+    assert worst < (2e-4 if precision == "fp32" else 5e-2), worst
+    assert relerr(af, ag) < (1e-4 if precision == "fp32" else 2e-2)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_volume_consumers_golden(params0, precision):
+    """eval_shadow_data (mg_Shadow_Eval.py:72-104) and eval_HM to the scores before alignment (Eval_funcs.py:298-395) on the
+    device vs the unmodified reference (fixture evals)."""
+    import season_nerf_b200 as snb
+    from oracle import season_oracle as so
+    g = load_golden("evals")
+    net = make_net(params0, precision)
+    tol = TOL[precision]
+    ve, vs, sk = snb.eval_shadow_data(net, g["angles"], g["ground_points"], 96, so.OMA_W2C, so.oma_w2l_h(), 15000, t.device("cuda"))
+    assert ve.shape == g["vis_exact"].shape and vs.shape == g["vis_est"].shape and sk.shape == g["sky_col"].shape and ve.dtype == np.float64
+    assert maxabs(ve, g["vis_exact"]) < tol["out"] and maxabs(vs, g["vis_est"]) < tol["out"] and maxabs(sk, g["sky_col"]) < tol["rho"]
+    Imgs, scores, conf_stats = snb.eval_HM(net, g["hm_GT"], (300., 370.), 96, t.device("cuda"), 5000)
+    np.testing.assert_allclose(Imgs["GT"], g["hm_GT_m"], rtol=1e-12, equal_nan=True)
+    m = ~np.isnan(g["hm_est_no_shift"])
+    # heights in metres over a 70 m range: 1e-4 / 1e-2 of the normalised cube = 3.5 mm / 35 cm
+    assert np.abs(Imgs["Est_HM_no_Shift"][m] - g["hm_est_no_shift"][m]).max() < 35 * tol["out"]
+    for k, v in zip(g["before_keys"].tolist(), g["before_vals"].tolist()):
+        assert abs(scores[k] - v) <= (1e-3 if precision == "fp32" else 5e-2) * max(abs(v), 1.0), (k, scores[k], v)
+    if precision == "fp32":
+        assert abs(conf_stats[0] - float(g["conf_mean"])) < 1e-6 and abs(conf_stats[1] - float(g["conf_median"])) < 1e-6
+    else:       # one sample of a 96-sample column is 0.73 m of the 70 m range
+        assert abs(conf_stats[0] - float(g["conf_mean"])) < 1.5

@@ -368,3 +368,41 @@ def test_barron_partition_function_known_answers():
         r = t.tensor([[0.01, -0.02, 0.03]])
         want_nll = 0.5 * (r / 0.03) ** 2 + np.log(0.03) + 0.5 * np.log(2 * np.pi)
         assert float((A.lossfun(r) - want_nll).abs().max()) < 1e-5
+
+
+def test_volume_consumers_oracle_matches_reference(params0):
+    """eval_shadow_data (mg_Shadow_Eval.py:72-104) and the head of eval_HM (Eval_funcs.py:298-395) - restatements vs the
+    unmodified reference (fixture evals, oracle/make_golden_evals.py); the product's vectorised confidence-range loop vs the
+    oracle's literal double loop on the same volume."""
+    g = load_golden("evals")
+    ve, vs, sk = so.eval_shadow_data(params0, g["angles"], g["ground_points"], 96, so.OMA_W2C, so.oma_w2l_h())
+    close(ve, g["vis_exact"], rtol=1e-4, atol=2e-6)
+    close(vs, g["vis_est"], rtol=1e-4, atol=2e-6)
+    close(sk, g["sky_col"], rtol=1e-4, atol=2e-6)
+    GTm, est, conf, scores = so.eval_hm_head(params0, g["hm_GT"], (300., 370.), 96)
+    np.testing.assert_allclose(GTm, g["hm_GT_m"], rtol=1e-12, equal_nan=True)
+    np.testing.assert_allclose(est, g["hm_est_no_shift"], rtol=1e-6, equal_nan=True)
+    assert abs(np.nanmean(conf[:, :, 2]) - float(g["conf_mean"])) < 1e-9 and abs(np.nanmedian(conf[:, :, 2]) - float(g["conf_median"])) < 1e-9
+    for k, v in zip(g["before_keys"].tolist(), g["before_vals"].tolist()):
+        assert abs(scores[k] - v) <= 1e-5 * max(abs(v), 1.0), (k, scores[k], v)
+    from season_nerf_b200 import shadow_eval, volume
+    _, _, _, ps, _ = so.gen_results(params0, g["hm_GT"].shape, 96)
+    got = volume.confidence_range(t.tensor(ps), (300., 370.)).numpy()
+    assert np.array_equal(got, conf)
+    ps2 = np.abs(np.random.RandomState(0).randn(7, 9, 33)) ** 3            # spiky random PDFs incl. an all-zero column
+    ps2[1, 2] = 0
+    pdf = ps2 / np.sum(ps2, 2, keepdims=True)
+    ref = np.zeros([7, 9, 2])
+    for i in range(7):
+        for j in range(9):
+            z0 = int(np.argmax(pdf[i, j])); z1 = z0 + 1; value = pdf[i, j, z0]
+            while value < .67 and (z0 != 0 or z1 != 33):
+                z0, z1 = max(0, z0 - 1), min(z1 + 1, 33)
+                value = np.sum(pdf[i, j, z0:z1])
+            ref[i, j] = z0, z1
+    with np.errstate(invalid="ignore"):
+        got = volume.confidence_range(t.tensor(ps2), (0., 1.)).numpy()
+    assert np.array_equal(got[:, :, :2], ref)
+    sa = shadow_eval.shadow_anaylysis(g["ground_points"], g["angles"], {"Exact_Vis": g["vis_exact"].astype(np.float64), "Est_Vis": g["vis_est"].astype(np.float64)})
+    for k, v in zip(g["sa_keys"].tolist(), g["sa_vals"].tolist()):
+        assert (np.isnan(v) and np.isnan(sa[k])) or abs(sa[k] - v) <= 1e-6 * max(abs(v), 1.0), (k, sa[k], v)
