@@ -137,6 +137,14 @@ int snb_gemm(const void* A, int lda, int a_t, const void* B, int ldb, int b_t, v
  * Replaces nn.Linear + the batch-statistics pass of nn.BatchNorm1d in misc.py:169-170,188-189. */
 int snb_gemm_stats(const void* A, int lda, const void* B, int ldb, void* C, int ldc, const float* bias, float alpha,
                    long long M, int N, int K, float* stats, void* stream);
+/* snb_gemm_stats whose A operand is the SAVED PRE-ACTIVATION of the previous SIREN layer: C = alpha * (sin(xa[k] * Zprev[m,k]
+ * + xc[k]) . B^T + bias) - the previous layer's activation sin(BatchNorm(.)) (misc.py:188-189, xa / xc = its folded affine)
+ * is applied by transform warps to the TMA-landed operand tile in shared memory, before the tensor core reads it: the
+ * stand-alone activation pass never runs and the activated [M,K] matrix is not read from HBM.  Y (optional, [M,K] bf16, row
+ * pitch ldy) receives the activated operand for a later weight gradient; NULL = it is never written either.  Same outputs as
+ * snb_gemm_stats (C bf16 + column sum / sum of squares); SNB_ERR_UNSUPPORTED for shapes the CTA-pair kernels do not take. */
+int snb_gemm_stats_xf(const void* Zprev, int lda, const float* xa, const float* xc, const void* B, int ldb, void* C, int ldc,
+                      const float* bias, float alpha, long long M, int N, int K, float* stats, void* Y, int ldy, void* stream);
 
 /* Forward of a SIREN layer WITHOUT BatchNorm in one kernel (bf16 tcgen05 GEMM + activation epilogue):
  *   Z[M,N] = alpha*(A[M,K].B[N,K]^T + bias)  (bf16, kept for the backward),   Y[M,N] = sin(Z)  (bf16).

@@ -40,6 +40,7 @@ SIGNATURES = {
     "snb_pe_encode": [_p, _i, _ll, _i, _i, _p, _i, _i, _i, _i, _p],
     "snb_gemm": [_p, _i, _i, _p, _i, _i, _p, _i, _p, _f, _i, _ll, _i, _i, _i, _i, _p],
     "snb_gemm_stats": [_p, _i, _p, _i, _p, _i, _p, _f, _ll, _i, _i, _p, _p],
+    "snb_gemm_stats_xf": [_p, _i, _p, _p, _p, _i, _p, _i, _p, _f, _ll, _i, _i, _p, _p, _i, _p],
     "snb_gemm_sine_fwd": [_p, _i, _p, _i, _p, _i, _p, _i, _p, _f, _ll, _i, _i, _p],
     "snb_gemm_sine_bwd": [_p, _i, _p, _i, _p, _i, _p, _i, _p, _p, _p, _p, _f, _ll, _i, _i, _p, _p],
     "snb_bn_bwd_apply": [_p, _i, _p, _i, _p, _p, _p, _p, _p, _f, _p, _i, _ll, _i, _i, _p],

@@ -3,6 +3,7 @@
 // serves forward (A.B^T), input gradients and weight gradients (transposed operands).  Not the production path:
 // production uses the tcgen05 kernel in gemm_tc.cu.
 //   reference: nn.Linear inside misc.py:188-189 and its autograd backward.
+#include <cstdlib>
 #include "common.cuh"
 #include "api.h"
 
@@ -89,7 +90,7 @@ int snb_gemm_bf16_tc2(const void* A, int lda, int a_t, const void* B, int ldb, i
                       const float* bias, float alpha, int accumulate, long long M, int N, int K, int out_dtype,
                       float* stats, cudaStream_t st, int epi = 0, const void* X = nullptr, int ldx = 0,
                       const float* ea = nullptr, const float* ec = nullptr, const float* emean = nullptr,
-                      const float* einvstd = nullptr);
+                      const float* einvstd = nullptr, const float* xa = nullptr, const float* xc = nullptr);
 
 extern "C" int snb_gemm_sine_fwd(const void* A, int lda, const void* B, int ldb, void* Z, int ldz, void* Y, int ldy,
                                  const float* bias, float alpha, long long M, int N, int K, void* stream) {
@@ -113,6 +114,30 @@ extern "C" int snb_gemm_stats(const void* A, int lda, const void* B, int ldb, vo
   SNB_CHECK_ARG(A && B && C && stats && M >= 0 && N > 0 && K > 0 && ldc >= N);
   if (M == 0) return SNB_OK;
   return snb_gemm_bf16_tc2(A, lda, 0, B, ldb, 0, C, ldc, bias, alpha, 0, M, N, K, SNB_BF16, stats, (cudaStream_t)stream);
+}
+
+// implemented in gemm_tc3.cu (resident-A kernel: every operand element is activated once)
+int snb_gemm_bf16_tc3(const void* Zprev, int lda, const float* xa, const float* xc, const void* B, int ldb, void* C, int ldc,
+                      const float* bias, float alpha, long long M, int N, int K, float* stats, void* Y, int ldy,
+                      cudaStream_t st);
+
+extern "C" int snb_gemm_stats_xf(const void* Zprev, int lda, const float* xa, const float* xc, const void* B, int ldb, void* C,
+                                 int ldc, const float* bias, float alpha, long long M, int N, int K, float* stats, void* Y,
+                                 int ldy, void* stream) {
+  SNB_CHECK_ARG(Zprev && xa && xc && B && C && stats && M >= 0 && N > 0 && K > 0 && ldc >= N && (!Y || ldy >= K));
+  if (M == 0) return SNB_OK;
+  static int force_tc2 = -1;
+  if (force_tc2 < 0) {
+    const char* e = getenv("SNB_XF_STREAMED");       // A/B switch: 1 = the streamed-A kernel of gemm_tc2.cu (activates twice)
+    force_tc2 = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (!force_tc2) {
+    const int rc = snb_gemm_bf16_tc3(Zprev, lda, xa, xc, B, ldb, C, ldc, bias, alpha, M, N, K, stats, Y, ldy, (cudaStream_t)stream);
+    if (rc != SNB_ERR_UNSUPPORTED) return rc;
+  }
+  if (Y) return SNB_ERR_UNSUPPORTED;                 // only the resident-A kernel writes the activated operand back
+  return snb_gemm_bf16_tc2(Zprev, lda, 0, B, ldb, 0, C, ldc, bias, alpha, 0, M, N, K, SNB_BF16, stats, (cudaStream_t)stream, 0,
+                           nullptr, 0, nullptr, nullptr, nullptr, nullptr, xa, xc);
 }
 
 extern "C" int snb_gemm(const void* A, int lda, int a_t, const void* B, int ldb, int b_t, void* C, int ldc,

@@ -40,7 +40,14 @@ constexpr int k2BK = 64;
 // dropped.  For reference, cuBLAS and the plain-store kernel both take 179 us on this shape, scripts/gemm_probe.py.)
 __host__ __device__ constexpr int k2_epi_warps(int epi) { return epi >= 2 ? 8 : 4; }
 __host__ __device__ constexpr int k2_base_epi(int epi) { return epi == 3 ? 0 : epi; }
-__host__ __device__ constexpr int k2_threads(int epi) { return 64 + 32 * k2_epi_warps(epi); }
+// kXf = 1: four TRANSFORM warps (2..5) sit between the TMA producer and the MMA issuer: the A operand arrives as the saved
+// pre-activation Z of the previous SIREN layer and is rewritten in shared memory as Y = sin(xa[k] * z + xc[k]) (the folded
+// BatchNorm affine of that layer, per K column) before the tensor core reads it - the consumer-side activation: the
+// stand-alone sin pass over the [M,K] matrix and the Y stream through HBM disappear (misc.py:188-189 for the NEXT layer's input).
+__host__ __device__ constexpr int k2_xf_warps(int xf) { return xf ? 4 : 0; }
+__host__ __device__ constexpr int k2_threads(int epi, int xf = 0) { return 64 + 32 * k2_xf_warps(xf) + 32 * k2_epi_warps(epi); }
+constexpr int k2MaxXfK = 1024;
+constexpr uint32_t k2XfBytes = 2 * k2MaxXfK * 4;              // xa[K], xc[K]
 constexpr int k2MaxBN = 256;
 constexpr uint32_t k2ABytes = k2BM * k2BK * 2;                 // 16 KB
 constexpr uint32_t k2BBytes = (k2MaxBN / 2) * k2BK * 2;        // 16 KB (this CTA's half of the B tile)
@@ -54,8 +61,8 @@ constexpr uint32_t k2StatBytes = 2 * k2MaxStatN * 4;           // 8 KB
 __host__ __device__ constexpr int k2_stages(int epi) { return epi ? 4 : 5; }
 __host__ __device__ constexpr uint32_t k2_cbytes(int epi) { return (uint32_t)k2_epi_warps(epi) * k2CWarpBytes; }
 __host__ __device__ constexpr uint32_t k2_xbytes(int epi) { return epi == 1 ? k2CBytes : 0u; }
-__host__ __device__ constexpr uint32_t k2_smem(int epi) {
-  return 1024 + k2_stages(epi) * k2StageBytes + k2_cbytes(epi) + k2_xbytes(epi) + k2StatBytes + 256;
+__host__ __device__ constexpr uint32_t k2_smem(int epi, int xf = 0) {
+  return 1024 + k2_stages(epi) * k2StageBytes + k2_cbytes(epi) + k2_xbytes(epi) + k2StatBytes + (xf ? k2XfBytes : 0u) + 256;
 }
 
 struct Gemm2Params {
@@ -81,17 +88,23 @@ struct Gemm2Params {
   const float* ec;
   const float* emean;
   const float* einvstd;
+  // kXf: A[m,k] <- sin(xa[k] * A[m,k] + xc[k]) in shared memory before the MMA
+  const float* xa;
+  const float* xc;
 };
 
-template <bool kAT, bool kBT, int kEpiT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2_threads(kEpiT), 1)
+template <bool kAT, bool kBT, int kEpiT, int kXf = 0>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2_threads(kEpiT, kXf), 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                   const __grid_constant__ CUtensorMap tmapC, const __grid_constant__ CUtensorMap tmapX,
                   const Gemm2Params p) {
   constexpr int kEpi = k2_base_epi(kEpiT);          // epilogue arithmetic; kEpiT also selects the warp count / staging
   constexpr int k2Stages = k2_stages(kEpiT);
   constexpr int kEpiWarps = k2_epi_warps(kEpiT);
-  constexpr int k2Threads = k2_threads(kEpiT);
+  constexpr int kXfWarps = k2_xf_warps(kXf);
+  constexpr int kEpiWarp0 = 2 + kXfWarps;                     // first epilogue warp
+  constexpr int k2Threads = k2_threads(kEpiT, kXf);
+  static_assert(kXf == 0 || (!kAT && !kBT), "the A transform is written for K-major operands");
   constexpr uint32_t kCBytes = k2_cbytes(kEpiT);
   constexpr uint32_t kXBytes = k2_xbytes(kEpiT);
 
@@ -101,14 +114,16 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   const uint32_t cstage_base = smem_base + k2Stages * k2StageBytes;
   const uint32_t xstage_base = cstage_base + kCBytes;
   float* stat_smem = reinterpret_cast<float*>(smem_al + k2Stages * k2StageBytes + kCBytes + kXBytes);
-  const uint32_t bar_base = cstage_base + kCBytes + kXBytes + k2StatBytes;
+  float* xf_smem = stat_smem + 2 * k2MaxStatN;                 // kXf: xa[0..K), xc at +k2MaxXfK
+  const uint32_t bar_base = cstage_base + kCBytes + kXBytes + k2StatBytes + (kXf ? k2XfBytes : 0u);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (k2Stages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * k2Stages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * k2Stages + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * k2Stages + 4);
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem_al + k2Stages * k2StageBytes + kCBytes + kXBytes + k2StatBytes + 8u * (2 * k2Stages + 4));
+  auto afull_bar = [&](int s) { return bar_base + 8u * (2 * k2Stages + 5 + s); };      // kXf: this CTA's A tile has landed
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
+      smem_al + k2Stages * k2StageBytes + kCBytes + kXBytes + k2StatBytes + (kXf ? k2XfBytes : 0u) + 8u * (2 * k2Stages + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -121,8 +136,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < k2Stages; ++s) {
-      mbar_init(full_bar(s), 1);
+      // kXf: the leader's full barrier also collects one arrival per transform warp of BOTH CTAs (operand rewritten)
+      mbar_init(full_bar(s), kXf ? 1 + 2 * kXfWarps : 1);
       mbar_init(empty_bar(s), 1);
+      if (kXf) mbar_init(afull_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
@@ -136,6 +153,12 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   }
   if (p.stats) {
     for (int i = threadIdx.x; i < 2 * k2MaxStatN; i += k2Threads) stat_smem[i] = 0.f;
+  }
+  if (kXf) {
+    for (int i = threadIdx.x; i < k2MaxXfK; i += k2Threads) {
+      xf_smem[i] = i < p.K ? __ldg(p.xa + i) : 0.f;
+      xf_smem[k2MaxXfK + i] = i < p.K ? __ldg(p.xc + i) : 0.f;
+    }
   }
   if (warp == 1) tmem_alloc_cg2(tmem_slot, 512);
   tc_fence_before();
@@ -166,7 +189,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     // ================= TMA producer (both CTAs; bytes are credited to the leader's full barrier) =================
     if (elect_one()) {
       const uint32_t b_bytes = kBT ? (uint32_t)(((half_n + 63) / 64) * 64 * k2BK * 2) : (uint32_t)(half_n * k2BK * 2);
-      const uint32_t tx_pair = 2u * (k2ABytes + b_bytes);
+      const uint32_t tx_pair = kXf ? 2u * b_bytes : 2u * (k2ABytes + b_bytes);
       int stage = 0;
       uint32_t phase = 0;
       for (int t = pair; t < total_items; t += num_pairs) {
@@ -183,7 +206,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
           const uint32_t fb = mapa_shared(full_bar(stage), 0);
           if (rank == 0) mbar_expect_tx(full_bar(stage), tx_pair);
           const int k0 = kb * k2BK;
-          if (!kAT) {
+          if (kXf) {
+            // the A tile is rewritten by this CTA's transform warps first: it completes on a LOCAL barrier
+            mbar_expect_tx(afull_bar(stage), k2ABytes);
+            tma_load_2d(sa, &tmapA, afull_bar(stage), k0, m0);
+          } else if (!kAT) {
             tma_load_2d_cg2(sa, &tmapA, fb, k0, m0);                 // box {64 k, 128 m}
           } else {
             tma_load_2d_cg2(sa, &tmapA, fb, m0, k0);                 // box {64 m, 64 k} x 2
@@ -236,12 +263,58 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         if (acc == 0) acc_phase ^= 1;
       }
     }
+  } else if (kXf != 0 && warp < kEpiWarp0) {
+    // ================= A-operand transform (both CTAs): Z tile -> sin(xa * z + xc), in place =================
+    // The A stage is 128 rows of 128 bytes (64 bf16), SWIZZLE_128B: 16-byte chunk j of row r sits at chunk j ^ (r & 7).
+    // Thread tt owns chunk j = tt & 7 of rows r0 + 16 i (r0 = tt >> 3): its 8 K-columns - and their xa / xc - stay the same
+    // for all 8 rows, and the 32 lanes of a warp cover 4 whole rows per access (conflict-free 16-byte accesses).
+    const int tt = threadIdx.x - 64;
+    const int j = tt & 7, r0 = tt >> 3;
+    const uint32_t toff = (uint32_t)r0 * 128u + (uint32_t)((j ^ (r0 & 7)) << 4);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = pair; t < total_items; t += num_pairs) {
+      int tm, tn, ks;
+      decode(t, tm, tn, ks);
+      const int kb0 = ks * p.kb_per_split;
+      const int kb1 = min(kb0 + p.kb_per_split, num_kb_total);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        const float4* xa4 = reinterpret_cast<const float4*>(xf_smem + kb * k2BK + 8 * j);
+        const float4* xc4 = reinterpret_cast<const float4*>(xf_smem + k2MaxXfK + kb * k2BK + 8 * j);
+        const float4 a_lo = xa4[0], a_hi = xa4[1], c_lo = xc4[0], c_hi = xc4[1];
+        const float xa[8] = {a_lo.x, a_lo.y, a_lo.z, a_lo.w, a_hi.x, a_hi.y, a_hi.z, a_hi.w};
+        const float xc[8] = {c_lo.x, c_lo.y, c_lo.z, c_lo.w, c_hi.x, c_hi.y, c_hi.z, c_hi.w};
+        mbar_wait(afull_bar(stage), phase);
+        const uint32_t sa = smem_base + stage * k2StageBytes + toff;
+        uint32_t w[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(w[i][0]), "=r"(w[i][1]), "=r"(w[i][2]), "=r"(w[i][3])
+                       : "r"(sa + (uint32_t)i * 2048u));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float z0 = __uint_as_float(w[i][e] << 16), z1 = __uint_as_float(w[i][e] & 0xFFFF0000u);
+            w[i][e] = pack_bf16x2(__sinf(fmaf(xa[2 * e], z0, xc[2 * e])), __sinf(fmaf(xa[2 * e + 1], z1, xc[2 * e + 1])));
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa + (uint32_t)i * 2048u), "r"(w[i][0]), "r"(w[i][1]),
+                       "r"(w[i][2]), "r"(w[i][3])
+                       : "memory");
+        }
+        fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core's (async proxy) reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_shared(full_bar(stage), 0));
+        if (++stage == k2Stages) { stage = 0; phase ^= 1; }
+      }
+    }
   } else {
     // ================= epilogue =================
     const int q = warp & 3;                 // TMEM lane quarter of this warp
     const uint32_t tempty_leader0 = mapa_shared(tempty_bar(0), 0);
     const uint32_t tempty_leader1 = mapa_shared(tempty_bar(1), 0);
-    const int ew = warp - 2;                // epilogue warp index
+    const int ew = warp - kEpiWarp0;        // epilogue warp index
     const int eh = ew >> 2;                 // which half of the tile's chunks (kEpiWarps == 8), else 0
     const uint32_t cbuf = cstage_base + (uint32_t)ew * k2CWarpBytes;
     const uint32_t xbuf = xstage_base + (uint32_t)(ew & 3) * k2CWarpBytes;     // kEpi 1: Y tiles out
@@ -554,7 +627,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
           }
         }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-      const int te = threadIdx.x - 64;
+      const int te = threadIdx.x - 32 * kEpiWarp0;
       const int ncols = p.N < k2MaxStatN ? p.N : k2MaxStatN;
       for (int i = te; i < ncols; i += 32 * kEpiWarps) {
         const float s = stat_smem[i], ss = stat_smem[k2MaxStatN + i];
@@ -583,8 +656,10 @@ using namespace snb;
 int snb_gemm_bf16_tc2(const void* A, int lda, int a_t, const void* B, int ldb, int b_t, void* C, int ldc,
                       const float* bias, float alpha, int accumulate, long long M, int N, int K, int out_dtype,
                       float* stats, cudaStream_t st, int epi, const void* X, int ldx, const float* ea, const float* ec,
-                      const float* emean, const float* einvstd) {
+                      const float* emean, const float* einvstd, const float* xa, const float* xc) {
   if (M < 256 || N < 128) return SNB_ERR_UNSUPPORTED;
+  const bool xf = xa != nullptr;
+  if (xf && (a_t || b_t || !xc || K > k2MaxXfK || accumulate != 0 || epi != 0 || !stats)) return SNB_ERR_UNSUPPORTED;
   if (stats && (N > 512 || accumulate != 0 || out_dtype != SNB_BF16)) return SNB_ERR_UNSUPPORTED;
   if (epi) {
     if (accumulate != 0 || out_dtype != SNB_BF16 || (N % 64) != 0 || N > 512 || !X || (ldx % 8) != 0 || (((uintptr_t)X) & 15) != 0)
@@ -615,6 +690,7 @@ int snb_gemm_bf16_tc2(const void* A, int lda, int a_t, const void* B, int ldb, i
   p.C = C, p.ldc = ldc, p.out_bf16 = out_dtype == SNB_BF16, p.mode = accumulate, p.bias = bias, p.alpha = alpha;
   p.stats = stats;
   p.ea = ea, p.ec = ec, p.emean = emean, p.einvstd = einvstd;
+  p.xa = xa, p.xc = xc;
   p.X = reinterpret_cast<const __nv_bfloat16*>(X), p.ldx = ldx;
   p.tma_store = (out_dtype == SNB_BF16 && accumulate <= 1 && (ldc % 8) == 0 && (((uintptr_t)C) & 15) == 0) ? 1 : 0;
   if ((stats || epi) && !p.tma_store) return SNB_ERR_UNSUPPORTED;
@@ -642,18 +718,20 @@ int snb_gemm_bf16_tc2(const void* A, int lda, int a_t, const void* B, int ldb, i
   }
   const int total = p.tiles_m * p.tiles_n * p.splits;
   const int grid = 2 * (total < num_pairs ? total : num_pairs);
-#define SNB_LAUNCH_GEMM2(AT, BT, EPI)                                                                        \
+#define SNB_LAUNCH_GEMM2X(AT, BT, EPI, XF)                                                                   \
   do {                                                                                                       \
     static bool attr_set = false;                                                                            \
     if (!attr_set) {                                                                                         \
-      cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel<AT, BT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                           k2_smem(EPI));                                                    \
+      cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel<AT, BT, EPI, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           k2_smem(EPI, XF));                                                \
       if (e != cudaSuccess) return (int)e;                                                                   \
       attr_set = true;                                                                                       \
     }                                                                                                        \
-    gemm2_bf16_kernel<AT, BT, EPI><<<grid, k2_threads(EPI), k2_smem(EPI), st>>>(ta, tb, tcm, tx, p);         \
+    gemm2_bf16_kernel<AT, BT, EPI, XF><<<grid, k2_threads(EPI, XF), k2_smem(EPI, XF), st>>>(ta, tb, tcm, tx, p); \
   } while (0)
-  if (epi == 1) SNB_LAUNCH_GEMM2(false, false, 1);
+#define SNB_LAUNCH_GEMM2(AT, BT, EPI) SNB_LAUNCH_GEMM2X(AT, BT, EPI, 0)
+  if (xf) SNB_LAUNCH_GEMM2X(false, false, 3, 1);          // forward + BatchNorm statistics, A = sin(xa * Z_prev + xc)
+  else if (epi == 1) SNB_LAUNCH_GEMM2(false, false, 1);
   else if (epi == 2) SNB_LAUNCH_GEMM2(false, true, 2);
   else if (!a_t && !b_t && stats) SNB_LAUNCH_GEMM2(false, false, 3);      // forward + BatchNorm statistics: 8 epilogue warps
   else if (!a_t && !b_t) SNB_LAUNCH_GEMM2(false, false, 0);
@@ -661,6 +739,7 @@ int snb_gemm_bf16_tc2(const void* A, int lda, int a_t, const void* B, int ldb, i
   else if (a_t && !b_t) SNB_LAUNCH_GEMM2(true, false, 0);
   else SNB_LAUNCH_GEMM2(true, true, 0);
 #undef SNB_LAUNCH_GEMM2
+#undef SNB_LAUNCH_GEMM2X
   count_launch();
   SNB_LAUNCH_CHECK();
   return SNB_OK;

@@ -28,6 +28,11 @@ FUSE_EPILOGUES = _os.environ.get("SNB_FUSE_EPILOGUES", "1") != "0"
 # and an activation pass that share the SMs finish in 290 us instead of 303 us back to back - both stream 403 MB matrices
 # and the step is HBM-bound - and the whole step gains 0.6 %.  Off by default (SNB_OVERLAP=1 enables).
 OVERLAP = _os.environ.get("SNB_OVERLAP", "0") == "1"
+# Consumer-side activation: a train-mode BatchNorm layer whose output feeds exactly one full-width BatchNorm layer (and whose
+# activated output nobody else needs - the no-grad trunk of the solar pass) skips its sin pass; the NEXT layer's GEMM applies
+# sin(a*z + c) to the operand tile in shared memory (ops.gemm_stats_xf).  SNB_XFORM=0 keeps the stand-alone pass (A/B tests).
+XFORM = _os.environ.get("SNB_XFORM", "1") != "0"
+XFORM_GRAD = _os.environ.get("SNB_XFORM_GRAD", "1") != "0"        # also in passes with a backward (activated operand written back)
 _side_streams = {}
 _consts = {}
 _capture_epoch = [0]        # bumped by train.TrainStep before every CUDA-graph capture (see _Pass._wc)
@@ -536,9 +541,11 @@ class _Pass:
         if "time_layer_1" in names:
             tenc = self._buf("tenc", N, 16)
             ops.pe_encode(time[:, 0:2].float().contiguous(), 2, tenc, pad_to=16)
-        for sp in self.specs:
+        pending = {}        # buffer name -> (Z, a, c): the producer's activation is applied by its consumer (XFORM)
+        for si, sp in enumerate(self.specs):
             rows = N if sp.out in _RAY_BUFS else M
-            Xv = self.bufs[sp.inp][:, sp.in_col0:sp.in_col0 + sp.kp]
+            pend = pending.pop(sp.inp, None)
+            Xv = None if pend is not None else self.bufs[sp.inp][:, sp.in_col0:sp.in_col0 + sp.kp]
             Wc, b = self._wc(sp)
             n_out = sp.n_out
             if sp.kind == "linear":
@@ -549,8 +556,22 @@ class _Pass:
                 continue
             Z = t.empty(rows, n_out, device=dev, dtype=self.dt)
             st = None
-            if training and sp.layer.has_bn:          # batch statistics fused into the GEMM epilogue (CTA-pair kernel)
+            if pend is not None:                      # A = sin(a_prev * Z_prev + c_prev), formed in shared memory
+                st = ops.gemm_stats_xf(pend[0], pend[1], pend[2], Wc, Z, bias=b, alpha=OMEGA_0, stats=self._stats_slot(n_out),
+                                       Y=pend[3])    # Y: the activated operand, written back only if a backward pass needs it
+                if st is None:                        # shape not taken by the CTA-pair kernels: materialise the activation
+                    Xv = self._buf(sp.inp, rows, pend[0].shape[1])
+                    ops.sine_fwd(pend[0], pend[1], pend[2], Xv)
+            if st is None and training and sp.layer.has_bn:          # batch statistics fused into the GEMM epilogue (CTA-pair kernel)
                 st = ops.gemm_stats(Xv, Wc, Z, bias=b, alpha=OMEGA_0, stats=self._stats_slot(n_out))
+            if self._defer_activation(si, sp, rows, training, keep, st):
+                a, c, mean, invstd = self._affine(sp.layer, Z, rows, training, st)
+                nx = [s_ for s_ in self.specs[si + 1:] if s_.inp == sp.out][0]
+                Ybuf = self._buf(sp.out, rows, n_out) if (keep and nx.grad) else None     # operand of nx's weight gradient
+                pending[sp.out] = (Z, a, c, Ybuf)
+                if keep and sp.grad:
+                    self.saved[sp.name] = (Wc, Z, a, c, mean, invstd)
+                continue
             if sp.out in ("cat5", "cats1"):
                 Y = self.bufs[sp.out][:, sp.out_col0:sp.out_col0 + n_out]
             else:
@@ -578,6 +599,25 @@ class _Pass:
         if not keep:
             self.bufs = {k: v for k, v in self.bufs.items() if k in ("pos", "vis", "adj", "sky", "cls", "y")}
         return res
+
+    def _defer_activation(self, si, sp, rows, training, keep, st):
+        """True if layer `sp`'s sin(BatchNorm(.)) can be left to its consumer's GEMM (ops.gemm_stats_xf): train-mode BatchNorm
+        with fused statistics, bf16, and exactly one consumer - a full-width train-mode BatchNorm layer reading the whole
+        buffer (no concatenation, not a network output).  If a backward pass follows, the consumer's kernel writes the
+        activated operand back (it is the B operand of the consumer's weight gradient): the resident-A kernel's shapes only."""
+        if not (XFORM and training and st is not None and sp.layer.has_bn and self.dt == t.bfloat16 and rows >= 256):
+            return False
+        if sp.out in ("cat5", "cats1") or sp.out in (self.outs or ()) or _sync_world(self.net) > 1:
+            return False
+        users = [s_ for s_ in self.specs[si + 1:] if s_.inp == sp.out]
+        if len(users) != 1:
+            return False
+        nx = users[0]
+        if not (nx.kind == "sine" and nx.layer.has_bn and nx.in_col0 == 0 and nx.kp == sp.n_out and nx.n_out >= 128 and nx.kp <= 1024):
+            return False
+        if keep and nx.grad:       # Y must be written back: gemm_tc3.cu (N = 256 / 512, K <= 512 in steps of 64)
+            return nx.n_out in (256, 512) and nx.kp <= 512 and nx.kp % 64 == 0 and XFORM_GRAD
+        return True
 
     def _affine(self, layer, Z, rows, training, stats=None):
         """fold BatchNorm1d(momentum=.01, eps=1e-5) into y = a*z + c  (misc.py:169-170)."""

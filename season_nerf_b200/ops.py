@@ -474,6 +474,37 @@ def gemm_stats(A, B, out, bias=None, alpha=1.0, stats=None):
     return s[0], s[1]
 
 
+def gemm_stats_xf(Zprev, xa, xc, B, out, bias=None, alpha=1.0, stats=None, Y=None):
+    """gemm_stats with A = sin(xa * Zprev + xc) formed in shared memory (consumer-side activation of the previous SIREN
+    layer: no activation pass, the activated matrix is not read from HBM); Y [M,K] bf16 (optional) receives the activated
+    operand for a later weight gradient.  -> (sum[N], sumsq[N]) or None when the shape is not taken."""
+    Zprev, lda = _mat(Zprev, "Zprev")
+    B, ldb = _mat(B, "B")
+    out, ldc = _mat(out, "out")
+    M, N = out.shape
+    K = Zprev.shape[1]
+    if Zprev.dtype != torch.bfloat16 or B.dtype != torch.bfloat16 or out.dtype != torch.bfloat16:
+        return None
+    if B.shape[1] != K or Zprev.shape[0] != M or B.shape[0] != N or xa.shape[0] != K or xc.shape[0] != K:
+        raise ValueError("gemm_stats_xf shape mismatch: Zprev%s B%s out%s xa%s" % (tuple(Zprev.shape), tuple(B.shape), tuple(out.shape), tuple(xa.shape)))
+    xa = _cuda(xa, torch.float32, "xa").contiguous()
+    xc = _cuda(xc, torch.float32, "xc").contiguous()
+    if bias is not None:
+        _cuda(bias, torch.float32, "bias")
+    s = stats if stats is not None else torch.zeros(2, N, device=out.device, dtype=torch.float32)
+    ldy = 0
+    if Y is not None:
+        Y, ldy = _mat(Y, "Y")
+        if Y.dtype != torch.bfloat16 or tuple(Y.shape) != (M, K):
+            raise ValueError("gemm_stats_xf: Y must be bf16 [M,K]")
+    rc = _lib.load().snb_gemm_stats_xf(_ptr(Zprev), lda, _ptr(xa), _ptr(xc), _ptr(B), ldb, _ptr(out), ldc, _ptr(bias), float(alpha),
+                                       M, N, K, _ptr(s), _ptr(Y), ldy, _stream())
+    if rc == -2:
+        return None
+    check(rc)
+    return s[0], s[1]
+
+
 def gemm_sine_fwd(A, B, Z, Y, bias=None, alpha=1.0):
     """Z = alpha*(A.B^T + bias), Y = sin(Z) in ONE kernel (SIREN layer without BatchNorm, bf16).  -> False when the
     CTA-pair kernel does not take the shape (caller: gemm + sine_fwd)."""
