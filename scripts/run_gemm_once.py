@@ -18,7 +18,7 @@ G = t.empty(M, N, device="cuda", dtype=t.bfloat16)
 dW = t.zeros(N, K, device="cuda", dtype=t.float32)
 ones, zeros = t.ones(N, device="cuda"), t.zeros(N, device="cuda")
 for rep in range(int(sys.argv[1]) if len(sys.argv) > 1 else 2):
-    ev = [t.cuda.Event(enable_timing=True) for _ in range(5)]
+    ev = [t.cuda.Event(enable_timing=True) for _ in range(7)]
     ev[0].record()
     ops.gemm_stats(X, W, Z, bias=b, alpha=30.0)
     ev[1].record()
@@ -28,8 +28,13 @@ for rep in range(int(sys.argv[1]) if len(sys.argv) > 1 else 2):
     ev[3].record()
     ops.gemm(G, X, dW, alpha=30.0, accumulate=2, a_t=True, b_t=True)
     ev[4].record()
+    ops.gemm_stats_xf(X, ones, zeros, W, Z, bias=b, alpha=30.0)                 # consumer-side activation, resident A (gemm_tc3.cu)
+    ev[5].record()
+    ops.gemm_stats_xf(X, ones, zeros, W, Z, bias=b, alpha=30.0, Y=Y)            # + activated operand written back
+    ev[6].record()
     t.cuda.synchronize()
-    ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(4)]
+    ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(6)]
     fl = 2.0 * M * N * K / 1e9
-    print("fwd+stats %.3f ms (%.0f TF)  fwd+sin %.3f ms (%.0f TF)  dgrad+cos+sums %.3f ms (%.0f TF)  wgrad %.3f ms (%.0f TF)"
-          % (ms[0], fl / ms[0], ms[1], fl / ms[1], ms[2], fl / ms[2], ms[3], fl / ms[3]))
+    print("fwd+stats %.3f ms (%.0f TF)  fwd+sin %.3f ms (%.0f TF)  dgrad+cos+sums %.3f ms (%.0f TF)  wgrad %.3f ms (%.0f TF)  "
+          "xf fwd+stats %.3f ms (%.0f TF)  xf+storeY %.3f ms (%.0f TF)"
+          % (ms[0], fl / ms[0], ms[1], fl / ms[1], ms[2], fl / ms[2], ms[3], fl / ms[3], ms[4], fl / ms[4], ms[5], fl / ms[5]))
