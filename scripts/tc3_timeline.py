@@ -29,7 +29,6 @@ for it in range(6):
     print("tile %d" % it)
     print("  A slot free / load issued :", [rel(700 + it * 8 + kb) for kb in range(8)])
     print("  transform: A landed       :", [rel(400 + (it * 8 + kb) * 2) for kb in range(8)])
-    print("  transform: math+STS done  :", [rel(800 + it * 8 + kb) for kb in range(8)])
     print("  transform: slot done      :", [rel(400 + (it * 8 + kb) * 2 + 1) for kb in range(8)])
     for tn in range(2):
         base = (it * 2 + tn) * 8

@@ -9,24 +9,33 @@
 //
 // Layout of the work (CTA pair = cluster of 2, tcgen05.mma.cta_group::2, 256 x 256 output tiles like gemm_tc2.cu):
 //   * A is RESIDENT: the 128 x K operand block of a CTA (K <= 512: 8 slots of 128 x 64 bf16, 128 KB) lands once per 256-row
-//     tile, is rewritten in place by four TRANSFORM warps (sin.approx on the MUFU pipe) and then feeds BOTH 256-column passes
+//     tile, is rewritten in place by eight TRANSFORM warps (sin.approx on the MUFU pipe) and then feeds BOTH 256-column passes
 //     of the tile - every element is activated exactly once, so the MUFU pipe runs at ~50 % of the tensor time instead
 //     of 100 % (transforming a streamed A stage once per N tile made the kernel MUFU bound: 320 us vs 204 us, gemm_tc2.cu kXf).
+//     Eight warps = two per scheduler: with four, the in-kernel timeline (scripts/tc3_timeline.py) showed the MMA warp
+//     waiting on `aready` while each transform warp spent 1.7 k clocks per slot at an issue rate of 0.16.
 //   * B (the weight, L2 resident) streams through a 3-stage ring, 128 rows x 64 k per CTA and stage.
 //   * two TMEM accumulator stages (2 x 256 columns): pass 0 / pass 1 of a tile, so the epilogue of one pass overlaps the
 //     MMAs of the next; slot kb of the NEXT tile is loaded and transformed as soon as pass 1 has consumed it.
 //   * store_y: the transform warps also write the activated slot to HBM (TMA store) - the image pass keeps Y for the
 //     weight gradient of this layer; the no-grad solar pass does not.
 //
-// Warps (512 threads, setmaxnreg moves registers from the data-movement warps to the epilogue):
-//   0 A producer | 1 MMA issuer (leader CTA) | 2 B producer | 3 idle | 4..7 transform | 8..15 epilogue
+// Warps (640 threads, setmaxnreg moves registers from the data-movement warps to the epilogue):
+//   0 A producer | 1 MMA issuer (leader CTA) | 2 B producer | 3 idle | 4..11 transform | 12..19 epilogue
+//
+// Measured and NOT kept (r02, profiles/r02_tc3_experiments/): a fourth B stage paid for by 4 epilogue warps (-4 %: the
+// epilogue then outlasts a pass); an L2 prefetch of the next tile's operand, per slot or whole (0 / -10 % with the Y
+// store); B multicast over a 4-CTA cluster (correct, -8 %: the limit is per SM - the tile period does not change when only
+// 36 of the 148 SMs run); feeding A through registers (ld.global two slots ahead, st.shared; -8 %).  The timeline says why:
+// per tile 8.2 k clocks of MMA take 14.5 k; the slots of the next tile can only be requested as the last pass drains them,
+// they arrive one per ~1.4 k clocks (the SM ingests ~42 B/clk through TMA, shared with the B stream of that pass), and with
+// 20 resident warps the transform, the epilogue and the MMA issue loop also compete for issue slots.
 // Barriers per CTA (leader = cluster rank 0):
 //   afull[kb]   each CTA   A slot landed (own TMA bytes)
-//   aready[kb]  leader     8 arrivals = transform warps of both CTAs (operand rewritten, fenced for the async proxy)
+//   aready[kb]  leader     16 arrivals = transform warps of both CTAs (operand rewritten, fenced for the async proxy)
 //   aempty[kb]  each CTA   slot consumed by the last pass (commit multicast) [+ 1 arrival: Y store has read it]
 //   bfull[s]    leader     B bytes of both CTAs;   bempty[s] each CTA (commit multicast)
 //   tfull[a]    each CTA   accumulator complete;   tempty[a] leader, 16 arrivals = 8 epilogue warps x 2 CTAs
-#include <cstdio>
 #include <cstdlib>
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -40,23 +49,23 @@ int make_tmap_bf16(CUtensorMap* m, const void* ptr, long long rows, long long co
 constexpr int k3BM = 128;
 constexpr int k3BK = 64;
 constexpr int k3MaxKB = 8;                         // K <= 512
+constexpr int k3BStages = 3;
+constexpr int k3EpiWarps = 8;
+constexpr int k3XfWarps = 8;
+constexpr int k3Threads = 32 * (4 + k3XfWarps + k3EpiWarps);          // 640
 constexpr uint32_t k3SlotBytes = k3BM * k3BK * 2;                      // 16 KB
 constexpr uint32_t k3ABytes = k3MaxKB * k3SlotBytes;                   // 128 KB
+constexpr uint32_t k3BBytes = k3BStages * k3SlotBytes;                 // 48 KB
 constexpr uint32_t k3CWarpBytes = 32 * 128;                            // one 32-row x 128-byte staging buffer per epilogue warp
+constexpr uint32_t k3CBytes = k3EpiWarps * k3CWarpBytes;               // 32 KB
 constexpr int k3MaxStatN = 512;
 constexpr uint32_t k3StatBytes = 2 * k3MaxStatN * 4;                   // 4 KB
 constexpr int k3MaxXfK = k3MaxKB * k3BK;                               // 512
 constexpr uint32_t k3XfBytes = 2 * k3MaxXfK * 4;                       // 4 KB
 constexpr uint32_t k3BiasBytes = k3MaxStatN * 4;                       // 2 KB
 constexpr uint32_t k3BarBytes = 512;
-// kEW epilogue warps (4: one warp per TMEM lane quarter drains all 256 columns of a pass; 8: two warps per quarter, 128
-// columns each) and kBS stages of the B ring: the staging buffers of 4 fewer epilogue warps pay for one more B stage
-__host__ __device__ constexpr int k3_threads(int kEW, int kXW) { return 32 * (4 + kXW + kEW); }
-__host__ __device__ constexpr uint32_t k3_bbytes(int kBS) { return (uint32_t)kBS * k3SlotBytes; }
-__host__ __device__ constexpr uint32_t k3_cbytes(int kEW) { return (uint32_t)kEW * k3CWarpBytes; }
-__host__ __device__ constexpr uint32_t k3_smem(int kEW, int kBS) {
-  return 1024 + k3ABytes + k3_bbytes(kBS) + k3_cbytes(kEW) + k3StatBytes + k3XfBytes + k3BiasBytes + k3BarBytes;
-}
+constexpr uint32_t k3Smem = 1024 + k3ABytes + k3BBytes + k3CBytes + k3StatBytes + k3XfBytes + k3BiasBytes + k3BarBytes;
+static_assert(k3Smem <= 232448, "shared memory budget");
 
 struct Gemm3Params {
   long long M;
@@ -68,14 +77,12 @@ struct Gemm3Params {
   const float* xa;           // [K]
   const float* xc;           // [K]
   int store_y;
-  int dbg_flags;             // timing experiments only (wrong results): 1 = no sin, 2 = no proxy fence
-  int prefetch;              // pull the whole operand block of the next tile into L2 when a tile starts
   long long* dbg;            // timeline of CTA 0 (SNB_TC3_TIMELINE, scripts/tc3_timeline.py); nullptr in production
 };
 
 // clock stamps of the first kDbgTiles tiles of CTA 0: MMA thread [((it*2+tn)*8+kb)*3 + {aready, bfull, issued}], accumulator
-// free 300 + it*2+tn, transform thread 0 [400 + (it*8+kb)*2 + {afull, done}], epilogue warp 0 [600 + (it*2+tn)*2 + {tfull,
-// done}], A producer 700 + it*8+kb (slot free, load issued)
+// free 300 + it*2+tn, transform thread 0 [400 + (it*8+kb)*2 + {A landed, slot done}], epilogue warp 0 [600 + (it*2+tn)*2 +
+// {tfull, done}], A producer 700 + it*8+kb (slot free, load issued)
 constexpr int kDbgTiles = 6;
 #define SNB_TL(cond, idx)                                                      \
   do {                                                                         \
@@ -85,18 +92,9 @@ constexpr int kDbgTiles = 6;
 template <int kRegs> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 template <int kRegs> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 
-template <int kEW, int kBS, bool kMC, int kXW>
-__global__ void __cluster_dims__(kMC ? 4 : 2, 1, 1) __launch_bounds__(k3_threads(kEW, kXW), 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k3Threads, 1)
 gemm3_xf_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                 const __grid_constant__ CUtensorMap tmapC, const __grid_constant__ CUtensorMap tmapY, const Gemm3Params p) {
-  constexpr int k3BStages = kBS;
-  constexpr int k3EpiWarps = kEW;
-  constexpr int k3XfWarps = kXW;
-  constexpr int k3Threads = k3_threads(kEW, kXW);
-  constexpr uint32_t k3BBytes = k3_bbytes(kBS);
-  constexpr uint32_t k3CBytes = k3_cbytes(kEW);
-  static_assert(k3_smem(kEW, kBS) <= 232448, "shared memory budget");
-  static_assert(8 * (3 * k3MaxKB + 2 * kBS + 5) <= k3BarBytes, "barrier area");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -120,18 +118,9 @@ gemm3_xf_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // kMC: cluster of FOUR CTAs = two CTA pairs working on adjacent 256-row tiles in lock step; every B (weight) stage is
-  // loaded once per cluster - each CTA fetches a quarter and multicasts it to its counterpart in the other pair - so the
-  // L2 -> SM traffic of B halves (the kernel sits on the ~6.5 KB/clk full-chip L2 output limit, not on HBM or the tensor pipe)
-  constexpr int kCL = kMC ? 4 : 2;
   const uint32_t rank = cluster_ctarank();
-  const uint32_t pr = rank & 1u;            // role inside the CTA pair (0 = leader: MMA issuer, barriers of the pair)
-  const uint32_t pp = rank >> 1;            // pair inside the cluster
-  const uint32_t lead = rank & ~1u;         // cluster rank of this pair's leader
-  const int unit = blockIdx.x / kCL;
-  const int num_units = gridDim.x / kCL;
-  const int units_total = kMC ? (p.tiles_m + 1) / 2 : p.tiles_m;      // odd tile count: the last tile of pair 1 is a phantom
-  auto tile_of = [&](int u) { return kMC ? 2 * u + (int)pp : u; };    // (all loads out of range = zeros, nothing stored)
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
   const int nkb = p.nkb;
 
   if (threadIdx.x == 0) {
@@ -142,7 +131,7 @@ gemm3_xf_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
     }
     for (int s = 0; s < k3BStages; ++s) {
       mbar_init(bfull(s), 1);
-      mbar_init(bempty(s), kMC ? 2 : 1);      // one commit per CTA pair that reads the stage
+      mbar_init(bempty(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull(a), 1);
@@ -157,7 +146,7 @@ gemm3_xf_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
   for (int i = threadIdx.x; i < 2 * k3MaxStatN; i += k3Threads) stat_smem[i] = 0.f;
   for (int i = threadIdx.x; i < k3MaxStatN; i += k3Threads) bias_smem[i] = (p.bias && i < p.N) ? __ldg(p.bias + i) : 0.f;
   // operand-transform constants as float4 planes: [k-block][plane: xa 0-3, xa 4-7, xc 0-3, xc 4-7][chunk j][4] - the 8 lanes
-  // of a quarter warp (j = 0..7) read 128 contiguous bytes per plane
+  // of a quarter warp (j = 0..7) read 128 contiguous bytes per plane (conflict-free)
   for (int i = threadIdx.x; i < k3MaxXfK; i += k3Threads) {
     const int kb_ = i >> 6, j_ = (i & 63) >> 3, e_ = i & 7;
     const int o = (((kb_ * 4 + (e_ >> 2)) * 8 + j_) << 2) + (e_ & 3);
@@ -177,16 +166,8 @@ gemm3_xf_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
       // ================= A producer (both CTAs): one 128 x K block per tile, slot by slot =================
       if (elect_one()) {
         int it = 0;
-        for (int u = unit; u < units_total; u += num_units, ++it) {
-          const int m0 = tile_of(u) * (2 * k3BM) + (int)pr * k3BM;
-          if (p.prefetch && u + num_units < units_total) {
-            // the resident operand has no second buffer: a slot of the next tile cannot be requested before the MMAs have
-            // drained it.  All 8 slots of that tile are pulled into L2 NOW, back to back - 128 whole rows, one contiguous
-            // DRAM stream instead of 128-byte pieces of the same rows requested 600 clocks apart - so the later loads pay
-            // the L2 latency
-            const int m1 = tile_of(u + num_units) * (2 * k3BM) + (int)pr * k3BM;
-            for (int kb = 0; kb < nkb; ++kb) tma_prefetch_2d(&tmapA, kb * k3BK, m1);
-          }
+        for (int tm = pair; tm < p.tiles_m; tm += num_pairs, ++it) {
+          const int m0 = tm * (2 * k3BM) + (int)rank * k3BM;
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(aempty(kb), (uint32_t)((it & 1) ^ 1));
             SNB_TL(it < kDbgTiles, 700 + it * 8 + kb);
@@ -200,18 +181,14 @@ gemm3_xf_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
       if (elect_one()) {
         int stage = 0;
         uint32_t phase = 0;
-        for (int u = unit; u < units_total; u += num_units) {
+        for (int tm = pair; tm < p.tiles_m; tm += num_pairs) {
           for (int tn = 0; tn < p.n_passes; ++tn) {
-            const int n0 = tn * 256 + (int)pr * 128 + (kMC ? (int)pp * 64 : 0);
+            const int n0 = tn * 256 + (int)rank * 128;
             for (int kb = 0; kb < nkb; ++kb) {
-              mbar_wait(bempty(stage), phase ^ 1);         // kMC: free in BOTH destination CTAs (commits of both pairs)
-              const uint32_t fb = mapa_shared(bfull(stage), lead);
-              if (pr == 0) mbar_expect_tx(bfull(stage), 2u * k3SlotBytes);
-              if (kMC)      // 64 of the 128 rows, to the same offset of this CTA and of its counterpart in the other pair
-                tma_load_2d_cg2_mc(b_base + stage * k3SlotBytes + pp * (k3SlotBytes / 2), &tmapB, fb, kb * k3BK, n0,
-                                   (uint16_t)((1u << pr) | (4u << pr)));
-              else
-                tma_load_2d_cg2(b_base + stage * k3SlotBytes, &tmapB, fb, kb * k3BK, n0);
+              mbar_wait(bempty(stage), phase ^ 1);
+              const uint32_t fb = mapa_shared(bfull(stage), 0);
+              if (rank == 0) mbar_expect_tx(bfull(stage), 2u * k3SlotBytes);
+              tma_load_2d_cg2(b_base + stage * k3SlotBytes, &tmapB, fb, kb * k3BK, n0);
               if (++stage == k3BStages) { stage = 0; phase ^= 1; }
             }
           }
@@ -219,13 +196,12 @@ gemm3_xf_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
       }
     } else if (warp == 1) {
       // ================= MMA issuer (leader CTA only) =================
-      if (pr == 0) {
-        const uint16_t pair_mask = (uint16_t)(3u << lead);
+      if (rank == 0) {
         const uint32_t idesc = make_idesc_bf16(2 * k3BM, 256, 0, 0);
         int stage = 0;
         uint32_t phase = 0;
         int item = 0, it = 0;
-        for (int u = unit; u < units_total; u += num_units, ++it) {
+        for (int tm = pair; tm < p.tiles_m; tm += num_pairs, ++it) {
           for (int tn = 0; tn < p.n_passes; ++tn, ++item) {
             const int acc = item & 1;
             const uint32_t acc_phase = (uint32_t)((item >> 1) & 1);
@@ -248,9 +224,9 @@ gemm3_xf_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
                   const uint64_t bdesc = make_smem_desc(sb + k * 32, 16, 1024);
                   umma_f16_cg2(d_tmem, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
                 }
-                umma_commit_cg2_mc(bempty(stage), kMC ? (uint16_t)0xF : pair_mask);
-                if (tn == p.n_passes - 1) umma_commit_cg2_mc(aempty(kb), pair_mask);      // last pass: the slot may be reloaded
-                if (kb == nkb - 1) umma_commit_cg2_mc(tfull(acc), pair_mask);
+                umma_commit_cg2_mc(bempty(stage), 3);
+                if (tn == p.n_passes - 1) umma_commit_cg2_mc(aempty(kb), 3);      // last pass: the slot may be reloaded
+                if (kb == nkb - 1) umma_commit_cg2_mc(tfull(acc), 3);
               }
               __syncwarp();
               SNB_TL(it < kDbgTiles && lane == 0, ((it * 2 + tn) * 8 + kb) * 3 + 2);
@@ -261,21 +237,19 @@ gemm3_xf_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
       }
     }
   } else if (warp < 4 + k3XfWarps) {
-    reg_dec<kXW == 8 ? (kEW == 8 ? 64 : 88) : (kEW == 8 ? 104 : 120)>();
+    reg_dec<64>();
     // ================= A-operand transform (both CTAs): Z slot -> sin(xa * z + xc), in place =================
     // slot = 128 rows of 128 bytes (64 bf16), SWIZZLE_128B: 16-byte chunk j of row r sits at chunk j ^ (r & 7).  Thread tt
-    // owns chunk j = tt & 7 of rows r0 + kRS i (r0 = tt >> 3, kRS = 4 rows per warp x transform warps): its 8 K-columns and
-    // their xa / xc are the same for all its rows; the 32 lanes of a warp cover 4 whole rows per access (conflict-free
-    // 16-byte accesses).  Eight warps = two per scheduler: one warp alone cannot keep the MUFU pipe busy (ncu: 71 % of its
-    // time in the 64-element loop at an issue rate of 0.16, the MMA warp waiting on `aready`).
-    constexpr int kRS = 4 * kXW;          // row stride between a thread's rows
+    // owns chunk j = tt & 7 of rows r0 + 32 i (r0 = tt >> 3, i < 4): its 8 K-columns and their xa / xc are the same for all
+    // its rows; the 32 lanes of a warp cover 4 whole rows per access (conflict-free 16-byte accesses).
+    constexpr int kRS = 4 * k3XfWarps;    // row stride between a thread's rows
     constexpr int kRI = k3BM / kRS;       // rows per thread and slot
     const int tt = threadIdx.x - 128;
     const int j = tt & 7, r0 = tt >> 3;
     const uint32_t toff = (uint32_t)r0 * 128u + (uint32_t)((j ^ (r0 & 7)) << 4);
     int it = 0;
-    for (int u = unit; u < units_total; u += num_units, ++it) {
-      const int m0 = tile_of(u) * (2 * k3BM) + (int)pr * k3BM;
+    for (int tm = pair; tm < p.tiles_m; tm += num_pairs, ++it) {
+      const int m0 = tm * (2 * k3BM) + (int)rank * k3BM;
       for (int kb = 0; kb < nkb; ++kb) {
         const float4* xp = reinterpret_cast<const float4*>(xf_smem) + kb * 32 + j;
         const float4 a_lo = xp[0], a_hi = xp[8], c_lo = xp[16], c_hi = xp[24];
@@ -295,18 +269,16 @@ gemm3_xf_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float z0 = __uint_as_float(w[i][e] << 16), z1 = __uint_as_float(w[i][e] & 0xFFFF0000u);
-            const float f0 = fmaf(xa[2 * e], z0, xc[2 * e]), f1 = fmaf(xa[2 * e + 1], z1, xc[2 * e + 1]);
-            w[i][e] = (p.dbg_flags & 1) ? pack_bf16x2(f0, f1) : pack_bf16x2(__sinf(f0), __sinf(f1));
+            w[i][e] = pack_bf16x2(__sinf(fmaf(xa[2 * e], z0, xc[2 * e])), __sinf(fmaf(xa[2 * e + 1], z1, xc[2 * e + 1])));
           }
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa + (uint32_t)i * (uint32_t)(kRS * 128)), "r"(w[i][0]), "r"(w[i][1]),
                        "r"(w[i][2]), "r"(w[i][3])
                        : "memory");
         }
-        SNB_TL(it < kDbgTiles && tt == 0, 800 + (it * 8 + kb));
-        if (!(p.dbg_flags & 2)) fence_proxy_async_smem();          // generic-proxy writes -> visible to the async proxy (tensor core, TMA store)
+        fence_proxy_async_smem();          // generic-proxy writes -> visible to the async proxy (tensor core, TMA store)
         if (p.store_y) asm volatile("bar.sync 2, %0;" ::"n"(32 * k3XfWarps) : "memory");      // whole slot rewritten
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(mapa_shared(aready(kb), lead));
+        if (lane == 0) mbar_arrive_cluster(mapa_shared(aready(kb), 0));
         SNB_TL(it < kDbgTiles && tt == 0, 400 + (it * 8 + kb) * 2 + 1);
         if (p.store_y && tt == 0) {
           // the activated slot is the next layer's input matrix Y (needed by this layer's weight gradient): 128 x 64 tile
@@ -319,31 +291,28 @@ gemm3_xf_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
     }
     if (p.store_y && tt == 0) bulk_wait_group<0>();
   } else {
-    reg_inc<kEW == 8 ? (kXW == 8 ? 152 : 176) : 232>();
+    reg_inc<152>();
     // ================= epilogue: TMEM -> (alpha, bias) -> bf16 -> swizzled staging -> TMA store; column statistics =========
     const int q = warp & 3;                 // TMEM lane quarter of this warp
-    const uint32_t tempty_leader0 = mapa_shared(tempty(0), lead);
-    const uint32_t tempty_leader1 = mapa_shared(tempty(1), lead);
+    const uint32_t tempty_leader0 = mapa_shared(tempty(0), 0);
+    const uint32_t tempty_leader1 = mapa_shared(tempty(1), 0);
     const int ew = warp - (4 + k3XfWarps);
     const int eh = ew >> 2;                 // which half of the pass's 256 columns
     const uint32_t cbuf = c_base + (uint32_t)ew * k3CWarpBytes;
-    constexpr int kCW = 256 / (kEW / 4);          // columns of a pass drained by one warp
-    constexpr int kNC = kCW / 64;                 // ... in 64-column chunks
-    const int c_begin = eh * kCW;
-    float st_acc[2][kNC][4];       // [pass][64-column chunk][sum c0, sum c1, sumsq c0, sumsq c1]
+    const int c_begin = eh * 128, c_end = c_begin + 128;
+    float st_acc[2][2][4];       // [pass][64-column chunk][sum c0, sum c1, sumsq c0, sumsq c1]
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int jx = 0; jx < kNC; ++jx)
+      for (int jx = 0; jx < 2; ++jx)
 #pragma unroll
         for (int k = 0; k < 4; ++k) st_acc[i][jx][k] = 0.f;
     int item = 0;
-    for (int u = unit; u < units_total; u += num_units) {
-      const int tm = tile_of(u);
+    for (int tm = pair; tm < p.tiles_m; tm += num_pairs) {
       for (int tn = 0; tn < p.n_passes; ++tn, ++item) {
         const int acc = item & 1;
         const uint32_t acc_phase = (uint32_t)((item >> 1) & 1);
-        const long long row0 = (long long)tm * (2 * k3BM) + (long long)pr * k3BM + q * 32;
+        const long long row0 = (long long)tm * (2 * k3BM) + (long long)rank * k3BM + q * 32;
         const int n0 = tn * 256;
         int rows_valid = 0;
         if (row0 < p.M) rows_valid = (int)min((long long)32, p.M - row0);
@@ -352,7 +321,7 @@ gemm3_xf_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
         SNB_TL(item < 2 * kDbgTiles && ew == 0 && lane == 0, 600 + item * 2);
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
 #pragma unroll
-        for (int cc = 0; cc < kNC; ++cc) {
+        for (int cc = 0; cc < 2; ++cc) {
           const int c = c_begin + 64 * cc;
           const float4* b4 = reinterpret_cast<const float4*>(bias_smem + n0 + c);      // broadcast reads
           uint32_t r0v[32], r1v[32];
@@ -431,7 +400,7 @@ gemm3_xf_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
 #pragma unroll
     for (int tnn = 0; tnn < 2; ++tnn)
 #pragma unroll
-      for (int cc = 0; cc < kNC; ++cc) {
+      for (int cc = 0; cc < 2; ++cc) {
         const int col = tnn * 256 + c_begin + 64 * cc + 2 * lane;
         if (tnn < p.n_passes) {
           atomicAdd(stat_smem + col, st_acc[tnn][cc][0]);
@@ -463,36 +432,6 @@ gemm3_xf_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
 
 using namespace snb;
 
-template <int kEW, int kBS, bool kMC, int kXW>
-static int launch3(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm, const CUtensorMap& ty,
-                   const Gemm3Params& p, cudaStream_t st) {
-  constexpr int kCL = kMC ? 4 : 2;
-  static int max_units = 0;       // clusters of kCL CTAs (one CTA per SM) that are resident at the same time
-  if (max_units == 0) {
-    cudaError_t e = cudaFuncSetAttribute(gemm3_xf_kernel<kEW, kBS, kMC, kXW>, cudaFuncAttributeMaxDynamicSharedMemorySize, k3_smem(kEW, kBS));
-    if (e != cudaSuccess) return (int)e;
-    int n = num_sms() / kCL;
-    if (kMC) {      // a GPC whose SM count is not a multiple of 4 leaves SMs without a cluster: ask the driver
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(num_sms() / kCL * kCL), cfg.blockDim = dim3(k3_threads(kEW, kXW)), cfg.dynamicSmemBytes = k3_smem(kEW, kBS);
-      cudaLaunchAttribute at;
-      at.id = cudaLaunchAttributeClusterDimension;
-      at.val.clusterDim.x = kCL, at.val.clusterDim.y = 1, at.val.clusterDim.z = 1;
-      cfg.attrs = &at, cfg.numAttrs = 1;
-      int q = 0;
-      if (cudaOccupancyMaxActiveClusters(&q, gemm3_xf_kernel<kEW, kBS, kMC, kXW>, &cfg) == cudaSuccess && q > 0 && q < n) n = q;
-      else cudaGetLastError();
-      if (getenv("SNB_TC3_VERBOSE")) fprintf(stderr, "gemm3: %d resident clusters of %d CTAs\n", n, kCL);
-    }
-    if (const char* e = getenv("SNB_TC3_MAXUNITS")) n = atoi(e) < n ? atoi(e) : n;      // diagnostics: fewer resident clusters
-    max_units = n;
-  }
-  const int units_total = kMC ? (p.tiles_m + 1) / 2 : p.tiles_m;
-  const int grid = kCL * (units_total < max_units ? units_total : max_units);
-  gemm3_xf_kernel<kEW, kBS, kMC, kXW><<<grid, k3_threads(kEW, kXW), k3_smem(kEW, kBS), st>>>(ta, tb, tcm, ty, p);
-  return 0;
-}
-
 // C = alpha * (sin(xa * Zprev + xc) . B^T + bias) with column statistics; Y (optional) receives the activated operand.
 // SNB_ERR_UNSUPPORTED for shapes outside the resident-A design (the caller falls back to the stand-alone activation pass).
 int snb_gemm_bf16_tc3(const void* Zprev, int lda, const float* xa, const float* xc, const void* B, int ldb, void* C, int ldc,
@@ -510,18 +449,12 @@ int snb_gemm_bf16_tc3(const void* Zprev, int lda, const float* xa, const float* 
   p.n_passes = N / 256;
   p.nkb = K / k3BK;
   p.bias = bias, p.alpha = alpha, p.stats = stats, p.xa = xa, p.xc = xc, p.store_y = Y ? 1 : 0;
-  static const int pf = [] { const char* e = getenv("SNB_TC3_PREFETCH"); return e ? atoi(e) : 1; }();
-  p.prefetch = pf;
-  p.dbg_flags = getenv("SNB_TC3_DBGFLAGS") ? atoi(getenv("SNB_TC3_DBGFLAGS")) : 0;
   const char* tl = getenv("SNB_TC3_TIMELINE");      // device pointer (decimal) of >= 1024 int64: debugging only
   p.dbg = tl ? reinterpret_cast<long long*>(strtoull(tl, nullptr, 10)) : nullptr;
-  // SNB_TC3_VARIANT (A/B measurements): <epilogue warps, B stages, B multicast over a 4-CTA cluster, transform warps>
-  static const int variant = [] { const char* e = getenv("SNB_TC3_VARIANT"); return e ? atoi(e) : 7; }();
-  const bool mc = variant >= 7;
   CUtensorMap ta, tb, tcm, ty;
   int rc = make_tmap_bf16(&ta, Zprev, M, K, lda, k3BK, k3BM);
   if (rc) return rc;
-  rc = make_tmap_bf16(&tb, B, N, K, ldb, k3BK, mc ? 64 : 128);
+  rc = make_tmap_bf16(&tb, B, N, K, ldb, k3BK, 128);
   if (rc) return rc;
   rc = make_tmap_bf16(&tcm, C, M, N, ldc, 64, 32);
   if (rc) return rc;
@@ -531,12 +464,15 @@ int snb_gemm_bf16_tc3(const void* Zprev, int lda, const float* xa, const float* 
   } else {
     ty = ta;
   }
-  int rc2;
-  if (variant == 0) rc2 = launch3<8, 3, false, 4>(ta, tb, tcm, ty, p, st);
-  else if (variant == 4) rc2 = launch3<8, 3, false, 8>(ta, tb, tcm, ty, p, st);
-  else if (variant == 8) rc2 = launch3<4, 4, true, 8>(ta, tb, tcm, ty, p, st);
-  else rc2 = launch3<8, 3, true, 8>(ta, tb, tcm, ty, p, st);
-  if (rc2) return rc2;
+  const int num_pairs = num_sms() / 2;
+  const int grid = 2 * (p.tiles_m < num_pairs ? p.tiles_m : num_pairs);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm3_xf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k3Smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  gemm3_xf_kernel<<<grid, k3Threads, k3Smem, st>>>(ta, tb, tcm, ty, p);
   count_launch();
   SNB_LAUNCH_CHECK();
   return SNB_OK;

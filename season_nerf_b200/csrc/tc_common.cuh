@@ -85,12 +85,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
-// pull one box of a tensor map into L2 (no shared-memory destination, no completion tracking)
-__device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
-               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1)
-               : "memory");
-}
 // 1-D bulk copy global -> shared (weights are pre-tiled in HBM in the exact swizzled shared-memory image)
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -177,16 +171,6 @@ __device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const void* tmap, 
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster), "r"(c0), "r"(c1)
-      : "memory");
-}
-// the same, multicast: the box lands at the same CTA-relative offset in every CTA of `cta_mask`, and each destination's bytes
-// are credited to the barrier at `bar_cluster`'s offset in the even CTA of that destination's pair (peer bit clear)
-__device__ __forceinline__ void tma_load_2d_cg2_mc(uint32_t dst, const void* tmap, uint32_t bar_cluster, int c0, int c1,
-                                                   uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster), "r"(c0), "r"(c1), "h"(cta_mask)
       : "memory");
 }
 __device__ __forceinline__ void bulk_load_cg2(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar_cluster) {
