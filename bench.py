@@ -457,7 +457,7 @@ def run_ours(a):
     flops_step = TRAIN_FLOP_PER_RAY * n
     achieved = flops_step / (gemm_ms * 1e-3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
-    roofline = {"bound": "tensor", "kernel": "gemm2_bf16_kernel (tcgen05 cta_group::2, fused SIREN epilogues)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+    roofline = {"bound": "tensor", "kernel": "gemm2_bf16_kernel + gemm3_xf_kernel (tcgen05 cta_group::2, fused SIREN epilogues / consumer-side activation)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": ncu_traffic("gemm2_trunk_mean"), "traffic_source": os.path.relpath(TRAFFIC_FILE, ROOT), "peak_source": peaks["source"] + " sustained cuBLAS bf16",
                 "launches_per_step": n_gemm, "kernel_ms_per_step": gemm_ms, "step_ms": ms / a.steps,
                 "kernel_share_of_step": gemm_ms / (ms / a.steps),
@@ -468,7 +468,7 @@ def run_ours(a):
     # ncu --set full capture committed as profiles/r01_ncu_gemm2_variants_v4.txt (scripts/profile_gpu.sh step 2)
     if not a.no_trunk:
         roofline["trunk_launches"] = bench_trunk_gemms(min(n, a.micro_batch or n) * S, peak, {k: ncu_traffic("gemm2_" + k) for k in
-                                                                      ("fwd_bn_stats", "fwd_sin", "fwd_xf_bn_stats", "dgrad_cos_bnsums", "wgrad_splitk")})
+                                                                      ("fwd_bn_stats", "fwd_sin", "fwd_xf_bn_stats", "fwd_xf_storeY", "dgrad_cos_bnsums", "wgrad_splitk")})
     roofline["traffic_note"] = "dram bytes per launch, mean over the trunk-shaped launches of a step (ncu --set full); per variant under trunk_launches"
 
     out = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world,
@@ -600,6 +600,7 @@ def bench_trunk_gemms(M, peak, traffic, reps=5):
     fns = {"fwd_bn_stats": lambda: ops.gemm_stats(X, W, Z, bias=b, alpha=30.0),
            "fwd_sin": lambda: ops.gemm_sine_fwd(X, W, Z, Y, bias=b, alpha=30.0),
            "fwd_xf_bn_stats": lambda: ops.gemm_stats_xf(X, ones, zeros, W, Z, bias=b, alpha=30.0),
+           "fwd_xf_storeY": lambda: ops.gemm_stats_xf(X, ones, zeros, W, Z, bias=b, alpha=30.0, Y=Y),
            "dgrad_cos_bnsums": lambda: ops.gemm_sine_bwd(Y, W, G, Z, ones, zeros, zeros, ones, alpha=30.0),
            "wgrad_splitk": lambda: ops.gemm(G, X, dW, alpha=30.0, accumulate=2, a_t=True, b_t=True)}
     out = {}
@@ -621,6 +622,7 @@ def bench_trunk_gemms(M, peak, traffic, reps=5):
     out["fwd_bn_stats"]["algorithmic_bytes"] = 2 * M * N * 2            # read X, write Z
     out["fwd_sin"]["algorithmic_bytes"] = 3 * M * N * 2                 # read X, write Z and Y
     out["fwd_xf_bn_stats"]["algorithmic_bytes"] = 2 * M * N * 2         # read Z_prev (activated in shared memory), write Z
+    out["fwd_xf_storeY"]["algorithmic_bytes"] = 3 * M * N * 2           # ... and write the activated operand (weight gradient)
     out["dgrad_cos_bnsums"]["algorithmic_bytes"] = 3 * M * N * 2        # read dZ and Z, write G
     out["wgrad_splitk"]["algorithmic_bytes"] = 2 * M * N * 2            # read dZ and X
     return out

@@ -14,10 +14,10 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
-VARIANT = {"<0, 0, 3>": "fwd_bn_stats", "<0, 0, 1>": "fwd_sin", "<0, 1, 2>": "dgrad_cos_bnsums", "<1, 1, 0>": "wgrad_splitk",
-           "<0, 0, 4>": "fwd_sinA_bn_stats", "<0, 0, 5>": "fwd_sinA_sin"}
-# trunk-shaped launches of one training step (profiles/r01_launch_shares_v4.txt)
-STEP_COUNTS = {"fwd_bn_stats": 16, "fwd_sin": 15, "dgrad_cos_bnsums": 17, "wgrad_splitk": 15}
+VARIANT = {"<0, 0, 3, 0>": "fwd_bn_stats", "<0, 0, 1, 0>": "fwd_sin", "<0, 1, 2, 0>": "dgrad_cos_bnsums", "<1, 1, 0, 0>": "wgrad_splitk",
+           "<0, 0, 3, 1>": "fwd_xf_streamed_bn_stats"}
+# GEMM launches of one training step by variant (profiles/r02_step_table_v1.txt); fwd_xf_* = resident-A kernel gemm_tc3.cu
+STEP_COUNTS = {"fwd_bn_stats": 4, "fwd_sin": 15, "fwd_xf_bn_stats": 6, "fwd_xf_storeY": 6, "dgrad_cos_bnsums": 17, "wgrad_splitk": 15}
 _UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 
@@ -25,6 +25,8 @@ def key_of(name):
     if "gemm2_bf16_kernel" in name:
         m = re.search(r"<[^>]*>", name)
         return "gemm2_" + VARIANT.get(m.group(0), m.group(0)) if m else None
+    if "gemm3_xf_kernel" in name:
+        return "gemm3"
     if "fused_eval2" in name:
         return "fused_eval2_full"
     if "composite_fwd" in name:
@@ -53,6 +55,8 @@ def main(paths):
                 continue
             rd = float(r[col["dram__bytes_read.sum"]]) * _UNIT[units[col["dram__bytes_read.sum"]]]
             wr = float(r[col["dram__bytes_write.sum"]]) * _UNIT[units[col["dram__bytes_write.sum"]]]
+            if k == "gemm3":      # the same kernel with / without the write-back of the activated operand (trunk shape: 403 MB)
+                k = "gemm2_fwd_xf_storeY" if wr > 1.5 * rd else "gemm2_fwd_xf_bn_stats"
             d[k] = {"dram_bytes": rd + wr, "read": rd, "write": wr, "duration_us": float(r[col["gpu__time_duration.sum"]]) *
                     {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(units[col["gpu__time_duration.sum"]], 1.0),
                     "kernel": r[col["Kernel Name"]][:90], "source": os.path.basename(path)}

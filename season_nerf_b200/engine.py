@@ -19,6 +19,10 @@ from .geometry import world_angle_2_local_vec
 # (ops.heads_composite / ops.solar_loss) instead of ~65 element-wise torch launches and their autograd nodes.
 # SNB_FAST_LOSS=0 keeps the general path (eval / eval_Rho_Only dictionaries) for A/B tests.
 FAST_LOSS = os.environ.get("SNB_FAST_LOSS", "1") != "0"
+# The loss terms that only read the image pass (adaptive colour loss, sky / albedo regularisers: ~200 launches of a few
+# microseconds, forward and again in backward) are enqueued on a side stream while the solar pass - 3 ms of GEMMs that do not
+# depend on them - runs on the main one; inside the captured step graph this is a fork / join.  SNB_LOSS_OVERLAP=0 keeps one stream.
+LOSS_OVERLAP = os.environ.get("SNB_LOSS_OVERLAP", "1") != "0"
 
 
 def _dev(x, device):
@@ -320,6 +324,55 @@ class All_in_One_Eval():
         return R
 
     # ---------------------------------------------------------------------------------------------------
+    def _image_terms(self, out, gt, train_mode):
+        """the terms of get_loss that read the image pass only (Eval_Tools_2.py:370-443), keyed for get_loss's assembly:
+        regularisers Sky_Color_Var / Albedo_Color (:370-390), colour terms (:401-443), `scale` = mean colour-loss scale ** 2"""
+        args = self.args
+        T = {}
+        if args.Use_Solar and args.Solar_Type_2 is False:
+            alb = out["Albedo_Color"]
+            sk_alb, _ = t.min(alb, 0)
+            m = (sk_alb < .2).float()           # branch-free: no host sync (SURVEY 7: .item() stalls)
+            if self.sync_world > 1 and train_mode:
+                # global minimum: only the rank that owns it contributes (the mean over ranks of the gradient
+                # all-reduce then equals the single-batch term  sum_c (1 - min_c/.2)^2 / N_total)
+                m = m * owns_global_min(sk_alb)
+            alb_loss = t.sum(m * (1. - sk_alb / .2) ** 2) / alb.shape[0]
+            # Sky_Col is [N,S,3] in the reference (one colour per ray, repeated over its samples); the fast path keeps
+            # the [N,3] rows: sum / numel is the same mean
+            sk = (out["Sky_Col"] - .5) / .5
+            sk_loss = t.sum(t.relu(sk) ** 2) / float(np.prod(sk.shape))
+            if self.use_prior:
+                sk_loss = sk_loss.detach()
+            T["Sky_Color_Var"], T["Albedo_Color"] = sk_loss, alb_loss
+        merged = "Rendered_Col_Merged" if (self.use_prior and train_mode) else "Rendered_Col"
+        if self.use_MSE_loss is True:
+            T["Color"] = self.MSE_loss(out[merged], gt)
+            if self.use_prior:
+                T["Alpha_Adjust"] = self.MSE_loss(out["PE"], out["PE_Supervised"].detach())
+        else:
+            diff = out["Rendered_Col"] - gt
+            if self.use_prior:
+                a0, a1 = self.ada_loss[0], self.ada_loss[1]
+                adiff = (out["PE"] - out["PE_Supervised"].detach()).reshape([-1, 1])
+                T["Alpha_Adjust_ada"] = t.mean(a1.lossfun(adiff))
+                T["Color_ada"] = t.mean(a0.lossfun(diff))
+                T["Color_alpha"] = t.mean(a0.alpha().detach())
+                T["Color_width"] = t.mean(a0.scale().detach())
+                T["Alpha_Adjust_mse"] = self.MSE_loss(out["PE"], out["PE_Supervised"].detach())
+                T["scale"] = t.mean(a0.scale().detach()) ** 2
+                T["Alpha_alpha"] = t.mean(a1.alpha().detach())
+                T["Alpha_width"] = t.mean(a1.scale().detach())
+            else:
+                a0 = self.ada_loss
+                T["Color_ada"] = t.mean(a0.lossfun(diff))
+                T["Color_alpha"] = t.mean(a0.alpha().detach())
+                T["Color_width"] = t.mean(a0.scale().detach())
+                T["scale"] = t.mean(a0.scale().detach()) ** 2
+            with t.no_grad():
+                T["Color_mse"] = self.MSE_loss(out[merged], gt).detach()
+        return T
+
     def get_loss(self, data_dict, Network, current_step, train_mode, jitter=None, solar=None, solar_jitter=None,
                  ts=None, solar_ts=None):
         """Eval_Tools_2.py:340-459."""
@@ -343,10 +396,20 @@ class All_in_One_Eval():
             fork.record(main)
         fast = (FAST_LOSS and not self.use_prior and not overlap and hasattr(Network, "forward_rays")
                 and ops.heads_composite_usable(args.n_samples, getattr(Network, "n_classes", 99)))
-        sol = sol_fast = None
+        sol = sol_fast = img_terms = None
         try:
             if fast:
                 out = self._eval_fast(data_dict, Network, train_mode, jitter=jitter, ts=ts)
+                if LOSS_OVERLAP and train_mode and args.Use_Solar and n_rays >= 64:
+                    gt = _dev(data_dict["GT_Color"], device)
+                    main_s = t.cuda.current_stream()
+                    side_s = _nw.side_stream(("loss", main_s.cuda_stream))
+                    side_s.wait_stream(main_s)
+                    for v in list(out.values()) + [gt]:
+                        v.record_stream(side_s)
+                    with t.cuda.stream(side_s):
+                        img_terms = self._image_terms(out, gt, train_mode)
+                    join = (main_s, side_s)
             else:
                 out = self.eval(data_dict, Network, current_step, train_mode, jitter=jitter, ts=ts)
             if args.Use_Solar:
@@ -373,6 +436,12 @@ class All_in_One_Eval():
         finally:
             if overlap:
                 Network._bn_order = None
+        if img_terms is not None:        # join: the main stream consumes the side stream's scalars from here on
+            join[0].wait_stream(join[1])
+            for v in img_terms.values():
+                v.record_stream(join[0])
+        gt = _dev(data_dict["GT_Color"], device)
+        img_terms = self._image_terms(out, gt, train_mode) if img_terms is None else img_terms
         if args.Use_Solar:
             if sol_fast is not None:
                 err, absorb = t.mean(sol_fast[0]), t.mean(sol_fast[1])
@@ -382,50 +451,16 @@ class All_in_One_Eval():
             Loss["Solar_Correction"] = [err, weight["Solar_Correction"]]
             Loss["Solar_Correction_2"] = [absorb if args.Solar_Type_2 else absorb.detach(), weight["Solar_Correction"]]
             if args.Solar_Type_2 is False:
-                alb = out["Albedo_Color"]
-                sk_alb, _ = t.min(alb, 0)
-                m = (sk_alb < .2).float()           # branch-free: no host sync (.item() stalls)
-                if self.sync_world > 1 and train_mode:
-                    # global minimum: only the rank that owns it contributes (the mean over ranks of the gradient
-                    # all-reduce then equals the single-batch term  sum_c (1 - min_c/.2)^2 / N_total)
-                    m = m * owns_global_min(sk_alb)
-                alb_loss = t.sum(m * (1. - sk_alb / .2) ** 2) / alb.shape[0]
-                # Sky_Col is [N,S,3] in the reference (one colour per ray, repeated over its samples); the fast path keeps
-                # the [N,3] rows: sum / numel is the same mean
-                sk = (out["Sky_Col"] - .5) / .5
-                sk_loss = t.sum(t.relu(sk) ** 2) / float(np.prod(sk.shape))
-                if self.use_prior:
-                    sk_loss = sk_loss.detach()
-                Loss["Sky_Color_Var"] = [sk_loss, weight["Solar_Correction"]]
-                Loss["Albedo_Color"] = [alb_loss, weight["Solar_Correction"]]
-        gt = _dev(data_dict["GT_Color"], device)
-        merged = "Rendered_Col_Merged" if (self.use_prior and train_mode) else "Rendered_Col"
-        if self.use_MSE_loss is True:
-            Loss["Color"] = [self.MSE_loss(out[merged], gt), weight["Color"]]
-            if self.use_prior:
-                Loss["Alpha_Adjust"] = [self.MSE_loss(out["PE"], out["PE_Supervised"].detach()), weight["Alpha_Adjust"]]
-        else:
-            diff = out["Rendered_Col"] - gt
-            if self.use_prior:
-                a0, a1 = self.ada_loss[0], self.ada_loss[1]
-                adiff = (out["PE"] - out["PE_Supervised"].detach()).reshape([-1, 1])
-                Loss["Alpha_Adjust_ada"] = [t.mean(a1.lossfun(adiff)), weight["Alpha_Adjust"]]
-                Loss["Color_ada"] = [t.mean(a0.lossfun(diff)), weight["Color"]]
-                Loss["Color_alpha"] = [t.mean(a0.alpha().detach()), 1.]
-                Loss["Color_width"] = [t.mean(a0.scale().detach()), 1.]
-                Loss["Alpha_Adjust"] = [self.MSE_loss(out["PE"], out["PE_Supervised"].detach()), weight["Alpha_Adjust"]]
-                scale = t.mean(a0.scale().detach()) ** 2
-                Loss["Alpha_alpha"] = [t.mean(a1.alpha().detach()), 1.]
-                Loss["Alpha_width"] = [t.mean(a1.scale().detach()), 1.]
-            else:
-                a0 = self.ada_loss
-                Loss["Color_ada"] = [t.mean(a0.lossfun(diff)), weight["Color"]]
-                Loss["Color_alpha"] = [t.mean(a0.alpha().detach()), 1.]
-                Loss["Color_width"] = [t.mean(a0.scale().detach()), 1.]
-                scale = t.mean(a0.scale().detach()) ** 2
-            if args.Use_Solar:
-                Loss["Solar_Correction"][1] = Loss["Solar_Correction"][1] / scale
-                Loss["Solar_Correction_2"][1] = Loss["Solar_Correction_2"][1] / scale
-            with t.no_grad():
-                Loss["Color"] = [self.MSE_loss(out[merged], gt).detach(), weight["Color"]]
+                Loss["Sky_Color_Var"] = [img_terms["Sky_Color_Var"], weight["Solar_Correction"]]
+                Loss["Albedo_Color"] = [img_terms["Albedo_Color"], weight["Solar_Correction"]]
+        for k in ("Color", "Alpha_Adjust", "Alpha_Adjust_ada", "Color_ada", "Color_alpha", "Color_width", "Alpha_Adjust_mse",
+                  "Alpha_alpha", "Alpha_width", "Color_mse"):
+            if k in img_terms:
+                name = {"Alpha_Adjust_mse": "Alpha_Adjust", "Color_mse": "Color"}.get(k, k)
+                Loss[name] = [img_terms[k], {"Color": weight["Color"], "Color_ada": weight["Color"], "Color_mse": weight["Color"],
+                                             "Alpha_Adjust": weight["Alpha_Adjust"], "Alpha_Adjust_ada": weight["Alpha_Adjust"],
+                                             "Alpha_Adjust_mse": weight["Alpha_Adjust"]}.get(k, 1.)]
+        if "scale" in img_terms and args.Use_Solar:
+            Loss["Solar_Correction"][1] = Loss["Solar_Correction"][1] / img_terms["scale"]
+            Loss["Solar_Correction_2"][1] = Loss["Solar_Correction_2"][1] / img_terms["scale"]
         return Loss

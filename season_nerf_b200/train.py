@@ -2,12 +2,16 @@
 T_NeRF_Full_2/Net_Tool_2.py:63-129 (T_NeRF_Net_Tool.reset_eval), plus the ONLY parallelism of the build: ray-sharded
 data parallel over the GPUs of one box with one flat NCCL all-reduce of the gradients per step.
 The reference's DataLoader / TensorBoard / checkpoint glue stays out of scope; `step()` takes the batch dict."""
+import os
+
 import torch as t
 import torch.distributed as dist
 
 from .adaptive_loss import AdaptiveLossFunction
 from .engine import All_in_One_Eval, sample_ts
 from .network import T_NeRF
+
+FUSED_ADAM = os.environ.get("SNB_FUSED_ADAM", "1") != "0"
 
 
 def flat_allreduce_mean_(tensors, world_size, flat=None):
@@ -125,7 +129,9 @@ class TrainStep:
         gk = {}
         lr1, lr2 = args.lr, args.lr * args.lr_alpha_scale
         if self.use_graph:       # graph-capturable Adam: step counters and learning rates are device tensors
-            gk = dict(capturable=True)
+            # fused: one multi-tensor kernel per optimiser instead of ~12 foreach launches over the 70 parameter tensors
+            # (0.4 ms of a 15.7 ms step); same fp32 arithmetic as the reference's default Adam (Net_Tool_2.py:110-119)
+            gk = dict(capturable=True, fused=FUSED_ADAM)
             lr1, lr2 = t.tensor(lr1, device=self.device), t.tensor(lr2, device=self.device)
         self.optim = t.optim.Adam(self.params, lr=lr1, **gk)                       # Net_Tool_2.py:110-119
         self.optim2 = t.optim.Adam(ada_params, lr=lr2, **gk) if ada_params else None
