@@ -262,6 +262,10 @@ class TrainStep:
         self.optim.step()
         if self.optim2 is not None:
             self.optim2.step()
+        # torch's fused Adam (torch._fused_adam_) rewrites the parameters WITHOUT bumping their version counters (measured:
+        # scripts/adam_probe.py): every cache derived from them - staged bf16 weights, packed render program - would go stale
+        if self.use_graph and FUSED_ADAM and not t.cuda.is_current_stream_capturing():
+            t.autograd.graph.increment_version(self._versioned)
 
     def _zero_grads(self, to_none):
         self.optim.zero_grad(set_to_none=to_none)
@@ -344,6 +348,7 @@ class TrainStep:
                 self._allreduce_grads()
             if self.capture_optim:
                 st["g_opt"].replay()
+                t.autograd.graph.increment_version(self._versioned)      # the replayed optimiser rewrote the parameters
             else:
                 self._optim_step()
         if self.sched is not None:
