@@ -15,7 +15,7 @@ H = np.eye(4)
 H[0, 0], H[1, 1], H[2, 2] = 2 / 0.0024, 2 / 0.0032, 2 / 70.0
 H[0, 3], H[1, 3], H[2, 3] = -W2C[0] * H[0, 0], -W2C[1] * H[1, 1], -W2C[2] * H[2, 2]
 t.manual_seed(0)
-ts = snb.TrainStep(args, dev, H, W2C, world_size=1, precision="bf16")
+ts = snb.TrainStep(args, dev, H, W2C, world_size=1, precision="bf16", use_graph=os.environ.get("SNB_PROFILE_GRAPH", "0") == "1")
 g = t.Generator().manual_seed(1)
 xy = (t.rand(n, 2, generator=g) * 2 - 1) * 0.8
 dxy = (t.rand(n, 2, generator=g) * 2 - 1) * 0.2
@@ -48,6 +48,8 @@ for e in ev:
     a[0] += 1
     a[1] += e.device_time if hasattr(e, "device_time") else e.cuda_time
 tot = sum(v[1] for v in agg.values())
+span = max(e.time_range.end for e in ev) - min(e.time_range.start for e in ev)
+print("first kernel start -> last kernel end: %.3f ms (kernels on parallel streams overlap; gaps = launch / dependency latency)" % (span / 1e3))
 print("total kernel time %.3f ms in %d launches" % (tot / 1e3, sum(v[0] for v in agg.values())))
 for k, (c, d) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
     print("%9.3f ms %5d %5.1f%%  %s" % (d / 1e3, c, 100 * d / tot, k))

@@ -15,6 +15,14 @@
 //     CTA and flushed with one atomicAdd per column per CTA at the end.
 //   * direct mode (fp32 output, accumulate, split-K atomics): registers -> global, vectorised (red.global.add.v4.f32).
 //
+// Where the time goes (r02, in-kernel timeline scripts/tc2_timeline.py -> profiles/r02_tc2_timeline_*.txt, trunk shape): every
+// variant moves 50-63 bytes per clock through the SM's port to the L2 fabric, reads and writes together (forward + statistics:
+// 256 KB in + 128 KB out per 256 x 256 x 512 item in 6.1 k clocks; sin epilogue: 512 KB in 9.2 k; input gradient: 448 KB in
+// 8.7 k; 4.1 k clocks of MMA each).  A reloaded stage lands 3-5 k clocks after its request whether or not the rows were
+// prefetched into L2 (measured: an L2 prefetch of the next items' A rows made every variant 4-6 % slower) - the requests
+// queue at the port, they do not wait for HBM.  The remaining lever is bytes per item, not latency hiding: the resident-A
+// kernel (gemm_tc3.cu) reads A once for both 256-column halves.
+//
 // Barrier protocol per CTA pair (leader = cluster rank 0):
 //   full[s]   leader only; 1 arrival (leader's expect_tx) + the TMA bytes of BOTH CTAs
 //   empty[s]  each CTA; released by tcgen05.commit multicast from the leader's MMA thread
@@ -91,7 +99,17 @@ struct Gemm2Params {
   // kXf: A[m,k] <- sin(xa[k] * A[m,k] + xc[k]) in shared memory before the MMA
   const float* xa;
   const float* xc;
+  long long* dbg;              // clock stamps of CTA 0 (SNB_TC2_TIMELINE, scripts/tc2_timeline.py); nullptr in production
 };
+
+// timeline of the first kDbg2Items work items of CTA 0: producer [it*8+kb] = stage free / loads issued; MMA thread
+// 200 + it*24 + kb*3 + {0: operands landed, 1: MMAs issued}, 200 + it*24 + 23 = accumulator stage free; epilogue warp 0
+// 600 + it*2 + {0: accumulator complete, 1: epilogue done}
+constexpr int kDbg2Items = 12;
+#define SNB_TL2(cond, idx)                                                      \
+  do {                                                                          \
+    if (p.dbg != nullptr && blockIdx.x == 0 && (cond)) p.dbg[(idx)] = clock64(); \
+  } while (0)
 
 template <bool kAT, bool kBT, int kEpiT, int kXf = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2_threads(kEpiT, kXf), 1)
@@ -192,7 +210,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       const uint32_t tx_pair = kXf ? 2u * b_bytes : 2u * (k2ABytes + b_bytes);
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = pair; t < total_items; t += num_pairs) {
+      int itp = 0;
+      for (int t = pair; t < total_items; t += num_pairs, ++itp) {
         int tm, tn, ks;
         decode(t, tm, tn, ks);
         const int m0 = tm * (2 * k2BM) + (int)rank * k2BM;
@@ -201,6 +220,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         const int kb1 = min(kb0 + p.kb_per_split, num_kb_total);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
+          SNB_TL2(itp < kDbg2Items && kb - kb0 < 8, itp * 8 + (kb - kb0));
           const uint32_t sa = smem_base + stage * k2StageBytes;
           const uint32_t sb = sa + k2ABytes;
           const uint32_t fb = mapa_shared(full_bar(stage), 0);
@@ -233,16 +253,19 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = pair; t < total_items; t += num_pairs) {
+      int itm = 0;
+      for (int t = pair; t < total_items; t += num_pairs, ++itm) {
         int tm, tn, ks;
         decode(t, tm, tn, ks);
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, num_kb_total);
         mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
+        SNB_TL2(itm < kDbg2Items && lane == 0, 200 + itm * 24 + 23);
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * k2MaxBN;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
+          SNB_TL2(itm < kDbg2Items && lane == 0 && kb - kb0 < 7, 200 + itm * 24 + (kb - kb0) * 3);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t sa = smem_base + stage * k2StageBytes;
@@ -257,6 +280,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
             if (kb == kb1 - 1) umma_commit_cg2_mc(tfull_bar(acc), 3);  // accumulator complete -> both epilogues
           }
           __syncwarp();
+          SNB_TL2(itm < kDbg2Items && lane == 0 && kb - kb0 < 7, 200 + itm * 24 + (kb - kb0) * 3 + 1);
           if (++stage == k2Stages) { stage = 0; phase ^= 1; }
         }
         acc ^= 1;
@@ -334,7 +358,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int k = 0; k < 4; ++k) st_acc[i][j][k] = 0.f;
+    int ite = -1;
     for (int t = pair; t < total_items; t += num_pairs) {
+      ++ite;
       int tm, tn, ks;
       decode(t, tm, tn, ks);
       const long long row0 = (long long)tm * (2 * k2BM) + (long long)rank * k2BM + q * 32;
@@ -376,6 +402,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      SNB_TL2(ite < kDbg2Items && ew == 0 && lane == 0, 600 + ite * 2);
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * k2MaxBN;
       if (p.tma_store) {
         for (int c = c_begin; c < c_end; c += 64) {
@@ -608,6 +635,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
+      SNB_TL2(ite < kDbg2Items && ew == 0 && lane == 0, 600 + ite * 2 + 1);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -692,6 +720,8 @@ int snb_gemm_bf16_tc2(const void* A, int lda, int a_t, const void* B, int ldb, i
   p.ea = ea, p.ec = ec, p.emean = emean, p.einvstd = einvstd;
   p.xa = xa, p.xc = xc;
   p.X = reinterpret_cast<const __nv_bfloat16*>(X), p.ldx = ldx;
+  const char* tl = getenv("SNB_TC2_TIMELINE");      // device pointer (decimal) of >= 1024 int64: debugging only
+  p.dbg = tl ? reinterpret_cast<long long*>(strtoull(tl, nullptr, 10)) : nullptr;
   p.tma_store = (out_dtype == SNB_BF16 && accumulate <= 1 && (ldc % 8) == 0 && (((uintptr_t)C) & 15) == 0) ? 1 : 0;
   if ((stats || epi) && !p.tma_store) return SNB_ERR_UNSUPPORTED;
 
