@@ -17,8 +17,10 @@
 //   * B (the weight, L2 resident) streams through a 3-stage ring, 128 rows x 64 k per CTA and stage.
 //   * two TMEM accumulator stages (2 x 256 columns): pass 0 / pass 1 of a tile, so the epilogue of one pass overlaps the
 //     MMAs of the next; slot kb of the NEXT tile is loaded and transformed as soon as pass 1 has consumed it.
-//   * store_y: the transform warps also write the activated slot to HBM (TMA store) - the image pass keeps Y for the
-//     weight gradient of this layer; the no-grad solar pass does not.
+//   * store_y: the transform warps also write the activated values to HBM, straight from their registers (st.global, 16
+//     bytes per thread, a quarter warp = one whole 128-byte line; a TMA store would read the slot once more through the
+//     shared-memory pipe the tensor core and the TMA fills already saturate) - the image pass keeps Y for the weight
+//     gradient of this layer; the no-grad solar pass does not.
 //
 // Warps (640 threads, setmaxnreg moves registers from the data-movement warps to the epilogue):
 //   0 A producer | 1 MMA issuer (leader CTA) | 2 B producer | 3 idle | 4..11 transform | 12..19 epilogue
@@ -33,7 +35,7 @@
 // Barriers per CTA (leader = cluster rank 0):
 //   afull[kb]   each CTA   A slot landed (own TMA bytes)
 //   aready[kb]  leader     16 arrivals = transform warps of both CTAs (operand rewritten, fenced for the async proxy)
-//   aempty[kb]  each CTA   slot consumed by the last pass (commit multicast) [+ 1 arrival: Y store has read it]
+//   aempty[kb]  each CTA   slot consumed by the last pass (commit multicast)
 //   bfull[s]    leader     B bytes of both CTAs;   bempty[s] each CTA (commit multicast)
 //   tfull[a]    each CTA   accumulator complete;   tempty[a] leader, 16 arrivals = 8 epilogue warps x 2 CTAs
 #include <cstdlib>
@@ -76,7 +78,8 @@ struct Gemm3Params {
   float* stats;              // [2*N]
   const float* xa;           // [K]
   const float* xc;           // [K]
-  int store_y;
+  __nv_bfloat16* Y;          // activated operand out [M, K] (row pitch ldy) or nullptr
+  long long ldy;
   long long* dbg;            // timeline of CTA 0 (SNB_TC3_TIMELINE, scripts/tc3_timeline.py); nullptr in production
 };
 
@@ -94,7 +97,7 @@ template <int kRegs> __device__ __forceinline__ void reg_inc() { asm volatile("s
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k3Threads, 1)
 gemm3_xf_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
-                const __grid_constant__ CUtensorMap tmapC, const __grid_constant__ CUtensorMap tmapY, const Gemm3Params p) {
+                const __grid_constant__ CUtensorMap tmapC, const Gemm3Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -127,7 +130,7 @@ gemm3_xf_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
     for (int k = 0; k < k3MaxKB; ++k) {
       mbar_init(afull(k), 1);
       mbar_init(aready(k), 2 * k3XfWarps);
-      mbar_init(aempty(k), p.store_y ? 2 : 1);
+      mbar_init(aempty(k), 1);
     }
     for (int s = 0; s < k3BStages; ++s) {
       mbar_init(bfull(s), 1);
@@ -141,7 +144,6 @@ gemm3_xf_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
     tma_prefetch_desc(&tmapA);
     tma_prefetch_desc(&tmapB);
     tma_prefetch_desc(&tmapC);
-    if (p.store_y) tma_prefetch_desc(&tmapY);
   }
   for (int i = threadIdx.x; i < 2 * k3MaxStatN; i += k3Threads) stat_smem[i] = 0.f;
   for (int i = threadIdx.x; i < k3MaxStatN; i += k3Threads) bias_smem[i] = (p.bias && i < p.N) ? __ldg(p.bias + i) : 0.f;
@@ -275,21 +277,23 @@ gemm3_xf_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
                        "r"(w[i][2]), "r"(w[i][3])
                        : "memory");
         }
-        fence_proxy_async_smem();          // generic-proxy writes -> visible to the async proxy (tensor core, TMA store)
-        if (p.store_y) asm volatile("bar.sync 2, %0;" ::"n"(32 * k3XfWarps) : "memory");      // whole slot rewritten
+        fence_proxy_async_smem();          // generic-proxy writes -> visible to the async proxy (tensor core)
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(mapa_shared(aready(kb), 0));
         SNB_TL(it < kDbgTiles && tt == 0, 400 + (it * 8 + kb) * 2 + 1);
-        if (p.store_y && tt == 0) {
-          // the activated slot is the next layer's input matrix Y (needed by this layer's weight gradient): 128 x 64 tile
-          tma_store_2d(&tmapY, a_base + kb * k3SlotBytes, kb * k3BK, m0);
-          bulk_commit_group();
-          bulk_wait_group_read<0>();       // the store has read the slot: it may be reloaded once the MMAs are done too
-          mbar_arrive(aempty(kb));
+        if (p.Y != nullptr) {
+          // the activated slot is the next layer's input matrix Y (needed by this layer's weight gradient)
+          const long long row = (long long)m0 + r0;
+          __nv_bfloat16* dst = p.Y + row * p.ldy + kb * k3BK + 8 * j;
+#pragma unroll
+          for (int i = 0; i < kRI; ++i)
+            if (row + kRS * i < p.M)
+              asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(dst + (long long)(kRS * i) * p.ldy), "r"(w[i][0]), "r"(w[i][1]),
+                           "r"(w[i][2]), "r"(w[i][3])
+                           : "memory");
         }
       }
     }
-    if (p.store_y && tt == 0) bulk_wait_group<0>();
   } else {
     reg_inc<152>();
     // ================= epilogue: TMEM -> (alpha, bias) -> bf16 -> swizzled staging -> TMA store; column statistics =========
@@ -448,22 +452,17 @@ int snb_gemm_bf16_tc3(const void* Zprev, int lda, const float* xa, const float* 
   p.tiles_m = (int)((M + 2 * k3BM - 1) / (2 * k3BM));
   p.n_passes = N / 256;
   p.nkb = K / k3BK;
-  p.bias = bias, p.alpha = alpha, p.stats = stats, p.xa = xa, p.xc = xc, p.store_y = Y ? 1 : 0;
+  p.bias = bias, p.alpha = alpha, p.stats = stats, p.xa = xa, p.xc = xc;
+  p.Y = reinterpret_cast<__nv_bfloat16*>(Y), p.ldy = ldy;
   const char* tl = getenv("SNB_TC3_TIMELINE");      // device pointer (decimal) of >= 1024 int64: debugging only
   p.dbg = tl ? reinterpret_cast<long long*>(strtoull(tl, nullptr, 10)) : nullptr;
-  CUtensorMap ta, tb, tcm, ty;
+  CUtensorMap ta, tb, tcm;
   int rc = make_tmap_bf16(&ta, Zprev, M, K, lda, k3BK, k3BM);
   if (rc) return rc;
   rc = make_tmap_bf16(&tb, B, N, K, ldb, k3BK, 128);
   if (rc) return rc;
   rc = make_tmap_bf16(&tcm, C, M, N, ldc, 64, 32);
   if (rc) return rc;
-  if (Y) {
-    rc = make_tmap_bf16(&ty, Y, M, K, ldy, k3BK, k3BM);
-    if (rc) return rc;
-  } else {
-    ty = ta;
-  }
   const int num_pairs = num_sms() / 2;
   const int grid = 2 * (p.tiles_m < num_pairs ? p.tiles_m : num_pairs);
   static bool attr_set = false;
@@ -472,7 +471,7 @@ int snb_gemm_bf16_tc3(const void* Zprev, int lda, const float* xa, const float* 
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  gemm3_xf_kernel<<<grid, k3Threads, k3Smem, st>>>(ta, tb, tcm, ty, p);
+  gemm3_xf_kernel<<<grid, k3Threads, k3Smem, st>>>(ta, tb, tcm, p);
   count_launch();
   SNB_LAUNCH_CHECK();
   return SNB_OK;
