@@ -303,7 +303,7 @@ gemm3_xf_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
     const int ew = warp - (4 + k3XfWarps);
     const int eh = ew >> 2;                 // which half of the pass's 256 columns
     const uint32_t cbuf = c_base + (uint32_t)ew * k3CWarpBytes;
-    const int c_begin = eh * 128, c_end = c_begin + 128;
+    const int c_begin = eh * 128;
     float st_acc[2][2][4];       // [pass][64-column chunk][sum c0, sum c1, sumsq c0, sumsq c1]
 #pragma unroll
     for (int i = 0; i < 2; ++i)
