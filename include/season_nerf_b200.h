@@ -28,9 +28,6 @@ extern "C" {
 int snb_version(void);
 /* multiprocessor count of the current CUDA device (queried once per device): sizes every persistent grid */
 int snb_num_sms(void);
-/* Leave n SMs out of the persistent GEMM grids launched from now on (returns the previous value; 0 = none).  Used while a
- * chain of small kernels (the O(N) loss terms of Eval_Tools_2.py:370-443) runs on a second stream beside the GEMMs. */
-int snb_reserve_sms(int n);
 /* number of kernels this library has launched since load (bench.py "gpu_launches") */
 long long snb_launch_count(void);
 const char* snb_error_string(int code);

@@ -17,7 +17,6 @@ _p, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 SIGNATURES = {
     "snb_version": [],
     "snb_num_sms": [],
-    "snb_reserve_sms": [_i],
     "snb_launch_count": [],
     "snb_error_string": [_i],
     "snb_sample_rays": [_p, _p, _p, _i, _i, _i, _p, _p, _p],

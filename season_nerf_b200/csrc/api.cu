@@ -18,20 +18,8 @@ int num_sms() {
   }
   return n;
 }
-// SMs left free by the persistent GEMM grids (snb_reserve_sms): while a chain of small kernels runs on a second stream, a grid
-// of one CTA per SM would let it advance by one kernel per GEMM boundary only
-static std::atomic<int> g_reserved{0};
-int grid_sms() {
-  int n = num_sms() - g_reserved.load(std::memory_order_relaxed);
-  n &= ~1;                                  // CTA pairs
-  return n < 2 ? 2 : n;
-}
 }  // namespace snb
 
-extern "C" int snb_reserve_sms(int n) {
-  if (n < 0) n = 0;
-  return snb::g_reserved.exchange(n, std::memory_order_relaxed);
-}
 extern "C" int snb_version(void) { return 200; }
 extern "C" int snb_num_sms(void) { return snb::num_sms(); }
 extern "C" long long snb_launch_count(void) { return snb::g_launches.load(); }

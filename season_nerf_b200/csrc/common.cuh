@@ -24,7 +24,6 @@ namespace snb {
 // SM count of the current device, queried once per device (a full B200 has 148; a MIG slice or another SKU has fewer:
 // every persistent grid and split-K factor is sized from this, never from a compile-time constant)
 int num_sms();
-int grid_sms();      // num_sms() minus the SMs reserved through snb_reserve_sms (persistent GEMM grids)
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

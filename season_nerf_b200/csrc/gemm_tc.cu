@@ -306,7 +306,7 @@ int snb_gemm_bf16_tc(const void* A, int lda, int a_t, const void* B, int ldb, in
   if (rc) return rc;
 
   const int total = p.tiles_m * p.tiles_n * p.splits;
-  const int grid = total < grid_sms() ? total : grid_sms();
+  const int grid = total < num_sms() ? total : num_sms();
 #define SNB_LAUNCH_GEMM(AT, BT)                                                                             \
   do {                                                                                                      \
     static bool attr_set = false;                                                                           \

@@ -704,7 +704,7 @@ int snb_gemm_bf16_tc2(const void* A, int lda, int a_t, const void* B, int ldb, i
   p.block_n = N >= 192 ? 256 : 128;
   p.tiles_m = (int)((M + 2 * k2BM - 1) / (2 * k2BM));
   p.tiles_n = (N + p.block_n - 1) / p.block_n;
-  const int num_pairs = grid_sms() / 2;
+  const int num_pairs = num_sms() / 2;
   const int num_kb = (K + k2BK - 1) / k2BK;
   int splits = 1;
   if (accumulate == 2) {  // split-K for the (few output tiles, huge K) weight-gradient shape

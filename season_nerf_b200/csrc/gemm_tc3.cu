@@ -463,7 +463,7 @@ int snb_gemm_bf16_tc3(const void* Zprev, int lda, const float* xa, const float* 
   if (rc) return rc;
   rc = make_tmap_bf16(&tcm, C, M, N, ldc, 64, 32);
   if (rc) return rc;
-  const int num_pairs = grid_sms() / 2;
+  const int num_pairs = num_sms() / 2;
   const int grid = 2 * (p.tiles_m < num_pairs ? p.tiles_m : num_pairs);
   static bool attr_set = false;
   if (!attr_set) {

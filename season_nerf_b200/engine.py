@@ -23,9 +23,6 @@ FAST_LOSS = os.environ.get("SNB_FAST_LOSS", "1") != "0"
 # microseconds, forward and again in backward) are enqueued on a side stream while the solar pass - 3 ms of GEMMs that do not
 # depend on them - runs on the main one; inside the captured step graph this is a fork / join.  SNB_LOSS_OVERLAP=0 keeps one stream.
 LOSS_OVERLAP = os.environ.get("SNB_LOSS_OVERLAP", "1") != "0"
-# SMs the persistent GEMM grids of the solar pass (and of the backward sweep) leave to that side stream: with one CTA on
-# every SM the chain would advance by one small kernel per GEMM boundary
-LOSS_OVERLAP_SMS = int(os.environ.get("SNB_LOSS_OVERLAP_SMS", "2"))
 
 
 def _dev(x, device):
@@ -424,8 +421,7 @@ class All_in_One_Eval():
                     starts, ends, svec, stime = solar
                 sdict = {"Top": starts, "Bot": ends, "Sun_Angle": svec, "Time_Encoded": stime}
                 if fast:
-                    with ops.reserved_sms(LOSS_OVERLAP_SMS if img_terms is not None else 0):
-                        sol_fast = self._solar_fast(sdict, Network, train_mode, jitter=solar_jitter, ts=solar_ts)
+                    sol_fast = self._solar_fast(sdict, Network, train_mode, jitter=solar_jitter, ts=solar_ts)
                 elif overlap:
                     side = _nw.side_stream(("solar", main.cuda_stream))
                     side.wait_event(fork)
@@ -440,7 +436,6 @@ class All_in_One_Eval():
         finally:
             if overlap:
                 Network._bn_order = None
-        self.loss_overlapped = img_terms is not None
         if img_terms is not None:        # join: the main stream consumes the side stream's scalars from here on
             join[0].wait_stream(join[1])
             for v in img_terms.values():

@@ -553,23 +553,6 @@ def gemm_sine_bwd(dZn, W, G, Z, a, c, mean, invstd, alpha=1.0, stats=None):
     return s[0], s[1]
 
 
-class reserved_sms:
-    """with reserved_sms(n): the persistent GEMM grids launched inside leave n SMs free (for a chain of small kernels on a
-    second stream).  Grid sizes are fixed at launch - and baked into a CUDA graph at capture."""
-
-    def __init__(self, n):
-        self.n = int(n)
-
-    def __enter__(self):
-        self.prev = _lib.load().snb_reserve_sms(self.n) if self.n > 0 else None
-        return self
-
-    def __exit__(self, *exc):
-        if self.prev is not None:
-            _lib.load().snb_reserve_sms(self.prev)
-        return False
-
-
 def bn_bwd_apply(G, Z, a, mean, invstd, k1, k2, dZ, scale=1.0):
     """dZ = a*(G - scale*k1 - xhat*scale*k2) (may alias G); scale = 1/rows when k1, k2 are the raw column sums."""
     G, ldg = _mat(G, "G")

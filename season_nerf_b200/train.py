@@ -253,11 +253,7 @@ class TrainStep:
         total = 0
         for k in loss.keys():
             total = total + loss[k][0] * loss[k][1]
-        # the backward of the side-stream loss terms runs beside the backward of the solar pass: same reservation as in forward
-        from . import engine as _eng, ops as _ops
-        bw_sms = int(os.environ.get("SNB_LOSS_OVERLAP_BWD_SMS", str(_eng.LOSS_OVERLAP_SMS)))
-        with _ops.reserved_sms(bw_sms if getattr(self.eval_tool, "loss_overlapped", False) else 0):
-            (total * scale if scale != 1.0 else total).backward()
+        (total * scale if scale != 1.0 else total).backward()
         # the step has consumed the autograd graph: hand back plain values (a caller that kept graph-attached losses alive
         # would also keep this iteration's AccumulateGrad nodes alive, which breaks a later CUDA-graph capture)
         return {k: [v[0].detach() if isinstance(v[0], t.Tensor) else v[0], v[1]] for k, v in loss.items()}, total.detach()
