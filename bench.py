@@ -429,7 +429,7 @@ def run_ours(a):
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM): per-launch CUDA events on the launching stream --------------
     ev = []
-    gemm_entry = ("gemm", "gemm_stats", "gemm_sine_fwd", "gemm_sine_bwd")      # every tcgen05 GEMM entry point of ops.py
+    gemm_entry = ("gemm", "gemm_stats", "gemm_stats_xf", "gemm_sine_fwd", "gemm_sine_bwd")      # every tcgen05 GEMM entry point of ops.py
     orig = {k: getattr(ops, k) for k in gemm_entry}
 
     def _timed(fn):

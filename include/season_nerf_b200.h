@@ -236,6 +236,23 @@ int snb_solar_loss_fwd(const float* rho_raw, int ld_rho, const float* vis_raw, i
 int snb_solar_loss_bwd(const float* rho_raw, int ld_rho, const float* vis_raw, int ld_vis, const float* deltas, int N, int S,
                        const float* g_err, const float* g_abs, float* d_vis_raw, void* stream);
 
+/* The O(N) loss terms of one training step in one kernel each way (Eval_Tools_2.py:353-443, default configuration: Barron
+ * adaptive colour loss - lossfun / log-partition of season_nerf_b200/adaptive_loss.py -, solar correction terms, no prior):
+ * vals[0..10] = Color_ada, Color_alpha, Color_width, Color (mse), Solar_Correction, Solar_Correction_2, Sky_Color_Var,
+ * Albedo_Color, scale^2, sc_lambda / scale^2, weighted total; aux[0..14] = sums the backward kernel needs.  rendered, gt,
+ * albedo, sky [N,3]; err, absorb [N]; alpha, scale [3] (computed by the caller from the latent parameters); theta, qw [768]
+ * float64 Gauss-Legendre nodes / weights times pi/2. */
+int snb_loss_tail_fwd(const float* rendered, const float* gt, const float* albedo, const float* sky, const float* err,
+                      const float* absorb, const float* alpha, const float* scale, const double* theta, const double* qw,
+                      int N, float sc_lambda, int solar_type2, float* vals, float* aux, void* stream);
+/* Gradients of sum_k g_k * term_k + g_total * total (device scalars, null = 0) w.r.t. rendered, albedo, sky [N,3], err,
+ * absorb [N], alpha, scale [3]. */
+int snb_loss_tail_bwd(const float* rendered, const float* gt, const float* sky, const float* alpha, const float* scale,
+                      const float* aux, const float* vals, const float* g_color, const float* g_err, const float* g_abs,
+                      const float* g_sky, const float* g_alb, const float* g_total, int N, float sc_lambda, int solar_type2,
+                      float* d_rendered, float* d_albedo, float* d_sky, float* d_err, float* d_absorb, float* d_alpha,
+                      float* d_scale, void* stream);
+
 /* ---- fused eval-mode network (render): T_NeRF_net_v2.py:75-105,131-151,169-170 + G_NeRF.py:74-133 --------------
  * One persistent tcgen05 kernel runs encoding -> trunk -> sigma/colour heads -> solar branch -> adjust branch with the
  * activations kept in shared memory / TMEM: two CTAs of a cluster render a tile of 256 sample points with

@@ -9,7 +9,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libseason_nerf_b200.so")
-SOURCES = ["api.cu", "sampling.cu", "composite.cu", "heads.cu", "elementwise.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_tc3.cu", "fused_eval2.cu"]
+SOURCES = ["api.cu", "sampling.cu", "composite.cu", "heads.cu", "loss.cu", "elementwise.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_tc3.cu", "fused_eval2.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--extended-lambda",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
 
