@@ -205,7 +205,9 @@ __global__ void __launch_bounds__(kLossThreads, 1) loss_tail_fwd_kernel(const Lo
     p.vals[0] = color_ada, p.vals[1] = color_alpha, p.vals[2] = color_width, p.vals[3] = mse;
     p.vals[4] = err_m, p.vals[5] = abs_m, p.vals[6] = sky_l, p.vals[7] = alb_l, p.vals[8] = scale_sq, p.vals[9] = w_s;
     // Eval_Tools_2.py:399-400,427-428: only the two solar-correction weights are divided by the squared colour-loss scale
-    p.vals[10] = err_m * w_s + abs_m * w_s + sky_l * p.sc_lambda + alb_l * p.sc_lambda + color_ada + color_alpha + color_width + mse;
+    // (and the sky / albedo regularisers exist only without Solar_Type_2, :370)
+    p.vals[10] = err_m * w_s + abs_m * w_s + (p.solar_type2 ? 0.f : sky_l * p.sc_lambda + alb_l * p.sc_lambda) + color_ada + color_alpha +
+                 color_width + mse;
     for (int c = 0; c < 3; ++c) {
       p.aux[c] = (float)tot_da[c], p.aux[3 + c] = (float)tot_ds[c], p.aux[6 + c] = (float)s_dlogz[c];
       p.aux[9 + c] = mv[c], p.aux[12 + c] = __int_as_float(mi[c]);
@@ -246,8 +248,8 @@ __global__ void __launch_bounds__(256) loss_tail_bwd_kernel(const LossTailBwdPar
   const float m_color = (p.g_color ? __ldg(p.g_color) : 0.f) + gt_;
   const float m_err = (p.g_err ? __ldg(p.g_err) : 0.f) + gt_ * w_s;
   const float m_abs = p.solar_type2 ? ((p.g_abs ? __ldg(p.g_abs) : 0.f) + gt_ * w_s) : 0.f;
-  const float m_sky = (p.g_sky ? __ldg(p.g_sky) : 0.f) + gt_ * p.sc_lambda;
-  const float m_alb = (p.g_alb ? __ldg(p.g_alb) : 0.f) + gt_ * p.sc_lambda;
+  const float m_sky = (p.g_sky ? __ldg(p.g_sky) : 0.f) + (p.solar_type2 ? 0.f : gt_ * p.sc_lambda);
+  const float m_alb = (p.g_alb ? __ldg(p.g_alb) : 0.f) + (p.solar_type2 ? 0.f : gt_ * p.sc_lambda);
   const float invN = 1.f / (float)p.N, inv3N = 1.f / (float)(3 * p.N);
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n < p.N) {

@@ -13,6 +13,7 @@ import numpy as np
 import torch as t
 
 from . import ops
+from .adaptive_loss import AdaptiveLossFunction as _OwnAdaptiveLoss
 from .geometry import world_angle_2_local_vec
 
 # get_loss without the prior: head activations + compositing + the solar-pass sums run in fused kernels on the RAW heads
@@ -23,6 +24,9 @@ FAST_LOSS = os.environ.get("SNB_FAST_LOSS", "1") != "0"
 # microseconds, forward and again in backward) are enqueued on a side stream while the solar pass - 3 ms of GEMMs that do not
 # depend on them - runs on the main one; inside the captured step graph this is a fork / join.  SNB_LOSS_OVERLAP=0 keeps one stream.
 LOSS_OVERLAP = os.environ.get("SNB_LOSS_OVERLAP", "1") != "0"
+# One kernel each way for ALL the O(N) loss terms of the default configuration (Barron colour loss, solar terms, no prior,
+# one rank per BatchNorm batch): csrc/loss.cu.  SNB_FUSED_TAIL=0 keeps the torch arithmetic (parity tests compare the two).
+FUSED_TAIL = os.environ.get("SNB_FUSED_TAIL", "1") != "0"
 
 
 def _dev(x, device):
@@ -324,6 +328,13 @@ class All_in_One_Eval():
         return R
 
     # ---------------------------------------------------------------------------------------------------
+    def _fused_tail_usable(self, train_mode):
+        """the fused loss kernels cover the default configuration: Barron colour loss of THIS package (the quadrature buffers
+        and the latent parameterisation are read directly), solar terms on, no prior DSM, no cross-rank albedo minimum"""
+        a = self.args
+        return bool(FUSED_TAIL and a.Use_Solar and not self.use_prior and self.use_MSE_loss is not True and self.sync_world == 1
+                    and isinstance(self.ada_loss, _OwnAdaptiveLoss) and self.ada_loss.latent_alpha.shape[-1] == 3)
+
     def _image_terms(self, out, gt, train_mode):
         """the terms of get_loss that read the image pass only (Eval_Tools_2.py:370-443), keyed for get_loss's assembly:
         regularisers Sky_Color_Var / Albedo_Color (:370-390), colour terms (:401-443), `scale` = mean colour-loss scale ** 2"""
@@ -397,10 +408,13 @@ class All_in_One_Eval():
         fast = (FAST_LOSS and not self.use_prior and not overlap and hasattr(Network, "forward_rays")
                 and ops.heads_composite_usable(args.n_samples, getattr(Network, "n_classes", 99)))
         sol = sol_fast = img_terms = None
+        fused_tail = False
+        self._fused_total = None
         try:
             if fast:
                 out = self._eval_fast(data_dict, Network, train_mode, jitter=jitter, ts=ts)
-                if LOSS_OVERLAP and train_mode and args.Use_Solar and n_rays >= 64:
+                fused_tail = self._fused_tail_usable(train_mode)
+                if LOSS_OVERLAP and train_mode and args.Use_Solar and n_rays >= 64 and not fused_tail:
                     gt = _dev(data_dict["GT_Color"], device)
                     main_s = t.cuda.current_stream()
                     side_s = _nw.side_stream(("loss", main_s.cuda_stream))
@@ -441,6 +455,23 @@ class All_in_One_Eval():
             for v in img_terms.values():
                 v.record_stream(join[0])
         gt = _dev(data_dict["GT_Color"], device)
+        if fused_tail and sol_fast is not None:
+            # every O(N) term, its weight and the weighted total in ONE kernel (and one for all their gradients)
+            a0 = self.ada_loss
+            T = ops.loss_tail(out["Rendered_Col"], gt, out["Albedo_Color"], out["Sky_Col"], sol_fast[0], sol_fast[1], a0.alpha(),
+                              a0.scale(), a0._th, a0._w, args.sc_lambda, bool(args.Solar_Type_2))
+            Loss["Solar_Correction"] = [T["Solar_Correction"], T["solar_weight"]]
+            Loss["Solar_Correction_2"] = [T["Solar_Correction_2"] if args.Solar_Type_2 else T["Solar_Correction_2"].detach(),
+                                          T["solar_weight"]]
+            if args.Solar_Type_2 is False:
+                Loss["Sky_Color_Var"] = [T["Sky_Color_Var"], weight["Solar_Correction"]]
+                Loss["Albedo_Color"] = [T["Albedo_Color"], weight["Solar_Correction"]]
+            Loss["Color_ada"] = [T["Color_ada"], weight["Color"]]
+            Loss["Color_alpha"] = [T["Color_alpha"], 1.]
+            Loss["Color_width"] = [T["Color_width"], 1.]
+            Loss["Color"] = [T["Color"], weight["Color"]]
+            self._fused_total = T["total"]       # = sum of term * weight over the dictionary (train.TrainStep back-propagates it)
+            return Loss
         img_terms = self._image_terms(out, gt, train_mode) if img_terms is None else img_terms
         if args.Use_Solar:
             if sol_fast is not None:

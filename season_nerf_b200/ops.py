@@ -313,6 +313,57 @@ def solar_loss(rho_raw, vis_raw, deltas):
     return _SolarLoss.apply(rho_raw, vis_raw, deltas)
 
 
+class _LossTail(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rendered, gt, albedo, sky, err, absorb, alpha, scale, theta, qw, sc_lambda, type2):
+        N = rendered.shape[0]
+        f = lambda x: _cuda(x, torch.float32, "loss input").contiguous()
+        rendered, gt, albedo, sky, err, absorb = f(rendered), f(gt), f(albedo), f(sky), f(err).reshape(-1), f(absorb).reshape(-1)
+        a3, s3 = f(alpha).reshape(-1), f(scale).reshape(-1)
+        if tuple(rendered.shape) != (N, 3) or tuple(gt.shape) != (N, 3) or tuple(albedo.shape) != (N, 3) or tuple(sky.shape) != (N, 3) \
+                or err.shape[0] != N or absorb.shape[0] != N or a3.shape[0] != 3 or s3.shape[0] != 3:
+            raise ValueError("loss_tail: rendered / gt / albedo / sky must be [N,3], err / absorb [N], alpha / scale 3 values")
+        theta, qw = _cuda(theta, torch.float64, "theta").contiguous(), _cuda(qw, torch.float64, "qw").contiguous()
+        if theta.shape[0] != 768 or qw.shape[0] != 768:
+            raise ValueError("loss_tail: the quadrature rule has 768 nodes")
+        buf = torch.empty(48, device=rendered.device, dtype=torch.float32)
+        vals, aux = buf[:16], buf[16:]
+        check(_lib.load().snb_loss_tail_fwd(_ptr(rendered), _ptr(gt), _ptr(albedo), _ptr(sky), _ptr(err), _ptr(absorb), _ptr(a3), _ptr(s3),
+                                            _ptr(theta), _ptr(qw), N, float(sc_lambda), int(bool(type2)), _ptr(vals), _ptr(aux), _stream()))
+        ctx.save_for_backward(rendered, gt, sky, a3, s3, buf)
+        ctx.meta = (N, float(sc_lambda), int(bool(type2)), tuple(alpha.shape), tuple(scale.shape))
+        ctx.set_materialize_grads(False)
+        v = vals.unbind(0)
+        # differentiable: Color_ada, Solar_Correction, Solar_Correction_2, Sky_Color_Var, Albedo_Color, total
+        nd = (v[1], v[2], v[3], v[8], v[9])
+        ctx.mark_non_differentiable(*nd)
+        return (v[0], v[4], v[5], v[6], v[7], v[10]) + nd
+
+    @staticmethod
+    def backward(ctx, g_color, g_err, g_abs, g_sky, g_alb, g_total, *unused):
+        rendered, gt, sky, a3, s3, buf = ctx.saved_tensors
+        N, sc_lambda, type2, a_shape, s_shape = ctx.meta
+        out = torch.empty(11 * N + 6, device=rendered.device, dtype=torch.float32)
+        d_r, d_a, d_s = out[:3 * N].view(N, 3), out[3 * N:6 * N].view(N, 3), out[6 * N:9 * N].view(N, 3)
+        d_e, d_b, d_al, d_sc = out[9 * N:10 * N], out[10 * N:11 * N], out[11 * N:11 * N + 3], out[11 * N + 3:]
+        g = [None if x is None else x.float().contiguous() for x in (g_color, g_err, g_abs, g_sky, g_alb, g_total)]
+        check(_lib.load().snb_loss_tail_bwd(_ptr(rendered), _ptr(gt), _ptr(sky), _ptr(a3), _ptr(s3), _ptr(buf[16:]), _ptr(buf[:16]),
+                                            *[_ptr(x) for x in g], N, sc_lambda, type2, _ptr(d_r), _ptr(d_a), _ptr(d_s), _ptr(d_e),
+                                            _ptr(d_b), _ptr(d_al), _ptr(d_sc), _stream()))
+        return d_r, None, d_a, d_s, d_e, d_b, d_al.view(a_shape), d_sc.view(s_shape), None, None, None, None
+
+
+def loss_tail(rendered, gt, albedo, sky, err, absorb, alpha, scale, theta, qw, sc_lambda, solar_type2=False):
+    """The O(N) loss terms of a training step (Eval_Tools_2.py:353-443, Barron colour loss, no prior) in one kernel each way.
+    -> dict of 0-dim tensors: Color_ada, Solar_Correction, Solar_Correction_2, Sky_Color_Var, Albedo_Color, total
+    (differentiable w.r.t. rendered, albedo, sky, err, absorb, alpha, scale), Color_alpha, Color_width, Color (mse), scale_sq,
+    solar_weight = sc_lambda / scale_sq (values only)."""
+    o = _LossTail.apply(rendered, gt, albedo, sky, err, absorb, alpha, scale, theta, qw, float(sc_lambda), bool(solar_type2))
+    keys = ("Color_ada", "Solar_Correction", "Solar_Correction_2", "Sky_Color_Var", "Albedo_Color", "total", "Color_alpha",
+            "Color_width", "Color", "scale_sq", "solar_weight")
+    return dict(zip(keys, o))
+
+
 def cli_composite(rho, deltas, base, vis, adj, cls, exact_vis=None):
     """mg_Img_Eval.py:123-190 sums in float64.  Inputs f32 or f64 device tensors; cls [C] f64."""
     N, S = rho.shape[0], rho.shape[1]

@@ -250,9 +250,12 @@ class TrainStep:
     def _fwd_bwd(self, batch, current_step, scale, **kw):
         """loss of one (micro-)batch and its backward; gradients accumulate into .grad (scale = 1 / number of chunks)"""
         loss = self.eval_tool.get_loss(batch, self.network, current_step, train_mode=True, **kw)
-        total = 0
-        for k in loss.keys():
-            total = total + loss[k][0] * loss[k][1]
+        total = getattr(self.eval_tool, "_fused_total", None)        # the weighted sum, already formed by the loss kernel
+        self.eval_tool._fused_total = None
+        if total is None:
+            total = 0
+            for k in loss.keys():
+                total = total + loss[k][0] * loss[k][1]
         (total * scale if scale != 1.0 else total).backward()
         # the step has consumed the autograd graph: hand back plain values (a caller that kept graph-attached losses alive
         # would also keep this iteration's AccumulateGrad nodes alive, which breaks a later CUDA-graph capture)
