@@ -118,8 +118,10 @@ class create_solor_rays_uniform():
         device = t.device(device)
         sc = self.__dict__.get("_dev_scale")
         if sc is None or sc[0] != device:
-            sc = self._dev_scale = (device, t.tensor([[360., 89.]], dtype=t.float64, device=device),
-                                    t.tensor([[-180., 1.]], dtype=t.float64, device=device))
+            # built from scalar fills: no host->device copy, so the first call may happen inside a CUDA-graph capture
+            mul, add = t.empty(1, 2, dtype=t.float64, device=device), t.empty(1, 2, dtype=t.float64, device=device)
+            mul[:, 0].fill_(360.), mul[:, 1].fill_(89.), add[:, 0].fill_(-180.), add[:, 1].fill_(1.)
+            sc = self._dev_scale = (device, mul, add)
         az_el = t.rand(n, 2, dtype=t.float64, device=device, generator=generator).mul_(sc[1]).add_(sc[2])
         u_xy = t.rand(n, 2, device=device, generator=generator)
         u_t = t.rand(n, 2, device=device, generator=generator) if include_times else None

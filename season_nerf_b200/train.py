@@ -208,13 +208,13 @@ class TrainStep:
     # ---- one step -----------------------------------------------------------------------------------------
     _BATCH_KEYS = ("Top", "Bot", "Sun_Angle", "Time_Encoded", "GT_Color")
 
-    def _draw_inputs(self, n, inject):
+    def _draw_inputs(self, n, inject, solar_in_graph=False):
         """host-side random draws of one step, in the reference's order (Eval_Tools_2.py:165-170 jitter, :350 solar rays,
         :300-301 solar jitter) -> ts_img [S], solar 4-tuple, ts_solar [S] (CPU tensors unless injected on the device)."""
         S = self.args.n_samples
         ts_img = sample_ts(S, False, False, inject.get("jitter"))
         solar = inject.get("solar")
-        if solar is None and self.args.Use_Solar:
+        if solar is None and self.args.Use_Solar and not solar_in_graph:
             if self.solar_rng == "device":
                 solar = self.eval_tool.solar_creation_tool.on_device(n, self.device, include_times=True)
             else:
@@ -244,8 +244,9 @@ class TrainStep:
         st["ts_img"].copy_(ts_img, non_blocking=True)
         if st["solar"] is not None:
             st["ts_sol"].copy_(ts_sol, non_blocking=True)
-            for d, s_ in zip(st["solar"], solar):
-                d.copy_(s_[lo:hi], non_blocking=True)
+            if solar is not None:            # None: the graph draws its own solar rays on the device
+                for d, s_ in zip(st["solar"], solar):
+                    d.copy_(s_[lo:hi], non_blocking=True)
 
     def _fwd_bwd(self, batch, current_step, scale, **kw):
         """loss of one (micro-)batch and its backward; gradients accumulate into .grad (scale = 1 / number of chunks)"""
@@ -291,10 +292,14 @@ class TrainStep:
         chunks = self._chunks(n)
         k = len(chunks)
         mb = chunks[0][1] - chunks[0][0]
-        ts_img, solar, ts_sol = self._draw_inputs(n, inject)
-        st = self._graphs.get((n, mb))
+        # device-drawn solar rays are drawn INSIDE the graph (torch's CUDA generator is graph-safe: every replay continues the
+        # stream): the eager draw + 4 copies into static buffers in front of every replay cost 0.15 ms of host time while the
+        # GPU idled.  Injected rays (tests, the device-timed bench loop) keep their static buffers - a graph of its own.
+        solar_in_graph = bool(self.args.Use_Solar and self.solar_rng == "device" and inject.get("solar") is None)
+        ts_img, solar, ts_sol = self._draw_inputs(n, inject, solar_in_graph)
+        st = self._graphs.get((n, mb, solar_in_graph))
         if st is None:
-            st = self._graphs[(n, mb)] = self._static(data_dict, mb)
+            st = self._graphs[(n, mb, solar_in_graph)] = self._static(data_dict, mb)
         if self.use_prior:
             if getattr(self.eval_tool, "trust_tensor", None) is None:
                 self.eval_tool.trust_tensor = t.zeros((), device=self.device, dtype=t.float32)
@@ -315,7 +320,8 @@ class TrainStep:
             from . import network as _nw
             _nw._capture_epoch[0] += 1          # weights staged by earlier passes / captures are not reused inside this one
             with t.cuda.graph(g_fb):
-                st["loss"], st["total"] = self._fwd_bwd(st["batch"], current_step, 1.0 / k, solar=st["solar"],
+                st["loss"], st["total"] = self._fwd_bwd(st["batch"], current_step, 1.0 / k,
+                                                        solar=None if solar_in_graph else st["solar"],
                                                         ts=st["ts_img"], solar_ts=st["ts_sol"])
                 if fused_opt:
                     if self.world_size > 1:
