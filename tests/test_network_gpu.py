@@ -464,3 +464,51 @@ def test_volume_consumers_golden(params0, precision):
         assert abs(conf_stats[0] - float(g["conf_mean"])) < 1e-6 and abs(conf_stats[1] - float(g["conf_median"])) < 1e-6
     else:       # one sample of a 96-sample column is 0.73 m of the 70 m range
         assert abs(conf_stats[0] - float(g["conf_mean"])) < 1.5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("type2", [False, True])
+def test_get_loss_fused_tail_equals_torch_terms(params0, type2):
+    """get_loss with the fused loss kernels (csrc/loss.cu, the default) against get_loss with the torch arithmetic
+    (engine.FUSED_TAIL = False) on the fp32 validation build: same dictionary (keys, order, terms, weights), same gradients
+    of the network and of the adaptive-loss parameters; and a caller that sums term * weight itself - the reference's
+    train_step (mg_run_NeRF.py:299-318) - gets the gradient of the fused total"""
+    import season_nerf_b200 as snb
+    from season_nerf_b200 import engine
+    from oracle import season_oracle as so
+    from gpu_util import make_net
+    args = so.default_args()
+    args.Solar_Type_2 = type2
+    n = 256
+    batch = so.synthetic_batch(n, seed=2)
+    st, en, vec, tm, _ = so.create_solar_rays_uniform(n, so.OMA_W2C, so.oma_w2l_h(), np.random.RandomState(5), t.Generator().manual_seed(5))
+    jit = t.rand(96, generator=t.Generator().manual_seed(6))
+    res = {}
+    for fused in (True, False):
+        engine.FUSED_TAIL = fused
+        try:
+            net = make_net(params0, "fp32", train=True)
+            ada = snb.AdaptiveLossFunction(3, t.float32, "cuda", alpha_hi=2.99, alpha_init=1.8, scale_init=0.03, scale_lo=0.01)
+            tool = snb.All_in_One_Eval(args, t.device("cuda"), 100, False, ada, so.oma_w2l_h(), so.OMA_W2C)
+            L = tool.get_loss(batch, net, 30, True, jitter=jit, solar=(st, en, vec, tm), solar_jitter=jit)
+            assert (tool._fused_total is not None) == fused
+            fused_total = tool._fused_total
+            tot = sum(L[k][0] * L[k][1] for k in L)
+            if fused:
+                assert abs(float(fused_total) - float(tot)) <= 1e-6 * abs(float(tot))
+            tot.backward()
+            res[fused] = ([(k, float(v[0]), float(v[1])) for k, v in L.items()],
+                          {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None},
+                          (ada.latent_alpha.grad.clone(), ada.latent_scale.grad.clone()))
+        finally:
+            engine.FUSED_TAIL = True
+    (la, ga, aa), (lb, gb, ab) = res[True], res[False]
+    assert [k for k, _, _ in la] == [k for k, _, _ in lb]
+    for (k, v1, w1), (_, v0, w0) in zip(la, lb):
+        assert abs(v1 - v0) <= 5e-6 * max(abs(v0), 1e-3) and abs(w1 - w0) <= 1e-6 * abs(w0), (k, v1, v0, w1, w0)
+    assert set(ga) == set(gb)
+    scale = max(float(g.norm()) for g in gb.values())
+    for k in gb:
+        assert float((ga[k] - gb[k]).norm()) <= 2e-5 * float(gb[k].norm()) + 1e-7 * scale, k
+    for x, y in zip(aa, ab):
+        assert float((x - y).abs().max()) <= 5e-5 * float(y.abs().max()) + 1e-9
