@@ -1,5 +1,5 @@
 #!/bin/bash
-# r02 closing set on one GPU: GPU suite, smoke, default bench + reference arm, step table of the graph replay, ncu launch list
+# Closing set of a round on one GPU (run under gpurun): GPU suite, smoke, default bench + reference arm, step table of the graph replay, ncu launch list
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -25 > gpurun_out/r02_pytest10.log
 grep -E "passed|failed|FAILED|^E  " gpurun_out/r02_pytest10.log | cut -c1-300
