@@ -194,6 +194,11 @@ int snb_sine_bwd_apply(const void* dY, int ldd, const void* Z, int ldz, const fl
                        const float* mean, const float* invstd, const float* k1, const float* k2, void* dZ, int ldo,
                        long long M, int N, int dtype, void* stream);
 
+/* fp32 -> bf16 staging of n_seg <= 48 weight matrices in one launch (host arrays of device pointers / shapes / row pitches):
+ * the bf16 operand copies of every nn.Linear a training pass uses (misc.py:148-194, G_NeRF.py, T_NeRF_net_v2.py). */
+int snb_stage_weights(const void* const* src, void* const* dst, const int* rows, const int* cols, const int* lds,
+                      const int* ldd, int n_seg, void* stream);
+
 /* dtype conversion with leading dimensions (f32 <-> bf16), used to stage operands */
 int snb_convert(const void* src, int src_dtype, int lds, void* dst, int dst_dtype, int ldd, long long M, int N,
                 void* stream);

@@ -44,6 +44,7 @@ SIGNATURES = {
     "snb_gemm_sine_fwd": [_p, _i, _p, _i, _p, _i, _p, _i, _p, _f, _ll, _i, _i, _p],
     "snb_loss_tail_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _f, _i, _p, _p, _p],
     "snb_loss_tail_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _f, _i, _p, _p, _p, _p, _p, _p, _p, _p],
+    "snb_stage_weights": [_p, _p, _p, _p, _p, _p, _i, _p],
     "snb_gemm_sine_bwd": [_p, _i, _p, _i, _p, _i, _p, _i, _p, _p, _p, _p, _f, _ll, _i, _i, _p, _p],
     "snb_bn_bwd_apply": [_p, _i, _p, _i, _p, _p, _p, _p, _p, _f, _p, _i, _ll, _i, _i, _p],
     "snb_bn_finalize": [_p, _p, _i, _ll, _i, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p],

@@ -643,6 +643,44 @@ extern "C" int snb_bn_finalize(const void* sum, const void* sumsq, int stats_dty
   return SNB_OK;
 }
 
+// fp32 -> bf16 staging of up to kStageMaxSeg weight matrices in ONE launch (the bf16 copies every layer's GEMMs read): the
+// segment descriptors travel in the kernel parameters, blockIdx.y = segment
+namespace snb {
+constexpr int kStageMaxSeg = 48;
+struct StageArgs {
+  const float* src[kStageMaxSeg];
+  __nv_bfloat16* dst[kStageMaxSeg];
+  int rows[kStageMaxSeg], cols[kStageMaxSeg], lds[kStageMaxSeg], ldd[kStageMaxSeg];
+};
+__global__ void __launch_bounds__(256) stage_weights_kernel(const __grid_constant__ StageArgs a) {
+  const int sg = blockIdx.y;
+  const float* __restrict__ src = a.src[sg];
+  __nv_bfloat16* __restrict__ dst = a.dst[sg];
+  const int N = a.cols[sg], lds = a.lds[sg], ldd = a.ldd[sg];
+  const int total = a.rows[sg] * N;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int m = i / N, col = i - m * N;
+    dst[(long long)m * ldd + col] = __float2bfloat16_rn(src[(long long)m * lds + col]);
+  }
+}
+}  // namespace snb
+
+extern "C" int snb_stage_weights(const void* const* src, void* const* dst, const int* rows, const int* cols, const int* lds,
+                                 const int* ldd, int n_seg, void* stream) {
+  SNB_CHECK_ARG(src && dst && rows && cols && lds && ldd && n_seg >= 0 && n_seg <= snb::kStageMaxSeg);
+  if (n_seg == 0) return SNB_OK;
+  snb::StageArgs a;
+  for (int i = 0; i < n_seg; ++i) {
+    SNB_CHECK_ARG(src[i] && dst[i] && rows[i] > 0 && cols[i] > 0 && lds[i] >= cols[i] && ldd[i] >= cols[i]);
+    a.src[i] = (const float*)src[i], a.dst[i] = (__nv_bfloat16*)dst[i];
+    a.rows[i] = rows[i], a.cols[i] = cols[i], a.lds[i] = lds[i], a.ldd[i] = ldd[i];
+  }
+  snb::stage_weights_kernel<<<dim3(8, n_seg), 256, 0, (cudaStream_t)stream>>>(a);
+  snb::count_launch();
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
 extern "C" int snb_convert(const void* src, int src_dtype, int lds, void* dst, int dst_dtype, int ldd, long long M, int N,
                            void* stream) {
   SNB_CHECK_ARG(src && dst && M >= 0 && N > 0 && lds >= N && ldd >= N);

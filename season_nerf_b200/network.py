@@ -35,6 +35,7 @@ XFORM = _os.environ.get("SNB_XFORM", "1") != "0"
 XFORM_GRAD = _os.environ.get("SNB_XFORM_GRAD", "1") != "0"        # also in passes with a backward (activated operand written back)
 _side_streams = {}
 _consts = {}
+BULK_STAGE = _os.environ.get("SNB_BULK_STAGE", "1") != "0"      # one launch for the bf16 copies of all weights of a pass
 _capture_epoch = [0]        # bumped by train.TrainStep before every CUDA-graph capture (see _Pass._wc)
 
 
@@ -463,6 +464,14 @@ class _Pass:
         # the same capture (solar pass after the image pass) reuse what that capture staged
         if hit is not None and hit[0] == key and (not capturing or hit[3] == _capture_epoch[0]):
             return hit[1], hit[2]
+        if BULK_STAGE and self.dt == t.bfloat16 and self.mode in ("full", "solar") and not self.__dict__.get("_bulk_done"):
+            # first stale layer of a training pass: stage EVERY layer of the pass in one launch (29 per-layer converts, their
+            # zero fills and concatenations were 0.15 ms of a step)
+            self._bulk_done = True
+            self._bulk_stage()
+            hit = spec.lin[0].__dict__.get("_snb_wc")
+            if hit is not None and hit[0] == key:
+                return hit[1], hit[2]
         W = t.cat([l.weight for l in spec.lin], 0) if len(spec.lin) > 1 else spec.lin[0].weight
         if spec.kp == W.shape[1]:
             Wc = t.empty(W.shape[0], spec.kp, device=W.device, dtype=self.dt)
@@ -473,6 +482,35 @@ class _Pass:
         b = b.detach().float().contiguous()
         spec.lin[0].__dict__["_snb_wc"] = (key, Wc, b, _capture_epoch[0] if capturing else None)
         return Wc, b
+
+    def _bulk_stage(self):
+        """bf16 copies of the weights of every stale layer of this pass: ONE zero-filled flat buffer (K padding), ONE kernel.
+        Fresh storage per staging, like the per-layer path: a backward pass still holds the copies it saved."""
+        capturing = t.cuda.is_current_stream_capturing()
+        todo, total = [], 0
+        for sp in self.specs:
+            key = (tuple((l.weight._version, l.bias._version, l.weight.data_ptr()) for l in sp.lin), self.dt, sp.kp)
+            hit = sp.lin[0].__dict__.get("_snb_wc")
+            if hit is not None and hit[0] == key and (not capturing or hit[3] == _capture_epoch[0]):
+                continue
+            if any(l.weight.dtype != t.float32 or not l.weight.is_contiguous() for l in sp.lin):
+                continue                                  # the per-layer path handles it
+            todo.append((sp, key, total))
+            total += sp.n_out * sp.kp
+        if not todo:
+            return
+        flat = t.zeros(total, device=todo[0][0].lin[0].weight.device, dtype=self.dt)
+        pairs = []
+        for sp, key, off in todo:
+            Wc = flat[off:off + sp.n_out * sp.kp].view(sp.n_out, sp.kp)
+            r0 = 0
+            for l in sp.lin:
+                pairs.append((l.weight.detach(), Wc[r0:r0 + l.out_features, :l.in_features]))
+                r0 += l.out_features
+            b = t.cat([l.bias for l in sp.lin], 0) if len(sp.lin) > 1 else sp.lin[0].bias
+            b = b.detach().float().contiguous()
+            sp.lin[0].__dict__["_snb_wc"] = (key, Wc, b, _capture_epoch[0] if capturing else None)
+        ops.stage_weights(pairs)
 
     def _buf(self, name, rows, width, dtype=None, zero=False):
         if name not in self.bufs:

@@ -662,6 +662,24 @@ def sine_bwd_apply(dY, Z, a, c, dZ, mean=None, invstd=None, k1=None, k2=None):
     return dZ
 
 
+def stage_weights(pairs):
+    """[(src fp32 [r, c] (row pitch = stride(0)), dst bf16 [r, c] view)] -> all copies in ONE launch (csrc/elementwise.cu)"""
+    n = len(pairs)
+    if n == 0:
+        return
+    if n > 48:
+        stage_weights(pairs[:48])
+        return stage_weights(pairs[48:])
+    for s_, d_ in pairs:
+        if not (s_.is_cuda and d_.is_cuda and s_.dtype == torch.float32 and d_.dtype == torch.bfloat16 and s_.dim() == 2
+                and tuple(s_.shape) == tuple(d_.shape) and s_.stride(1) == 1 and d_.stride(1) == 1):
+            raise ValueError("stage_weights: pairs of fp32 source / bf16 destination matrices of equal shape, unit column stride")
+    P, I = C.c_void_p * n, C.c_int * n
+    check(_lib.load().snb_stage_weights(P(*[s_.data_ptr() for s_, _ in pairs]), P(*[d_.data_ptr() for _, d_ in pairs]),
+                                        I(*[s_.shape[0] for s_, _ in pairs]), I(*[s_.shape[1] for s_, _ in pairs]),
+                                        I(*[s_.stride(0) for s_, _ in pairs]), I(*[d_.stride(0) for _, d_ in pairs]), n, _stream()))
+
+
 def convert(src, dst):
     src, lds = _mat(src, "src")
     dst, ldd = _mat(dst, "dst")
