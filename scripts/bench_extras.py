@@ -72,8 +72,18 @@ def bench_composite(dev, hbm_peak, peak_source, N=1 << 20, reps=5):
     b_fwd = S * 4 * 6 + 12 + 12 + 12 + 4
     # backward: the same inputs again + d_rendered [3]; d_rho [S], d_col [S,3], d_sky [3] out
     b_bwd = S * 4 * 6 + 12 + 12 + S * 4 * 4 + 12
+    def _traffic(key):
+        # dram bytes of one launch at 1 Mi rays from the ncu --set full capture (profiles/r02_ncu_traffic.json); null at other sizes
+        try:
+            import json
+            d = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r02_ncu_traffic.json")))
+            return d[key]["dram_bytes"] if N == 1 << 20 else None
+        except Exception:
+            return None
+
     mk = lambda ms, b, name: {"bound": "hbm", "kernel": name, "achieved": N * b / (ms * 1e-3) / 1e9, "peak": hbm_peak,
-                              "unit": "GB/s", "frac": N * b / (ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                              "unit": "GB/s", "frac": N * b / (ms * 1e-3) / 1e9 / hbm_peak,
+                              "traffic": _traffic("composite_fwd" if "fwd" in name else "composite_bwd"),
                               "bytes_per_ray": b, "rays": N, "ms_per_launch": ms, "rays_per_s": N / (ms * 1e-3),
                               "peak_source": peak_source}
     return {"fwd": mk(ms_f, b_fwd, "composite_fwd_kernel<false,false>"), "bwd": mk(ms_b, b_bwd, "composite_bwd_kernel<false,false,3>")}
