@@ -35,3 +35,5 @@ for it in range(12):
     print("  mma: operands landed    :", [rel(200 + it * 24 + kb * 3) for kb in range(7)])
     print("  mma: issued             :", [rel(200 + it * 24 + kb * 3 + 1) for kb in range(7)])
     print("  epilogue warp 0: accumulator complete %d  done %d" % (rel(600 + it * 2), rel(600 + it * 2 + 1)))
+    print("  epilogue done per warp, CTA 0:", [rel(700 + (it * 2) * 8 + w) for w in range(8)], " CTA 1 (its own clock):",
+          [d[700 + (it * 2 + 1) * 8 + w] - t0 if d[700 + (it * 2 + 1) * 8 + w] else -1 for w in range(8)])

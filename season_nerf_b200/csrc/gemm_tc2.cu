@@ -636,6 +636,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
       SNB_TL2(ite < kDbg2Items && ew == 0 && lane == 0, 600 + ite * 2 + 1);
+      if (p.dbg != nullptr && blockIdx.x < 2 && ite < kDbg2Items && lane == 0) p.dbg[700 + (ite * 2 + blockIdx.x) * 8 + ew] = clock64();
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
