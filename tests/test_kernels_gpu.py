@@ -678,3 +678,28 @@ def test_loss_tail_matches_torch_autograd(alpha_init, type2):
     assert float((L["rendered"].grad - g0["rendered"]).abs().max()) <= 5e-6 * float(g0["rendered"].abs().max())
     assert float((L["err"].grad - g0["err"]).abs().max()) <= 5e-6 * float(g0["err"].abs().max())
     assert L["sky"].grad is None or float(L["sky"].grad.abs().max()) == 0.0
+
+
+@pytest.mark.gpu
+def test_stage_weights_equals_per_matrix_convert():
+    """snb_stage_weights (one launch, segment descriptors in the kernel parameters) == snb_convert per matrix: padded
+    destinations (K -> kp zero columns stay untouched), row-offset destinations of concatenated heads, more than 48 segments"""
+    from season_nerf_b200 import ops
+    g = t.Generator(device="cuda").manual_seed(9)
+    shapes = [(512, 63), (512, 512), (512, 575), (256, 283), (1, 256), (3, 256), (12, 512)] * 8          # 56 segments
+    pairs, refs = [], []
+    for r, c in shapes:
+        src = t.randn(r, c, device="cuda", generator=g)
+        kp = (c + 7) // 8 * 8
+        big = t.zeros(r + 5, kp, device="cuda", dtype=t.bfloat16)
+        dst = big[2:2 + r, :c]                      # a row-offset, column-padded view like a concatenated, K-padded head
+        ref = t.zeros(r, c, device="cuda", dtype=t.bfloat16)
+        ops.convert(src, ref)
+        pairs.append((src, dst))
+        refs.append((big, ref, r, c))
+    ops.stage_weights(pairs)
+    for big, ref, r, c in refs:
+        assert t.equal(big[2:2 + r, :c], ref)
+        assert float(big[:2].abs().max()) == 0.0 and float(big[2 + r:].abs().max()) == 0.0 and float(big[:, c:].abs().max() if big.shape[1] > c else 0.0) == 0.0
+    with pytest.raises(ValueError):
+        ops.stage_weights([(t.zeros(4, 4, device="cuda"), t.zeros(4, 5, device="cuda", dtype=t.bfloat16))])
